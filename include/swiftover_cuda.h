@@ -1,0 +1,202 @@
+/*
+ * swiftover_cuda.h — C ABI of libswiftover_cuda.so, the B200 (sm_100a) engine
+ * for swiftover's liftover hot path.
+ *
+ * The seam it replaces is `struct ChainFile` of the reference
+ * (/root/reference/source/swiftover/chain.d:485-714) together with the
+ * per-record loop bodies that call it (bed.d:113-202, vcf.d:115-169).  The
+ * reference interface is one record per call; this one is batched: the host
+ * (D via extern(C), or the bundled C++ host) hands over whole buffers.
+ *
+ * Conventions
+ *   - every function returns SWO_OK (0) or a negative swo_status; the message
+ *     is available from swo_last_error().  Nothing throws, nothing exits.
+ *   - inputs are borrowed for the duration of the call only.
+ *   - host outputs live in library-owned PINNED host memory that stays valid
+ *     until the next lift call on the same ctx (or swo_destroy).
+ *   - a ctx is used by one host thread at a time; distinct ctxs are independent.
+ *   - coordinates are 32-bit (the reference parses them with to!int,
+ *     chain.d:347, bed.d:125-126).
+ *   - there is NO CPU fallback: without a CUDA device swo_create fails.
+ */
+#ifndef SWIFTOVER_CUDA_H
+#define SWIFTOVER_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum swo_status {
+    SWO_OK = 0,
+    SWO_E_IO = -1,        /* FileException (chain.d:513-514, main.d:91-101)        */
+    SWO_E_PARSE = -2,     /* ConvException / malformed chain or record              */
+    SWO_E_CUDA = -3,      /* CUDA runtime error or no device                        */
+    SWO_E_OOM = -4,       /* host or device allocation failed                       */
+    SWO_E_ARG = -5,       /* bad argument                                           */
+    SWO_E_STATE = -6,     /* e.g. lift before swo_load_chain                        */
+    SWO_E_CAPACITY = -7   /* caller-provided device output buffer too small         */
+} swo_status;
+
+typedef struct swo_ctx swo_ctx;
+
+/* ---- lifetime --------------------------------------------------------- */
+
+/* devices: CUDA ordinals the ctx may use (NULL/0 -> device 0).  The chain table
+ * and genome are replicated on each; text inputs are sharded by byte range
+ * over them.  The same ordinal may be listed several times
+ * ("logical shards") — used by the tests to exercise the sharder on one GPU. */
+int swo_create(swo_ctx **out, const int *devices, int ndev);
+/* A context WITHOUT a device: swo_load_chain* and the table accessors work (host
+ * parser only); every lift call fails with SWO_E_CUDA.  Used by CPU-side tests
+ * of the chain parser. */
+int swo_create_inspect(swo_ctx **out);
+void swo_destroy(swo_ctx *ctx);
+const char *swo_last_error(const swo_ctx *ctx);
+/* library build/ABI version, e.g. "swiftover_cuda 0.1 sm_100a" */
+const char *swo_version(void);
+
+/* ---- ChainFile.this(fn)  (chain.d:509-597) ----------------------------- */
+
+int swo_load_chain(swo_ctx *ctx, const char *path);
+int swo_load_chain_mem(swo_ctx *ctx, const char *text, size_t len);
+
+/* keys of chainsByContig (chain.d:495) = source-build ("target") contigs */
+int swo_num_tcontigs(const swo_ctx *ctx);
+const char *swo_tcontig_name(const swo_ctx *ctx, int tcid);
+/* -1 if the chain has no such contig */
+int swo_tcontig_id(const swo_ctx *ctx, const char *name, size_t len);
+int64_t swo_tcontig_nblocks(const swo_ctx *ctx, int tcid);
+/* tSize of the chain headers naming this contig (chain.d:298; last header wins) */
+int64_t swo_tcontig_size(const swo_ctx *ctx, int tcid);
+int64_t swo_num_blocks(const swo_ctx *ctx);
+/* 1 if no two blocks of a target contig overlap (true for UCSC over.chain) */
+int swo_table_is_disjoint(const swo_ctx *ctx);
+
+/* ChainFile.contigNames (chain.d:500): destination ("query") contig id -> name */
+int swo_num_qcontigs(const swo_ctx *ctx);
+const char *swo_qcontig_name(const swo_ctx *ctx, int qcid);
+/* ChainFile.qContigSizes (chain.d:504,551), in first-insertion order */
+int swo_num_qsizes(const swo_ctx *ctx);
+const char *swo_qsize_name(const swo_ctx *ctx, int i);
+int64_t swo_qsize_value(const swo_ctx *ctx, int i);
+
+/* Copy `n` blocks of target contig `tcid`, starting at `first`, in index order
+ * (tStart,tEnd,qStart) — the flattened form of the reference's per-contig tree
+ * (chain.d:537-548).  Any output pointer may be NULL. */
+int swo_get_blocks(const swo_ctx *ctx, int tcid, int64_t first, int64_t n, int32_t *t_start,
+                   int32_t *t_end, int32_t *q_start, int32_t *qcid, int8_t *invert);
+
+/* ---- ChainFile.lift + liftBED record body, binary  (chain.d:664-713,
+ *      bed.d:129-196) ----------------------------------------------------- */
+
+/* One lifted row.  Rows of one query are consecutive, sorted by raw qStart
+ * (bed.d:156-157; ties in block-index order), rows of different queries in
+ * query order. */
+typedef struct swo_row {
+    int32_t qcid_strand; /* bits 0-15 qcid; bits 16-23 strand byte after the
+                            cumulative STRAND_TABLE flip (bed.d:173), 0 if no
+                            strand input */
+    int32_t start;       /* orderStartEnd(qStart,qEnd).start (bed.d:165-168) */
+    int32_t end;
+    uint32_t src;        /* index of the source query */
+} swo_row;
+
+typedef struct swo_thick {
+    int32_t thick_start, thick_end; /* bed.d:175-196 */
+} swo_thick;
+
+typedef struct swo_lifted {
+    uint64_t n_rows;
+    uint64_t n_unmatched;           /* queries with zero overlapping blocks */
+    const uint32_t *row_offset;     /* [n+1] exclusive prefix of per-query fan-out */
+    const swo_row *rows;            /* [n_rows] */
+    const swo_thick *thick;         /* [n_rows] or NULL when no thick input */
+} swo_lifted;
+
+/* Host arrays in, pinned host arrays out.  tcid = swo_tcontig_id (negative ->
+ * no hit).  strand, thick_start/thick_end may be NULL (BED3 / BED6). */
+int swo_lift_intervals(swo_ctx *ctx, size_t n, const int32_t *tcid, const int32_t *start,
+                       const int32_t *end, const uint8_t *strand, const int32_t *thick_start,
+                       const int32_t *thick_end, swo_lifted *out);
+
+/* Same kernel, everything resident on device `devices[0]` (kernel-only
+ * measurement; no host copies).  d_row_offset[n+1], d_rows[rows_cap],
+ * d_thick[rows_cap] (or NULL) are caller-allocated device buffers.
+ * Asynchronous on `stream` (a cudaStream_t, NULL = legacy default stream);
+ * totals[0]=n_rows, totals[1]=n_unmatched are written to the DEVICE array
+ * d_totals[2].  If n_rows exceeds rows_cap nothing is written past the
+ * capacity and d_totals[0] still holds the required count. */
+int swo_lift_intervals_dev(swo_ctx *ctx, size_t n, const int32_t *d_tcid, const int32_t *d_start,
+                           const int32_t *d_end, const uint8_t *d_strand,
+                           const int32_t *d_thick_start, const int32_t *d_thick_end,
+                           uint32_t *d_row_offset, swo_row *d_rows, swo_thick *d_thick,
+                           size_t rows_cap, uint64_t *d_totals, void *stream);
+
+/* ---- liftCoordOnly / liftDirectly, batched  (chain.d:604-654) ----------- */
+
+/* hit[i] = 0|1; on 1 out_pos[i] = lifted coordinate and out_qcid[i] the
+ * destination contig id; on 0 out_pos[i] = pos[i], out_qcid[i] = -1. */
+int swo_lift_points(swo_ctx *ctx, size_t n, const int32_t *tcid, const int32_t *pos,
+                    int32_t *out_qcid, int32_t *out_pos, uint8_t *hit);
+
+/* ---- liftBED, text -> text  (bed.d:72-204) ------------------------------ */
+
+typedef struct swo_text_out {
+    const char *lifted;       /* what the reference writes to -o (bed.d:199) */
+    size_t lifted_len;
+    const char *unmatched;    /* what it writes to -u (bed.d:151)            */
+    size_t unmatched_len;
+    uint64_t n_records;       /* lines that were queried   */
+    uint64_t n_rows;          /* lifted rows               */
+    uint64_t n_unmatched;     /* records without any block */
+} swo_text_out;
+
+/* `in` = the whole BED file (any host memory; pinned is faster). */
+int swo_lift_bed_text(swo_ctx *ctx, const char *in, size_t in_len, swo_text_out *out);
+
+/* Same kernels on device-resident text (kernel-only measurement).  d_in must be
+ * 16-byte aligned.  d_sizes[0]=lifted bytes, [1]=unmatched bytes, [2]=records,
+ * [3]=rows, [4]=unmatched records, [5]=error (0 = every line parsed, else
+ * UINT64_MAX - byte offset of the first malformed line) — a DEVICE array of 6
+ * uint64.  Asynchronous on `stream`. */
+int swo_lift_bed_text_dev(swo_ctx *ctx, const char *d_in, size_t in_len, char *d_lifted,
+                          size_t lifted_cap, char *d_unmatched, size_t unmatched_cap,
+                          uint64_t *d_sizes, void *stream);
+
+/* ---- liftVCF record body  (vcf.d:115-169) ------------------------------- */
+
+/* Destination genome, 2 bit/base (A=0 C=1 G=2 T=3): base b of destination
+ * contig q is bits [2*(g%4), 2*(g%4)+2) of packed[g/4], g = contig_off[q]+b.
+ * Replaces IndexedFastaFile (vcf.d:38-39); indexed by qcid. */
+int swo_load_genome_2bit(swo_ctx *ctx, const uint8_t *packed, size_t packed_bytes,
+                         const int64_t *contig_off, const int64_t *contig_len, int n_contigs);
+
+/* flags bit0 = matched (vcf.d:134), bit1 = refchg (vcf.d:144-161).  out_ref has
+ * the layout of ref_bytes/ref_off and receives the destination REF
+ * (fetchSequence, vcf.d:143, clipped at the contig end), out_reflen its length. */
+int swo_lift_vcf_points(swo_ctx *ctx, size_t n, const int32_t *tcid, const int32_t *pos,
+                        const int32_t *reflen, const uint64_t *ref_off, const char *ref_bytes,
+                        size_t ref_bytes_len, int32_t *out_qcid, int32_t *out_pos, uint8_t *flags,
+                        int32_t *out_reflen, char *out_ref);
+
+/* ---- helpers ------------------------------------------------------------ */
+
+/* pinned host memory for inputs (cudaHostAlloc); faster H2D than pageable */
+void *swo_host_alloc(size_t bytes);
+void swo_host_free(void *p);
+
+/* tuning knobs: "chunk_bytes" = bytes of text per H2D/kernel/D2H pipeline stage
+ * (default 64 MiB; the tests shrink it to exercise chunk boundaries) */
+int swo_set_option(swo_ctx *ctx, const char *key, int64_t value);
+
+/* number of kernel launches issued by this ctx since creation (bench.py's
+ * gpu_launches claim) */
+uint64_t swo_launch_count(const swo_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SWIFTOVER_CUDA_H */

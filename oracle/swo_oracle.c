@@ -1039,3 +1039,17 @@ int orc_lift_vcf_points(const orc_chainfile *cf, const uint8_t *packed, const in
     }
     return ORC_OK;
 }
+
+/* ---------------------------------------------------- bench workload helper */
+size_t orc_format_bed3(const orc_chainfile *cf, size_t n, const int32_t *tcid, const int32_t *start,
+                       const int32_t *end, char *out, size_t cap) {
+    size_t o = 0;
+    for (size_t i = 0; i < n; i++) {
+        const tcontig *t = &cf->tc[tcid[i]];
+        if (o + t->name_len + 26 > cap) return 0;
+        memcpy(out + o, t->name, t->name_len);
+        o += t->name_len;
+        o += (size_t)sprintf(out + o, "\t%d\t%d\n", start[i], end[i]);
+    }
+    return o;
+}

@@ -164,6 +164,12 @@ int orc_lift_vcf_points(const orc_chainfile *cf, const uint8_t *packed,
                         int32_t *out_qcid, int32_t *out_pos, uint8_t *flags,
                         int32_t *out_reflen, char *out_ref);
 
+/* Workload helper for bench.py --impl reference (not part of the restatement):
+ * writes "name\tstart\tend\n" rows for n records, names taken from the chain's
+ * source contigs.  Returns bytes written (<= cap) or 0 if cap is too small. */
+size_t orc_format_bed3(const orc_chainfile *cf, size_t n, const int32_t *tcid, const int32_t *start,
+                       const int32_t *end, char *out, size_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,116 @@
+// device_util.cuh — CUB-free warp/block scans, the decoupled look-back chained
+// scan used by the single-pass lift kernels, and memory-access helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace swo {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
+
+// ---- cache-hinted accesses -------------------------------------------------
+// streaming (read-once) 128-bit load that does not allocate in L1
+__device__ __forceinline__ int4 ld_stream_v4(const void *p) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream_v4(void *p, const int4 &v) {
+    asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y),
+                 "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+// relaxed gpu-scope 64-bit accesses for the look-back descriptors (bypass L1)
+__device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t *p) {
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(uint64_t *p, uint64_t v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// ---- warp / block scans ----------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T warp_inclusive_scan(T v) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        T o = __shfl_up_sync(FULL, v, d);
+        if (lane_id() >= d) v += o;
+    }
+    return v;
+}
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
+    return v;
+}
+
+// Exclusive scan of one value per thread over a block of NWARPS*32 threads.
+// `scratch` is NWARPS+1 elements of shared memory.  Returns the exclusive prefix;
+// *total receives the block sum (same value in every thread).
+// Contains two __syncthreads(); safe to call repeatedly with the same scratch.
+template <typename T, int NWARPS>
+__device__ __forceinline__ T block_exclusive_scan(T v, T *scratch, T *total) {
+    const T inc = warp_inclusive_scan(v);
+    __syncthreads();  // previous users of scratch are done
+    if (lane_id() == 31) scratch[warp_id()] = inc;
+    __syncthreads();
+    T wbase = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < NWARPS; w++) {
+        const T s = scratch[w];
+        if (w < warp_id()) wbase += s;
+        tot += s;
+    }
+    *total = tot;
+    return wbase + inc - v;
+}
+
+// ---- decoupled look-back ---------------------------------------------------
+// One 64-bit descriptor per tile: bits 63..62 = state, bits 61..0 = value.
+constexpr uint64_t LB_EMPTY = 0ull, LB_AGG = 1ull << 62, LB_INC = 2ull << 62;
+constexpr uint64_t LB_STATE = 3ull << 62, LB_VALUE = ~LB_STATE;
+
+// Called by ONE full warp.  Publishes this tile's aggregate, walks the
+// predecessors' descriptors 32 at a time until an inclusive prefix is found,
+// publishes the inclusive prefix and returns the EXCLUSIVE prefix (all lanes).
+// Tiles must have been handed out by an atomic ticket so that every
+// predecessor is already running (forward progress).
+__device__ __forceinline__ uint64_t lookback_exclusive(uint64_t *desc, int tile, uint64_t aggregate) {
+    const int lane = lane_id();
+    if (tile == 0) {
+        if (lane == 0) st_relaxed_u64(desc, LB_INC | aggregate);
+        return 0;
+    }
+    if (lane == 0) st_relaxed_u64(desc + tile, LB_AGG | aggregate);
+    uint64_t excl = 0;
+    int look = tile - 1;
+    for (;;) {
+        const int idx = look - lane;
+        uint64_t v = LB_INC;  // virtual tile before tile 0: inclusive prefix 0
+        if (idx >= 0) {
+            v = ld_relaxed_u64(desc + idx);
+            while ((v & LB_STATE) == LB_EMPTY) {
+                __nanosleep(20);
+                v = ld_relaxed_u64(desc + idx);
+            }
+        }
+        const unsigned inc_mask = __ballot_sync(FULL, (v & LB_STATE) == LB_INC);
+        const int first = inc_mask ? (__ffs(inc_mask) - 1) : 32;
+        const uint64_t contrib = (lane <= first) ? (v & LB_VALUE) : 0ull;
+        excl += warp_sum(contrib);
+        if (inc_mask) break;
+        look -= 32;
+    }
+    if (lane == 0) st_relaxed_u64(desc + tile, LB_INC | (excl + aggregate));
+    return excl;
+}
+
+}  // namespace swo

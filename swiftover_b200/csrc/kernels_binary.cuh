@@ -1,0 +1,249 @@
+// kernels_binary.cuh — single-pass interval lift on binary records.
+//
+// Replaces, for a whole batch at once, the reference's per-record sequence
+//   cf.lift(contig,start,end)            chain.d:664-713 (+ intervaltree search)
+//   liftCoordOnly x2 for thickStart/End  bed.d:134-148, chain.d:637-654
+//   sort by qStart, orderStartEnd, strand table, thick clamp   bed.d:156-196
+//
+// One persistent kernel.  A tile is 1024 consecutive queries (256 threads x 4,
+// 128-bit loads).  Each thread searches its four queries, the per-query fan-out
+// is block-scanned, the tile aggregate is chained to its predecessors with a
+// decoupled look-back (so the variable-length output needs no separate count
+// and scan passes: every input byte is read once and every output byte is
+// written once), then rows are written in place.  Queries with one hit (the
+// common case) are written by their own thread; queries with >= 2 hits go to a
+// shared-memory work list and are expanded by a warp (or by the whole block
+// when the fan-out is large), each row computing its own sorted position.
+#pragma once
+#include "device_util.cuh"
+#include "lift_core.cuh"
+#include "swiftover_cuda.h"
+
+namespace swo {
+
+constexpr int LI_TPB = 256;
+constexpr int LI_IPT = 4;
+constexpr int LI_TILE = LI_TPB * LI_IPT;
+constexpr int LI_NW = LI_TPB / 32;
+constexpr int LI_WL_CAP = 256;      // multi-hit queries queued per tile
+constexpr int LI_HEAVY_MIN = 512;   // candidates >= this: whole block expands
+
+struct LiftArgs {
+    TableView T;
+    uint32_t n;
+    int ntiles;
+    const int32_t *tcid, *start, *end;
+    const uint8_t *strand;            // may be null
+    const int32_t *thick_s, *thick_e; // may be null (both)
+    uint32_t *row_offset;             // [n+1]
+    swo_row *rows;
+    swo_thick *thick;
+    uint64_t rows_cap;
+    uint64_t *desc;     // [ntiles] look-back descriptors, zeroed
+    unsigned *ticket;   // zeroed
+    uint64_t *totals;   // [0] rows, [1] unmatched   (zeroed)
+};
+
+// Expand one multi-hit query: every candidate block computes its own sorted
+// position (rank by (key, candidate index)), the cumulative strand byte and
+// the thick clamp, and writes its row.  Work is strided by (first, stride) so
+// the same code serves one thread, one warp or one block.
+__device__ __forceinline__ void expand_query(const LiftArgs &A, uint32_t q, int lo, int ncand, uint64_t rowbase,
+                                             int first, int stride) {
+    const TableView &T = A.T;
+    const int start = __ldg(A.start + q), end = __ldg(A.end + q);
+    const unsigned char orig = A.strand ? __ldg(A.strand + q) : 0;
+    Thick th{0, 0, 0};
+    if (A.thick_s) th = lift_thick(T, __ldg(A.tcid + q), __ldg(A.thick_s + q), __ldg(A.thick_e + q));
+    for (int c = first; c < ncand; c += stride) {
+        const Block bj = load_block(T, lo + c);
+        if (!T.disjoint && !block_hits(bj, start)) continue;
+        const RowCore rj = make_row(bj, start, end);
+        int rank = 0, negs = rj.inv < 0 ? 1 : 0;
+        int best_key = rj.key, best_k = c, best_inv = rj.inv;
+        for (int k = 0; k < ncand; k++) {
+            if (k == c) continue;
+            const Block bk = load_block(T, lo + k);
+            if (!T.disjoint && !block_hits(bk, start)) continue;
+            const RowCore rk = make_row(bk, start, end);
+            const bool before = rk.key < rj.key || (rk.key == rj.key && k < c);
+            rank += before;
+            negs += (before && rk.inv < 0) ? 1 : 0;
+            if (rk.key < best_key || (rk.key == best_key && k < best_k)) {
+                best_key = rk.key;
+                best_k = k;
+                best_inv = rk.inv;
+            }
+        }
+        const uint64_t pos = rowbase + (uint64_t)rank;
+        if (pos < A.rows_cap) {
+            const unsigned char sb = A.strand ? strand_at_rank(orig, best_inv, rank, negs) : 0;
+            swo_row r;
+            r.qcid_strand = rj.qcid | ((int)sb << 16);
+            r.start = rj.s;
+            r.end = rj.e;
+            r.src = q;
+            A.rows[pos] = r;
+            if (A.thick_s) {
+                swo_thick t;
+                thick_clamp(th, rj.s, rj.e, t.thick_start, t.thick_end);
+                A.thick[pos] = t;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(LI_TPB) lift_intervals_kernel(const LiftArgs A) {
+    __shared__ int s_tile;
+    __shared__ uint32_t s_scan[LI_NW + 1];
+    __shared__ uint64_t s_base;
+    __shared__ int s_wl_n;
+    __shared__ uint32_t s_wl_q[LI_WL_CAP];
+    __shared__ int s_wl_lo[LI_WL_CAP];
+    __shared__ int s_wl_cnt[LI_WL_CAP];
+    __shared__ uint32_t s_wl_off[LI_WL_CAP];
+
+    const int tid = threadIdx.x;
+    const TableView &T = A.T;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) {
+            s_tile = (int)atomicAdd(A.ticket, 1u);
+            s_wl_n = 0;
+        }
+        __syncthreads();
+        const int tile = s_tile;
+        if (tile >= A.ntiles) break;
+
+        const uint32_t q0 = (uint32_t)tile * LI_TILE + (uint32_t)tid * LI_IPT;
+        int tc[LI_IPT], st[LI_IPT], en[LI_IPT];
+        if (q0 + LI_IPT <= A.n) {
+            const int4 a = ld_stream_v4(A.tcid + q0), b = ld_stream_v4(A.start + q0), c = ld_stream_v4(A.end + q0);
+            tc[0] = a.x, tc[1] = a.y, tc[2] = a.z, tc[3] = a.w;
+            st[0] = b.x, st[1] = b.y, st[2] = b.z, st[3] = b.w;
+            en[0] = c.x, en[1] = c.y, en[2] = c.z, en[3] = c.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < LI_IPT; k++) {
+                const bool ok = q0 + k < A.n;
+                tc[k] = ok ? A.tcid[q0 + k] : -1;
+                st[k] = ok ? A.start[q0 + k] : 0;
+                en[k] = ok ? A.end[q0 + k] : 0;
+            }
+        }
+        Cand cd[LI_IPT];
+        int nh[LI_IPT];
+        uint32_t tsum = 0, unm = 0;
+#pragma unroll
+        for (int k = 0; k < LI_IPT; k++) {
+            cd[k] = find_candidates(T, tc[k], st[k], en[k]);
+            nh[k] = count_hits(T, cd[k], st[k]);
+            tsum += (uint32_t)nh[k];
+            unm += (q0 + k < A.n && nh[k] == 0) ? 1u : 0u;
+        }
+        uint32_t tile_total;
+        const uint32_t excl = block_exclusive_scan<uint32_t, LI_NW>(tsum, s_scan, &tile_total);
+        if (warp_id() == 0) {
+            const uint64_t b = lookback_exclusive(A.desc, tile, (uint64_t)tile_total);
+            if (tid == 0) s_base = b;
+        }
+        unm = warp_sum(unm);
+        if (lane_id() == 0 && unm) atomicAdd((unsigned long long *)(A.totals + 1), (unsigned long long)unm);
+        __syncthreads();
+        const uint64_t gbase = s_base;
+
+        // row_offset: four consecutive values per thread
+        uint32_t off[LI_IPT];
+        {
+            uint32_t run = (uint32_t)(gbase + excl);  // wraps only if rows >= 2^32 (host rejects)
+#pragma unroll
+            for (int k = 0; k < LI_IPT; k++) {
+                off[k] = run;
+                run += (uint32_t)nh[k];
+            }
+            if (q0 + LI_IPT <= A.n) {
+                st_stream_v4(A.row_offset + q0, make_int4((int)off[0], (int)off[1], (int)off[2], (int)off[3]));
+            } else {
+#pragma unroll
+                for (int k = 0; k < LI_IPT; k++)
+                    if (q0 + k < A.n) A.row_offset[q0 + k] = off[k];
+            }
+        }
+        if (tile == A.ntiles - 1 && tid == 0) {
+            const uint64_t total = gbase + tile_total;
+            A.row_offset[A.n] = (uint32_t)total;
+            A.totals[0] = total;
+        }
+
+        // rows
+        uint64_t run64 = gbase + excl;
+#pragma unroll
+        for (int k = 0; k < LI_IPT; k++) {
+            const uint32_t q = q0 + k;
+            if (nh[k] == 1) {
+                int j = cd[k].lo;
+                Block b = load_block(T, j);
+                if (!T.disjoint)
+                    while (!block_hits(b, st[k])) b = load_block(T, ++j);
+                const RowCore r = make_row(b, st[k], en[k]);
+                if (run64 < A.rows_cap) {
+                    const unsigned char sb = A.strand ? strand_flip(__ldg(A.strand + q), r.inv) : 0;
+                    st_stream_v4(A.rows + run64, make_int4(r.qcid | ((int)sb << 16), r.s, r.e, (int)q));
+                    if (A.thick_s) {
+                        const Thick th = lift_thick(T, tc[k], __ldg(A.thick_s + q), __ldg(A.thick_e + q));
+                        swo_thick t;
+                        thick_clamp(th, r.s, r.e, t.thick_start, t.thick_end);
+                        A.thick[run64] = t;
+                    }
+                }
+            } else if (nh[k] >= 2) {
+                const int slot = atomicAdd(&s_wl_n, 1);
+                if (slot < LI_WL_CAP) {
+                    s_wl_q[slot] = q;
+                    s_wl_lo[slot] = cd[k].lo;
+                    s_wl_cnt[slot] = cd[k].hi - cd[k].lo;
+                    s_wl_off[slot] = (uint32_t)(run64 - gbase);
+                } else {
+                    // work list full: expand serially in this thread
+                    expand_query(A, q, cd[k].lo, cd[k].hi - cd[k].lo, run64, 0, 1);
+                }
+            }
+            run64 += (uint64_t)nh[k];
+        }
+        __syncthreads();
+        const int nwl = min(s_wl_n, LI_WL_CAP);
+        // light and medium fan-out: one warp per query
+        for (int e = warp_id(); e < nwl; e += LI_NW) {
+            if (s_wl_cnt[e] < LI_HEAVY_MIN)
+                expand_query(A, s_wl_q[e], s_wl_lo[e], s_wl_cnt[e], gbase + s_wl_off[e], lane_id(), 32);
+        }
+        // heavy fan-out: the whole block per query
+        for (int e = 0; e < nwl; e++) {
+            if (s_wl_cnt[e] >= LI_HEAVY_MIN)
+                expand_query(A, s_wl_q[e], s_wl_lo[e], s_wl_cnt[e], gbase + s_wl_off[e], tid, LI_TPB);
+        }
+    }
+}
+
+// liftCoordOnly / liftDirectly for a batch of points (chain.d:604-654).
+__global__ void __launch_bounds__(256) lift_points_kernel(const TableView T, uint32_t n, const int32_t *__restrict__ tcid,
+                                                          const int32_t *__restrict__ pos, int32_t *__restrict__ out_qcid,
+                                                          int32_t *__restrict__ out_pos, uint8_t *__restrict__ hit) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int c = pos[i];
+        const int j = point_hit(T, tcid[i], c);
+        if (j < 0) {
+            out_qcid[i] = -1;
+            out_pos[i] = c;
+            hit[i] = 0;
+        } else {
+            const Block b = load_block(T, j);
+            out_qcid[i] = b.meta >> 1;
+            out_pos[i] = point_coord(b, c);
+            hit[i] = 1;
+        }
+    }
+}
+
+}  // namespace swo

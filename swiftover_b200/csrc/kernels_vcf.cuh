@@ -1,0 +1,68 @@
+// kernels_vcf.cuh — liftVCF record body on device.
+//
+// Replaces, per record (/root/reference/source/swiftover/vcf.d:115-169):
+//   liftDirectly(chrom, pos)                   vcf.d:125 -> chain.d:604-627
+//   fa.fetchSequence(chrom, pos, pos+refLen)   vcf.d:143  (here: gather from a
+//                                              2-bit packed genome held in HBM)
+//   REF != fetched -> replace REF, set refchg  vcf.d:144-161
+// The reference does no strand handling: on '-' blocks the
+// position is qStart - delta and alleles are not reverse-complemented; both are
+// reproduced.
+#pragma once
+#include "device_util.cuh"
+#include "lift_core.cuh"
+
+namespace swo {
+
+struct VcfArgs {
+    TableView T;
+    const uint8_t *packed;  // 2 bit/base, A=0 C=1 G=2 T=3
+    const int64_t *g_off;   // [g_n] first base of each destination contig
+    const int64_t *g_len;   // [g_n]
+    int g_n;
+    uint32_t n;
+    const int32_t *tcid, *pos, *reflen;
+    const uint64_t *ref_off;
+    const char *ref;
+    int32_t *out_qcid, *out_pos;
+    uint8_t *flags;
+    int32_t *out_reflen;
+    char *out_ref;
+};
+
+__global__ void __launch_bounds__(256) lift_vcf_points_kernel(const VcfArgs A) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < A.n; i += gridDim.x * blockDim.x) {
+        const int c0 = A.pos[i];
+        const int rl = A.reflen[i];
+        const uint64_t ro = A.ref_off[i];
+        const int j = point_hit(A.T, A.tcid[i], c0);
+        if (j < 0) {  // vcf.d:134-137: record goes to the unmatched file unchanged
+            A.out_qcid[i] = -1;
+            A.out_pos[i] = c0;
+            A.flags[i] = 0;
+            A.out_reflen[i] = rl;
+            for (int k = 0; k < rl; k++) A.out_ref[ro + k] = A.ref[ro + k];
+            continue;
+        }
+        const Block b = load_block(A.T, j);
+        const int q = b.meta >> 1;
+        const int c = point_coord(b, c0);
+        const int64_t L = q < A.g_n ? A.g_len[q] : 0;
+        int m = 0;  // faidx clips the fetch at the contig end
+        if (c >= 0 && (int64_t)c < L) m = (int64_t)c + rl > L ? (int)(L - c) : rl;
+        bool diff = m != rl;
+        const int64_t g0 = q < A.g_n ? A.g_off[q] + c : 0;
+        for (int k = 0; k < m; k++) {
+            const int64_t g = g0 + k;
+            const char base = "ACGT"[(__ldg(A.packed + (g >> 2)) >> ((g & 3) * 2)) & 3];
+            A.out_ref[ro + k] = base;
+            diff |= base != A.ref[ro + k];  // vcf.d:144 byte-exact compare
+        }
+        A.out_qcid[i] = q;
+        A.out_pos[i] = c;
+        A.out_reflen[i] = m;
+        A.flags[i] = diff ? 3 : 1;
+    }
+}
+
+}  // namespace swo

@@ -1,0 +1,191 @@
+// lift_core.cuh — the per-record arithmetic of the liftover path as
+// __host__ __device__ functions shared by the binary, text and VCF kernels.
+//
+// Reference semantics (paths relative to /root/reference/source/swiftover):
+//   overlap set      intervaltree findOverlapsWith, half-open (chain.d:667)
+//   intersect        chain.d:728-743
+//   qEnd             chain.d:128-134
+//   orderStartEnd    chain.d:787-793
+//   STRAND_TABLE     bed.d:34-52, applied cumulatively in place (bed.d:173)
+//   thick clamp      bed.d:175-196
+//   point lifts      chain.d:604-654 (first hit in (tStart,tEnd,qStart) order)
+#pragma once
+#include <stdint.h>
+
+#include "chain_table.hpp"
+
+#if defined(__CUDACC__)
+#define SWO_HD __host__ __device__ __forceinline__
+#else
+#define SWO_HD inline
+#endif
+
+namespace swo {
+
+// Device view of the flattened block table (see chain_table.hpp).
+struct TableView {
+    const Block *__restrict__ blk;        // [B] payload (128-bit per block)
+    const int32_t *__restrict__ tStartKey;  // [B]
+    const int32_t *__restrict__ pmaxKey;    // [B] prefix max of tEnd per contig
+    const int32_t *__restrict__ toff;       // [ntc+1]
+    int ntc;
+    int disjoint;  // pmaxKey == tEnd: candidates need no tEnd filter
+};
+
+#if defined(__CUDA_ARCH__)
+#define SWO_LDG(p) __ldg(p)
+#else
+#define SWO_LDG(p) (*(p))
+#endif
+
+// first j in [a,b) with key[j] > x, else b
+SWO_HD int lower_gt(const int32_t *__restrict__ key, int a, int b, int x) {
+    while (a < b) {
+        const int m = (int)(((unsigned)a + (unsigned)b) >> 1);
+        if (SWO_LDG(key + m) > x) b = m;
+        else a = m + 1;
+    }
+    return a;
+}
+
+// first j in [lo,b) with key[j] >= x, else b — exponential probe from lo
+// (the answer is almost always lo, lo+1 or lo+2), then bisection.
+SWO_HD int gallop_ge(const int32_t *__restrict__ key, int lo, int b, int x) {
+    int a = lo, step = 1;
+    while (a < b) {
+        int p = a + step - 1;
+        if (p >= b) p = b - 1;
+        if (SWO_LDG(key + p) >= x) {
+            int l = a, r = p;
+            while (l < r) {
+                const int m = (l + r) >> 1;
+                if (SWO_LDG(key + m) >= x) r = m;
+                else l = m + 1;
+            }
+            return l;
+        }
+        a = p + 1;
+        step <<= 1;
+    }
+    return b;
+}
+
+// Candidate block range of the half-open query [start,end) on contig tcid:
+// every block j in [lo,hi) has tStart < end and prefix-max(tEnd) > start; the
+// overlap set is { j in [lo,hi) : tEnd[j] > start } (all of them when the
+// table is target-disjoint).
+struct Cand {
+    int lo, hi;
+};
+SWO_HD Cand find_candidates(const TableView &T, int tcid, int start, int end) {
+    Cand c{0, 0};
+    if (tcid < 0 || tcid >= T.ntc) return c;
+    const int a = SWO_LDG(T.toff + tcid), b = SWO_LDG(T.toff + tcid + 1);
+    c.lo = lower_gt(T.pmaxKey, a, b, start);
+    c.hi = gallop_ge(T.tStartKey, c.lo, b, end);
+    return c;
+}
+
+SWO_HD Block load_block(const TableView &T, int j) {
+#if defined(__CUDA_ARCH__)
+    const int4 v = __ldg(reinterpret_cast<const int4 *>(T.blk) + j);
+    return Block{v.x, v.y, v.z, v.w};
+#else
+    return T.blk[j];
+#endif
+}
+
+SWO_HD bool block_hits(const Block &b, int start) { return b.tEnd > start; }
+
+// number of overlapping blocks in the candidate range
+SWO_HD int count_hits(const TableView &T, const Cand &c, int start) {
+    if (T.disjoint) return c.hi - c.lo;
+    int n = 0;
+    for (int j = c.lo; j < c.hi; j++) n += SWO_LDG(&T.blk[j].tEnd) > start;
+    return n;
+}
+
+// One lifted row before text formatting.
+struct RowCore {
+    int key;   // raw qStart after intersect == the sort key of bed.d:156
+    int s, e;  // orderStartEnd(qStart, qEnd)
+    int inv;   // +1 | -1
+    int qcid;
+};
+SWO_HD RowCore make_row(const Block &b, int start, int end) {
+    RowCore r;
+    const int ts = b.tStart > start ? b.tStart : start;  // chain.d:733-734
+    const int te = b.tEnd < end ? b.tEnd : end;
+    r.inv = (b.meta & 1) ? -1 : 1;
+    r.qcid = b.meta >> 1;
+    r.key = b.qStart + r.inv * (ts - b.tStart);  // chain.d:736-737
+    const int qe = r.key + r.inv * (te - ts);    // chain.d:133
+    r.s = r.key < qe ? r.key : qe;               // chain.d:787-793
+    r.e = r.key < qe ? qe : r.key;
+    return r;
+}
+
+// STRAND_TABLE[c + invert]  (bed.d:34-52,173)
+SWO_HD unsigned char strand_flip(unsigned char c, int inv) {
+    const int idx = (int)c + inv;
+    return (idx == 0x2A || idx == 0x2E) ? '-' : (idx == 0x2C ? '+' : '!');
+}
+// Strand byte of the row at sorted position `rank` of a record, given the
+// record's original byte, the invert of the rank-0 row and the number of
+// invert==-1 rows at ranks <= rank (self included).  Equals applying
+// strand_flip once per row in sorted order (the in-place update of bed.d:173).
+SWO_HD unsigned char strand_at_rank(unsigned char orig, int inv_first, int rank, int negs_le) {
+    const unsigned char f0 = strand_flip(orig, inv_first);
+    if (rank == 0 || f0 == '!') return f0;
+    const int negs_after_first = negs_le - (inv_first < 0 ? 1 : 0);
+    if ((negs_after_first & 1) == 0) return f0;
+    return f0 == '+' ? '-' : '+';
+}
+
+// liftCoordOnly / liftDirectly (chain.d:604-654): first block covering c.
+// Returns block index or -1.
+SWO_HD int point_hit(const TableView &T, int tcid, int c) {
+    if (tcid < 0 || tcid >= T.ntc) return -1;
+    const int a = SWO_LDG(T.toff + tcid), b = SWO_LDG(T.toff + tcid + 1);
+    int j = lower_gt(T.pmaxKey, a, b, c);
+    for (; j < b; j++) {
+        if (SWO_LDG(T.tStartKey + j) > c) return -1;
+        if (T.disjoint || SWO_LDG(&T.blk[j].tEnd) > c) return j;
+    }
+    return -1;
+}
+SWO_HD int point_coord(const Block &b, int c) {
+    return b.qStart + ((b.meta & 1) ? -1 : 1) * (c - b.tStart);
+}
+
+// thickStart/thickEnd of a record (bed.d:134-148).
+struct Thick {
+    int has;  // hasThickInterval
+    int ts, te;
+};
+SWO_HD Thick lift_thick(const TableView &T, int tcid, int ts, int te) {
+    Thick k{0, ts, te};
+    if (ts == te) return k;
+    const int j0 = point_hit(T, tcid, ts);
+    if (j0 < 0) return k;  // short-circuit: thickEnd is not looked up
+    const int j1 = point_hit(T, tcid, te);
+    if (j1 < 0) return k;
+    const int a = point_coord(load_block(T, j0), ts);
+    const int b = point_coord(load_block(T, j1), te);
+    k.has = 1;
+    k.ts = a < b ? a : b;  // orderStartEnd  bed.d:146
+    k.te = a < b ? b : a;
+    return k;
+}
+// columns 7 and 8 of one output row (bed.d:175-196)
+SWO_HD void thick_clamp(const Thick &k, int s, int e, int &c7, int &c8) {
+    if (!k.has || k.ts >= e || k.te <= s) {
+        c7 = s;
+        c8 = s;
+    } else {
+        c7 = k.ts < s ? s : k.ts;
+        c8 = k.te > e ? e : k.te;
+    }
+}
+
+}  // namespace swo

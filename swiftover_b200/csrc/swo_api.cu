@@ -1,0 +1,811 @@
+// swo_api.cu — C ABI of libswiftover_cuda.so (include/swiftover_cuda.h).
+//
+// Host-side plumbing around the sm_100a kernels: context, chain-table upload
+// (replacing the tree build of chain.d:509-597), device/pinned buffers,
+// byte-range sharding of text inputs over devices and the chunked
+// H2D -> kernel -> D2H pipeline.  No CPU compute path exists here: every lift
+// goes through a CUDA kernel or fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <memory>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "chain_table.hpp"
+#include "kernels_binary.cuh"
+#include "kernels_text.cuh"
+#include "kernels_vcf.cuh"
+#include "swiftover_cuda.h"
+#include "swo_internal.hpp"
+
+using namespace swo;
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = n + (n >> 3) + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct PinBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n, bool keep = false, size_t keep_bytes = 0) {
+        if (n <= cap) return cudaSuccess;
+        size_t want = n + (n >> 2) + 4096;
+        void *np = nullptr;
+        cudaError_t e = cudaHostAlloc(&np, want, cudaHostAllocPortable);
+        if (e != cudaSuccess) return e;
+        if (keep && p && keep_bytes) memcpy(np, p, keep_bytes);
+        if (p) cudaFreeHost(p);
+        p = np;
+        cap = want;
+        return cudaSuccess;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+constexpr int N_SLOTS = 2;  // chunk double-buffering
+
+// Everything one device (or logical shard) owns.
+struct Device {
+    int ordinal = 0;
+    int sms = 148;
+    cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
+    // chain table replica
+    DevBuf blk, tkey, pkey, toff, thash, tchars, tnoff, qoff, qchars;
+    TableView T{};
+    uint32_t thash_mask = 0;
+    // genome replica
+    DevBuf g_packed, g_off, g_len;
+    int g_n = 0;
+    // scratch for the look-back chains
+    DevBuf scratch;
+    // binary path buffers
+    DevBuf b_in, b_off, b_rows, b_thick, b_tot;
+    // text path: per-slot chunk buffers
+    DevBuf t_in[N_SLOTS], t_out[N_SLOTS], t_unm[N_SLOTS], t_sizes[N_SLOTS];
+    cudaEvent_t ev_h2d[N_SLOTS]{}, ev_comp[N_SLOTS]{}, ev_d2h[N_SLOTS]{};
+    PinBuf h_sizes;  // N_SLOTS * 6 u64
+    // per-shard host output arenas (multi-shard runs)
+    PinBuf a_lifted, a_unm;
+    int text_grid = 0, bin_grid = 0;
+};
+
+}  // namespace
+
+struct swo_ctx {
+    std::vector<Device> dev;
+    ChainTable tab;
+    bool have_chain = false;
+    std::string err;
+    uint64_t launches = 0;
+    // pinned result arenas handed to the caller
+    PinBuf r_lifted, r_unm, r_off, r_rows, r_thick;
+    size_t chunk_bytes = 64u << 20;
+};
+
+namespace {
+
+int fail(swo_ctx *c, int code, const char *fmt, ...) {
+    if (c) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        c->err = buf;
+    }
+    return code;
+}
+
+#define CK(ctx, call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(ctx, e__ == cudaErrorMemoryAllocation ? SWO_E_OOM : SWO_E_CUDA, "%s: %s (%s:%d)", #call, \
+                        cudaGetErrorString(e__), __FILE__, __LINE__);                              \
+    } while (0)
+
+template <typename T>
+int upload(swo_ctx *c, DevBuf &b, const T *src, size_t n, cudaStream_t s) {
+    CK(c, b.reserve(std::max<size_t>(n * sizeof(T), 16)));
+    if (n) CK(c, cudaMemcpyAsync(b.p, src, n * sizeof(T), cudaMemcpyHostToDevice, s));
+    return SWO_OK;
+}
+
+int upload_table(swo_ctx *c, Device &d) {
+    const ChainTable &t = c->tab;
+    CK(c, cudaSetDevice(d.ordinal));
+    int rc;
+    if ((rc = upload(c, d.blk, t.blocks.data(), t.blocks.size(), d.s_comp))) return rc;
+    if ((rc = upload(c, d.tkey, t.tStartKey.data(), t.tStartKey.size(), d.s_comp))) return rc;
+    if ((rc = upload(c, d.pkey, t.pmaxKey.data(), t.pmaxKey.size(), d.s_comp))) return rc;
+    if ((rc = upload(c, d.toff, t.toff.data(), t.toff.size(), d.s_comp))) return rc;
+    // source-contig name table (device text parser)
+    uint32_t hs = 16;
+    while (hs < (uint32_t)t.ntc() * 4u) hs <<= 1;
+    std::vector<NameEnt> ents(hs, NameEnt{0, -1, 0, 0});
+    std::string chars;
+    std::vector<uint32_t> tnoff(1, 0);
+    for (int i = 0; i < t.ntc(); i++) {
+        const std::string &nm = t.tnames[i];
+        NameEnt e{name_hash(nm.data(), nm.size()), i, (uint32_t)chars.size(), (uint32_t)nm.size()};
+        chars += nm;
+        tnoff.push_back((uint32_t)chars.size());
+        uint32_t s = e.hash & (hs - 1);
+        while (ents[s].id >= 0) s = (s + 1) & (hs - 1);
+        ents[s] = e;
+    }
+    chars.push_back('\0');
+    d.thash_mask = hs - 1;
+    if ((rc = upload(c, d.thash, ents.data(), ents.size(), d.s_comp))) return rc;
+    if ((rc = upload(c, d.tchars, chars.data(), chars.size(), d.s_comp))) return rc;
+    if ((rc = upload(c, d.tnoff, tnoff.data(), tnoff.size(), d.s_comp))) return rc;
+    std::vector<uint32_t> qoff(1, 0);
+    std::string qchars;
+    for (const std::string &nm : t.qnames) {
+        qchars += nm;
+        qoff.push_back((uint32_t)qchars.size());
+    }
+    qchars.push_back('\0');
+    if ((rc = upload(c, d.qoff, qoff.data(), qoff.size(), d.s_comp))) return rc;
+    if ((rc = upload(c, d.qchars, qchars.data(), qchars.size(), d.s_comp))) return rc;
+    CK(c, cudaStreamSynchronize(d.s_comp));
+    d.T.blk = d.blk.as<Block>();
+    d.T.tStartKey = d.tkey.as<int32_t>();
+    d.T.pmaxKey = d.pkey.as<int32_t>();
+    d.T.toff = d.toff.as<int32_t>();
+    d.T.ntc = t.ntc();
+    d.T.disjoint = t.disjoint ? 1 : 0;
+    return SWO_OK;
+}
+
+bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ---- binary path ---------------------------------------------------------------
+int launch_lift_intervals(swo_ctx *c, Device &d, size_t n, const int32_t *tcid, const int32_t *start,
+                          const int32_t *end, const uint8_t *strand, const int32_t *ths, const int32_t *the,
+                          uint32_t *row_offset, swo_row *rows, swo_thick *thick, size_t rows_cap, uint64_t *totals,
+                          cudaStream_t st) {
+    const int ntiles = (int)((n + LI_TILE - 1) / LI_TILE);
+    const size_t scratch_bytes = 16 + (size_t)ntiles * 8;
+    CK(c, d.scratch.reserve(scratch_bytes));
+    CK(c, cudaMemsetAsync(d.scratch.p, 0, scratch_bytes, st));
+    CK(c, cudaMemsetAsync(totals, 0, 16, st));
+    if (n == 0) {
+        CK(c, cudaMemsetAsync(row_offset, 0, 4, st));
+        return SWO_OK;
+    }
+    LiftArgs A;
+    A.T = d.T;
+    A.n = (uint32_t)n;
+    A.ntiles = ntiles;
+    A.tcid = tcid;
+    A.start = start;
+    A.end = end;
+    A.strand = strand;
+    A.thick_s = ths;
+    A.thick_e = the;
+    A.row_offset = row_offset;
+    A.rows = rows;
+    A.thick = thick;
+    A.rows_cap = rows_cap;
+    A.ticket = d.scratch.as<unsigned>();
+    A.desc = reinterpret_cast<uint64_t *>(d.scratch.as<char>() + 16);
+    A.totals = totals;
+    if (!d.bin_grid) {
+        int per = 0;
+        CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, lift_intervals_kernel, LI_TPB, 0));
+        d.bin_grid = std::max(1, per) * d.sms;
+    }
+    const int grid = std::min(ntiles, d.bin_grid);
+    lift_intervals_kernel<<<grid, LI_TPB, 0, st>>>(A);
+    c->launches++;
+    CK(c, cudaGetLastError());
+    return SWO_OK;
+}
+
+// ---- text path -------------------------------------------------------------------
+int launch_lift_text(swo_ctx *c, Device &d, const char *d_in, size_t in_len, char *d_lifted, size_t lifted_cap,
+                     char *d_unm, size_t unm_cap, uint64_t *d_sizes, cudaStream_t st) {
+    const int ntiles = (int)((in_len + TX_TILE - 1) / TX_TILE);
+    const size_t scratch_bytes = 16 + (size_t)ntiles * 16;
+    CK(c, d.scratch.reserve(scratch_bytes));
+    CK(c, cudaMemsetAsync(d.scratch.p, 0, scratch_bytes, st));
+    CK(c, cudaMemsetAsync(d_sizes, 0, 48, st));
+    if (in_len == 0) return SWO_OK;
+    TextArgs A;
+    A.T = d.T;
+    A.thash = d.thash.as<NameEnt>();
+    A.thash_mask = d.thash_mask;
+    A.tname_chars = d.tchars.as<char>();
+    A.qname_off = d.qoff.as<uint32_t>();
+    A.qname_chars = d.qchars.as<char>();
+    A.in = d_in;
+    A.in_len = in_len;
+    A.ntiles = ntiles;
+    A.lifted = d_lifted;
+    A.lifted_cap = lifted_cap;
+    A.unm = d_unm;
+    A.unm_cap = unm_cap;
+    A.ticket = d.scratch.as<unsigned>();
+    A.desc_l = reinterpret_cast<uint64_t *>(d.scratch.as<char>() + 16);
+    A.desc_u = A.desc_l + ntiles;
+    A.sizes = d_sizes;
+    const size_t smem = sizeof(TextSmem);
+    if (!d.text_grid) {
+        CK(c, cudaFuncSetAttribute(lift_bed_text_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per = 0;
+        CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, lift_bed_text_kernel, TX_TPB, smem));
+        d.text_grid = std::max(1, per) * d.sms;
+    }
+    const int grid = std::min(ntiles, d.text_grid);
+    lift_bed_text_kernel<<<grid, TX_TPB, smem, st>>>(A);
+    c->launches++;
+    CK(c, cudaGetLastError());
+    return SWO_OK;
+}
+
+struct ShardResult {
+    size_t lifted = 0, unm = 0;
+    uint64_t rec = 0, rows = 0, nunm = 0;
+    int rc = SWO_OK;
+    uint64_t err_off = 0;
+    bool has_err = false;
+};
+
+// Lift the byte range [a,b) of `in` (line aligned) on device d, streaming chunks
+// H2D -> kernel -> D2H.  Outputs are appended to (*pl)[base_l...] / (*pu)[base_u...].
+int run_shard(swo_ctx *c, Device &d, const char *in, size_t a, size_t b, PinBuf *pl, size_t base_l, PinBuf *pu,
+              size_t base_u, ShardResult &res) {
+    CK(c, cudaSetDevice(d.ordinal));
+    CK(c, d.h_sizes.reserve(N_SLOTS * 48));
+    uint64_t *hs = d.h_sizes.as<uint64_t>();
+    // chunk boundaries (line aligned)
+    std::vector<size_t> cuts(1, a);
+    while (cuts.back() < b) {
+        size_t e = std::min(b, cuts.back() + c->chunk_bytes);
+        if (e < b) {
+            const void *nl = memchr(in + e, '\n', b - e);
+            e = nl ? (size_t)((const char *)nl - in) + 1 : b;
+        }
+        cuts.push_back(e);
+    }
+    const int nch = (int)cuts.size() - 1;
+    size_t out_l = base_l, out_u = base_u;
+    auto issue = [&](int k) -> int {  // H2D + kernel + sizes readback for chunk k
+        const int s = k % N_SLOTS;
+        const size_t off = cuts[k], len = cuts[k + 1] - cuts[k];
+        CK(c, d.t_in[s].reserve(len + 32));
+        CK(c, d.t_out[s].reserve(len + (len >> 1) + 65536));
+        CK(c, d.t_unm[s].reserve(len + 64));
+        CK(c, d.t_sizes[s].reserve(48));
+        CK(c, cudaStreamWaitEvent(d.s_h2d, d.ev_d2h[s], 0));  // slot's previous outputs are on the host
+        CK(c, cudaMemcpyAsync(d.t_in[s].p, in + off, len, cudaMemcpyHostToDevice, d.s_h2d));
+        CK(c, cudaEventRecord(d.ev_h2d[s], d.s_h2d));
+        CK(c, cudaStreamWaitEvent(d.s_comp, d.ev_h2d[s], 0));
+        int rc = launch_lift_text(c, d, d.t_in[s].as<char>(), len, d.t_out[s].as<char>(), d.t_out[s].cap,
+                                  d.t_unm[s].as<char>(), d.t_unm[s].cap, d.t_sizes[s].as<uint64_t>(), d.s_comp);
+        if (rc) return rc;
+        CK(c, cudaMemcpyAsync(hs + 6 * s, d.t_sizes[s].p, 48, cudaMemcpyDeviceToHost, d.s_comp));
+        CK(c, cudaEventRecord(d.ev_comp[s], d.s_comp));
+        return SWO_OK;
+    };
+    int rc;
+    if (nch > 0 && (rc = issue(0))) return rc;
+    for (int k = 0; k < nch; k++) {
+        const int s = k % N_SLOTS;
+        if (k + 1 < nch && (rc = issue(k + 1))) return rc;
+        CK(c, cudaEventSynchronize(d.ev_comp[s]));
+        uint64_t sz[6];
+        memcpy(sz, hs + 6 * s, 48);
+        const size_t len = cuts[k + 1] - cuts[k];
+        if (sz[0] > d.t_out[s].cap) {
+            // fan-out larger than the guess: grow this slot's output and redo the chunk
+            CK(c, cudaStreamSynchronize(d.s_comp));
+            CK(c, d.t_out[s].reserve((size_t)sz[0] + 4096));
+            rc = launch_lift_text(c, d, d.t_in[s].as<char>(), len, d.t_out[s].as<char>(), d.t_out[s].cap,
+                                  d.t_unm[s].as<char>(), d.t_unm[s].cap, d.t_sizes[s].as<uint64_t>(), d.s_comp);
+            if (rc) return rc;
+            CK(c, cudaMemcpyAsync(hs + 6 * s, d.t_sizes[s].p, 48, cudaMemcpyDeviceToHost, d.s_comp));
+            CK(c, cudaEventRecord(d.ev_comp[s], d.s_comp));
+            CK(c, cudaEventSynchronize(d.ev_comp[s]));
+            memcpy(sz, hs + 6 * s, 48);
+        }
+        if (sz[5] && !res.has_err) {
+            res.has_err = true;
+            res.err_off = cuts[k] + (UINT64_MAX - sz[5]);
+        }
+        // grow the host arenas if needed (keeps what is already there)
+        if (out_l + sz[0] > pl->cap) {
+            CK(c, cudaStreamSynchronize(d.s_d2h));
+            CK(c, pl->reserve(out_l + sz[0], true, out_l));
+        }
+        if (out_u + sz[1] > pu->cap) {
+            CK(c, cudaStreamSynchronize(d.s_d2h));
+            CK(c, pu->reserve(out_u + sz[1], true, out_u));
+        }
+        CK(c, cudaStreamWaitEvent(d.s_d2h, d.ev_comp[s], 0));
+        if (sz[0]) CK(c, cudaMemcpyAsync(pl->as<char>() + out_l, d.t_out[s].p, sz[0], cudaMemcpyDeviceToHost, d.s_d2h));
+        if (sz[1]) CK(c, cudaMemcpyAsync(pu->as<char>() + out_u, d.t_unm[s].p, sz[1], cudaMemcpyDeviceToHost, d.s_d2h));
+        CK(c, cudaEventRecord(d.ev_d2h[s], d.s_d2h));
+        out_l += sz[0];
+        out_u += sz[1];
+        res.rec += sz[2];
+        res.rows += sz[3];
+        res.nunm += sz[4];
+    }
+    CK(c, cudaStreamSynchronize(d.s_d2h));
+    res.lifted = out_l - base_l;
+    res.unm = out_u - base_u;
+    return SWO_OK;
+}
+
+}  // namespace
+
+// =================================================================================
+extern "C" {
+
+const char *swo_version(void) { return "swiftover_cuda 0.1 sm_100a"; }
+
+int swo_create(swo_ctx **out, const int *devices, int ndev) {
+    if (!out) return SWO_E_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) return SWO_E_CUDA;  // no CPU fallback
+    std::unique_ptr<swo_ctx> c(new swo_ctx);
+    std::vector<int> ords;
+    if (!devices || ndev <= 0) ords.push_back(0);
+    else ords.assign(devices, devices + ndev);
+    for (int o : ords) {
+        if (o < 0 || o >= count) return SWO_E_ARG;
+        Device d;
+        d.ordinal = o;
+        if (cudaSetDevice(o) != cudaSuccess) return SWO_E_CUDA;
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, o) != cudaSuccess) return SWO_E_CUDA;
+        d.sms = p.multiProcessorCount;
+        if (cudaStreamCreateWithFlags(&d.s_h2d, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&d.s_comp, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&d.s_d2h, cudaStreamNonBlocking) != cudaSuccess)
+            return SWO_E_CUDA;
+        for (int s = 0; s < N_SLOTS; s++) {
+            cudaEventCreateWithFlags(&d.ev_h2d[s], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&d.ev_comp[s], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&d.ev_d2h[s], cudaEventDisableTiming);
+        }
+        c->dev.push_back(d);
+    }
+    *out = c.release();
+    return SWO_OK;
+}
+
+int swo_create_inspect(swo_ctx **out) {
+    if (!out) return SWO_E_ARG;
+    *out = new swo_ctx;  // no devices: chain parsing + table inspection only
+    return SWO_OK;
+}
+
+void swo_destroy(swo_ctx *c) {
+    if (!c) return;
+    for (Device &d : c->dev) {
+        cudaSetDevice(d.ordinal);
+        cudaDeviceSynchronize();
+        for (DevBuf *b : {&d.blk, &d.tkey, &d.pkey, &d.toff, &d.thash, &d.tchars, &d.tnoff, &d.qoff, &d.qchars, &d.g_packed,
+                          &d.g_off, &d.g_len, &d.scratch, &d.b_in, &d.b_off, &d.b_rows, &d.b_thick, &d.b_tot})
+            b->release();
+        for (int s = 0; s < N_SLOTS; s++) {
+            d.t_in[s].release();
+            d.t_out[s].release();
+            d.t_unm[s].release();
+            d.t_sizes[s].release();
+            cudaEventDestroy(d.ev_h2d[s]);
+            cudaEventDestroy(d.ev_comp[s]);
+            cudaEventDestroy(d.ev_d2h[s]);
+        }
+        d.h_sizes.release();
+        d.a_lifted.release();
+        d.a_unm.release();
+        cudaStreamDestroy(d.s_h2d);
+        cudaStreamDestroy(d.s_comp);
+        cudaStreamDestroy(d.s_d2h);
+    }
+    for (PinBuf *b : {&c->r_lifted, &c->r_unm, &c->r_off, &c->r_rows, &c->r_thick}) b->release();
+    delete c;
+}
+
+const char *swo_last_error(const swo_ctx *c) { return c ? c->err.c_str() : "null ctx"; }
+uint64_t swo_launch_count(const swo_ctx *c) { return c ? c->launches : 0; }
+
+void *swo_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) return nullptr;
+    return p;
+}
+void swo_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+int swo_set_option(swo_ctx *c, const char *key, int64_t value) {
+    if (!c || !key) return SWO_E_ARG;
+    if (!strcmp(key, "chunk_bytes")) {
+        if (value < 64) return fail(c, SWO_E_ARG, "chunk_bytes must be >= 64");
+        c->chunk_bytes = (size_t)value;
+        return SWO_OK;
+    }
+    return fail(c, SWO_E_ARG, "unknown option %s", key);
+}
+
+// ---- chain ------------------------------------------------------------------------
+int swo_load_chain_mem(swo_ctx *c, const char *text, size_t len) {
+    if (!c || (!text && len)) return SWO_E_ARG;
+    std::string err;
+    ChainTable t;
+    if (!parse_chain_text(std::string_view(text, len), t, err)) return fail(c, SWO_E_PARSE, "%s", err.c_str());
+    c->tab = std::move(t);
+    c->have_chain = false;
+    for (Device &d : c->dev) {
+        int rc = upload_table(c, d);
+        if (rc) return rc;
+    }
+    c->have_chain = true;
+    return SWO_OK;
+}
+
+int swo_load_chain(swo_ctx *c, const char *path) {
+    if (!c || !path) return SWO_E_ARG;
+    std::ifstream f(path, std::ios::binary);
+    if (!f) return fail(c, SWO_E_IO, "File does not exist: %s", path);  // chain.d:513-514
+    std::string text((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    return swo_load_chain_mem(c, text.data(), text.size());
+}
+
+int swo_num_tcontigs(const swo_ctx *c) { return c ? c->tab.ntc() : 0; }
+const char *swo_tcontig_name(const swo_ctx *c, int i) {
+    return (c && i >= 0 && i < c->tab.ntc()) ? c->tab.tnames[i].c_str() : nullptr;
+}
+int swo_tcontig_id(const swo_ctx *c, const char *name, size_t len) {
+    return c ? c->tab.tcontig_id(std::string_view(name, len)) : -1;
+}
+int64_t swo_tcontig_nblocks(const swo_ctx *c, int i) {
+    return (c && i >= 0 && i < c->tab.ntc()) ? (int64_t)c->tab.toff[i + 1] - c->tab.toff[i] : 0;
+}
+int64_t swo_tcontig_size(const swo_ctx *c, int i) {
+    return (c && i >= 0 && i < c->tab.ntc()) ? c->tab.tsizes[i] : -1;
+}
+int64_t swo_num_blocks(const swo_ctx *c) { return c ? c->tab.nblocks() : 0; }
+int swo_table_is_disjoint(const swo_ctx *c) { return c && c->tab.disjoint; }
+int swo_num_qcontigs(const swo_ctx *c) { return c ? (int)c->tab.qnames.size() : 0; }
+const char *swo_qcontig_name(const swo_ctx *c, int i) {
+    return (c && i >= 0 && i < (int)c->tab.qnames.size()) ? c->tab.qnames[i].c_str() : nullptr;
+}
+int swo_num_qsizes(const swo_ctx *c) { return c ? (int)c->tab.qsizes.size() : 0; }
+const char *swo_qsize_name(const swo_ctx *c, int i) {
+    return (c && i >= 0 && i < (int)c->tab.qsizes.size()) ? c->tab.qsizes[i].first.c_str() : nullptr;
+}
+int64_t swo_qsize_value(const swo_ctx *c, int i) {
+    return (c && i >= 0 && i < (int)c->tab.qsizes.size()) ? c->tab.qsizes[i].second : -1;
+}
+
+int swo_get_blocks(const swo_ctx *c, int tcid, int64_t first, int64_t n, int32_t *ts, int32_t *te, int32_t *qs,
+                   int32_t *qcid, int8_t *inv) {
+    if (!c || tcid < 0 || tcid >= c->tab.ntc()) return SWO_E_ARG;
+    const int64_t a = c->tab.toff[tcid], b = c->tab.toff[tcid + 1];
+    if (first < 0 || n < 0 || a + first + n > b) return SWO_E_ARG;
+    for (int64_t i = 0; i < n; i++) {
+        const Block &k = c->tab.blocks[a + first + i];
+        if (ts) ts[i] = k.tStart;
+        if (te) te[i] = k.tEnd;
+        if (qs) qs[i] = k.qStart;
+        if (qcid) qcid[i] = k.meta >> 1;
+        if (inv) inv[i] = (k.meta & 1) ? -1 : 1;
+    }
+    return SWO_OK;
+}
+
+// ---- binary lift --------------------------------------------------------------------
+int swo_lift_intervals_dev(swo_ctx *c, size_t n, const int32_t *d_tcid, const int32_t *d_start, const int32_t *d_end,
+                           const uint8_t *d_strand, const int32_t *d_ths, const int32_t *d_the,
+                           uint32_t *d_row_offset, swo_row *d_rows, swo_thick *d_thick, size_t rows_cap,
+                           uint64_t *d_totals, void *stream) {
+    if (!c) return SWO_E_ARG;
+    if (c->dev.empty()) return fail(c, SWO_E_CUDA, "inspection-only context: no CUDA device, and there is no CPU fallback");
+    if (!c->have_chain) return fail(c, SWO_E_STATE, "no chain loaded");
+    if (n >= 0xFFFFFFFFull) return fail(c, SWO_E_ARG, "n must be < 2^32-1 per call");
+    if ((d_ths == nullptr) != (d_the == nullptr) || (d_ths && !d_thick)) return fail(c, SWO_E_ARG, "thick arrays");
+    if (!aligned16(d_tcid) || !aligned16(d_start) || !aligned16(d_end) || !aligned16(d_row_offset) ||
+        !aligned16(d_rows))
+        return fail(c, SWO_E_ARG, "device arrays must be 16-byte aligned");
+    Device &d = c->dev[0];
+    CK(c, cudaSetDevice(d.ordinal));
+    return launch_lift_intervals(c, d, n, d_tcid, d_start, d_end, d_strand, d_ths, d_the, d_row_offset, d_rows,
+                                 d_thick, rows_cap, d_totals, (cudaStream_t)stream);
+}
+
+int swo_lift_intervals(swo_ctx *c, size_t n, const int32_t *tcid, const int32_t *start, const int32_t *end,
+                       const uint8_t *strand, const int32_t *ths, const int32_t *the, swo_lifted *out) {
+    if (!c || !out) return SWO_E_ARG;
+    memset(out, 0, sizeof *out);
+    if (c->dev.empty()) return fail(c, SWO_E_CUDA, "inspection-only context: no CUDA device, and there is no CPU fallback");
+    if (!c->have_chain) return fail(c, SWO_E_STATE, "no chain loaded");
+    if (n >= 0xFFFFFFFFull) return fail(c, SWO_E_ARG, "n must be < 2^32-1 per call");
+    if ((ths == nullptr) != (the == nullptr)) return fail(c, SWO_E_ARG, "thick_start and thick_end go together");
+    Device &d = c->dev[0];
+    CK(c, cudaSetDevice(d.ordinal));
+    cudaStream_t st = d.s_comp;
+    // device input block: [tcid][start][end][thick_s][thick_e][strand], each 16-byte aligned
+    const size_t na = (n * 4 + 15) & ~(size_t)15;
+    const size_t total_in = na * 5 + ((n + 15) & ~(size_t)15) + 16;
+    CK(c, d.b_in.reserve(total_in));
+    char *base = d.b_in.as<char>();
+    int32_t *d_tcid = (int32_t *)base, *d_start = (int32_t *)(base + na), *d_end = (int32_t *)(base + 2 * na);
+    int32_t *d_ths = ths ? (int32_t *)(base + 3 * na) : nullptr, *d_the = ths ? (int32_t *)(base + 4 * na) : nullptr;
+    uint8_t *d_strand = strand ? (uint8_t *)(base + 5 * na) : nullptr;
+    if (n) {
+        CK(c, cudaMemcpyAsync(d_tcid, tcid, n * 4, cudaMemcpyHostToDevice, st));
+        CK(c, cudaMemcpyAsync(d_start, start, n * 4, cudaMemcpyHostToDevice, st));
+        CK(c, cudaMemcpyAsync(d_end, end, n * 4, cudaMemcpyHostToDevice, st));
+        if (ths) {
+            CK(c, cudaMemcpyAsync(d_ths, ths, n * 4, cudaMemcpyHostToDevice, st));
+            CK(c, cudaMemcpyAsync(d_the, the, n * 4, cudaMemcpyHostToDevice, st));
+        }
+        if (strand) CK(c, cudaMemcpyAsync(d_strand, strand, n, cudaMemcpyHostToDevice, st));
+    }
+    CK(c, d.b_off.reserve((n + 1) * 4 + 16));
+    CK(c, d.b_tot.reserve(16));
+    size_t cap = std::max(d.b_rows.cap / sizeof(swo_row), n + (n >> 2) + 1024);
+    uint64_t tot[2] = {0, 0};
+    for (int attempt = 0; attempt < 2; attempt++) {
+        CK(c, d.b_rows.reserve(cap * sizeof(swo_row)));
+        if (ths) CK(c, d.b_thick.reserve(cap * sizeof(swo_thick)));
+        int rc = launch_lift_intervals(c, d, n, d_tcid, d_start, d_end, d_strand, d_ths, d_the, d.b_off.as<uint32_t>(),
+                                       d.b_rows.as<swo_row>(), ths ? d.b_thick.as<swo_thick>() : nullptr, cap,
+                                       d.b_tot.as<uint64_t>(), st);
+        if (rc) return rc;
+        CK(c, cudaMemcpyAsync(tot, d.b_tot.p, 16, cudaMemcpyDeviceToHost, st));
+        CK(c, cudaStreamSynchronize(st));
+        if (tot[0] <= cap) break;
+        if (tot[0] > 0xFFFFFFFFull) return fail(c, SWO_E_ARG, "more than 2^32 rows in one call; split the batch");
+        cap = (size_t)tot[0];
+    }
+    CK(c, c->r_off.reserve((n + 1) * 4));
+    CK(c, c->r_rows.reserve(std::max<size_t>(tot[0], 1) * sizeof(swo_row)));
+    if (ths) CK(c, c->r_thick.reserve(std::max<size_t>(tot[0], 1) * sizeof(swo_thick)));
+    CK(c, cudaMemcpyAsync(c->r_off.p, d.b_off.p, (n + 1) * 4, cudaMemcpyDeviceToHost, st));
+    if (tot[0]) {
+        CK(c, cudaMemcpyAsync(c->r_rows.p, d.b_rows.p, tot[0] * sizeof(swo_row), cudaMemcpyDeviceToHost, st));
+        if (ths) CK(c, cudaMemcpyAsync(c->r_thick.p, d.b_thick.p, tot[0] * sizeof(swo_thick), cudaMemcpyDeviceToHost, st));
+    }
+    CK(c, cudaStreamSynchronize(st));
+    out->n_rows = tot[0];
+    out->n_unmatched = tot[1];
+    out->row_offset = c->r_off.as<uint32_t>();
+    out->rows = c->r_rows.as<swo_row>();
+    out->thick = ths ? c->r_thick.as<swo_thick>() : nullptr;
+    return SWO_OK;
+}
+
+int swo_lift_points(swo_ctx *c, size_t n, const int32_t *tcid, const int32_t *pos, int32_t *out_qcid,
+                    int32_t *out_pos, uint8_t *hit) {
+    if (!c || (n && (!tcid || !pos || !out_qcid || !out_pos || !hit))) return SWO_E_ARG;
+    if (c->dev.empty()) return fail(c, SWO_E_CUDA, "inspection-only context: no CUDA device, and there is no CPU fallback");
+    if (!c->have_chain) return fail(c, SWO_E_STATE, "no chain loaded");
+    if (n >= 0xFFFFFFFFull) return fail(c, SWO_E_ARG, "n must be < 2^32-1 per call");
+    if (!n) return SWO_OK;
+    Device &d = c->dev[0];
+    CK(c, cudaSetDevice(d.ordinal));
+    cudaStream_t st = d.s_comp;
+    const size_t na = (n * 4 + 15) & ~(size_t)15;
+    CK(c, d.b_in.reserve(na * 4 + n + 16));
+    char *base = d.b_in.as<char>();
+    int32_t *d_tcid = (int32_t *)base, *d_pos = (int32_t *)(base + na), *d_oq = (int32_t *)(base + 2 * na),
+            *d_op = (int32_t *)(base + 3 * na);
+    uint8_t *d_hit = (uint8_t *)(base + 4 * na);
+    CK(c, cudaMemcpyAsync(d_tcid, tcid, n * 4, cudaMemcpyHostToDevice, st));
+    CK(c, cudaMemcpyAsync(d_pos, pos, n * 4, cudaMemcpyHostToDevice, st));
+    const int grid = (int)std::min<size_t>((n + 255) / 256, (size_t)d.sms * 8);
+    lift_points_kernel<<<grid, 256, 0, st>>>(d.T, (uint32_t)n, d_tcid, d_pos, d_oq, d_op, d_hit);
+    c->launches++;
+    CK(c, cudaGetLastError());
+    CK(c, cudaMemcpyAsync(out_qcid, d_oq, n * 4, cudaMemcpyDeviceToHost, st));
+    CK(c, cudaMemcpyAsync(out_pos, d_op, n * 4, cudaMemcpyDeviceToHost, st));
+    CK(c, cudaMemcpyAsync(hit, d_hit, n, cudaMemcpyDeviceToHost, st));
+    CK(c, cudaStreamSynchronize(st));
+    return SWO_OK;
+}
+
+// ---- text lift ------------------------------------------------------------------------
+int swo_lift_bed_text_dev(swo_ctx *c, const char *d_in, size_t in_len, char *d_lifted, size_t lifted_cap,
+                          char *d_unm, size_t unm_cap, uint64_t *d_sizes, void *stream) {
+    if (!c || !d_sizes || (in_len && (!d_in || !d_lifted || !d_unm))) return SWO_E_ARG;
+    if (c->dev.empty()) return fail(c, SWO_E_CUDA, "inspection-only context: no CUDA device, and there is no CPU fallback");
+    if (!c->have_chain) return fail(c, SWO_E_STATE, "no chain loaded");
+    if (!aligned16(d_in)) return fail(c, SWO_E_ARG, "d_in must be 16-byte aligned");
+    Device &d = c->dev[0];
+    CK(c, cudaSetDevice(d.ordinal));
+    return launch_lift_text(c, d, d_in, in_len, d_lifted, lifted_cap, d_unm, unm_cap, d_sizes, (cudaStream_t)stream);
+}
+
+int swo_lift_bed_text(swo_ctx *c, const char *in, size_t in_len, swo_text_out *out) {
+    if (!c || !out || (in_len && !in)) return SWO_E_ARG;
+    memset(out, 0, sizeof *out);
+    if (c->dev.empty()) return fail(c, SWO_E_CUDA, "inspection-only context: no CUDA device, and there is no CPU fallback");
+    if (!c->have_chain) return fail(c, SWO_E_STATE, "no chain loaded");
+    const int nd = (int)c->dev.size();
+    // byte-range shards; a shard owns the lines that start inside it
+    std::vector<size_t> cut(nd + 1, in_len);
+    cut[0] = 0;
+    for (int k = 1; k < nd; k++) {
+        size_t e = (size_t)((unsigned __int128)in_len * (unsigned)k / (unsigned)nd);
+        e = std::max(e, cut[k - 1]);
+        while (e < in_len && e > 0 && in[e - 1] != '\n') e++;
+        cut[k] = e;
+    }
+    std::vector<ShardResult> res(nd);
+    CK(c, c->r_lifted.reserve(in_len + (in_len >> 2) + 4096));
+    CK(c, c->r_unm.reserve(in_len / 4 + 4096));
+    if (nd == 1) {
+        int rc = run_shard(c, c->dev[0], in, 0, in_len, &c->r_lifted, 0, &c->r_unm, 0, res[0]);
+        if (rc) return rc;
+    } else {
+        // one host thread per shard; each streams into its own pinned arena, then the
+        // arenas are concatenated in shard order (== single-device output order)
+        std::vector<std::thread> th;
+        std::vector<std::string> emsg(nd);
+        for (int k = 0; k < nd; k++) {
+            th.emplace_back([&, k]() {
+                swo_ctx local;  // private error sink; run_shard only touches err/launches/chunk_bytes
+                local.chunk_bytes = c->chunk_bytes;
+                Device &d = c->dev[k];
+                res[k].rc = run_shard(&local, d, in, cut[k], cut[k + 1], &d.a_lifted, 0, &d.a_unm, 0, res[k]);
+                emsg[k] = local.err;
+                __atomic_fetch_add(&c->launches, local.launches, __ATOMIC_RELAXED);
+            });
+        }
+        for (auto &t : th) t.join();
+        size_t tl = 0, tu = 0;
+        for (int k = 0; k < nd; k++) {
+            if (res[k].rc) return fail(c, res[k].rc, "%s", emsg[k].c_str());
+            tl += res[k].lifted;
+            tu += res[k].unm;
+        }
+        CK(c, c->r_lifted.reserve(tl + 1));
+        CK(c, c->r_unm.reserve(tu + 1));
+        size_t ol = 0, ou = 0;
+        for (int k = 0; k < nd; k++) {
+            memcpy(c->r_lifted.as<char>() + ol, c->dev[k].a_lifted.p, res[k].lifted);
+            memcpy(c->r_unm.as<char>() + ou, c->dev[k].a_unm.p, res[k].unm);
+            ol += res[k].lifted;
+            ou += res[k].unm;
+        }
+    }
+    for (int k = 0; k < nd; k++) {
+        if (res[k].has_err)
+            return fail(c, SWO_E_PARSE, "BED line at byte %llu has fewer than 3 fields or a non-integer coordinate",
+                        (unsigned long long)res[k].err_off);
+        out->lifted_len += res[k].lifted;
+        out->unmatched_len += res[k].unm;
+        out->n_records += res[k].rec;
+        out->n_rows += res[k].rows;
+        out->n_unmatched += res[k].nunm;
+    }
+    out->lifted = c->r_lifted.as<char>();
+    out->unmatched = c->r_unm.as<char>();
+    return SWO_OK;
+}
+
+// ---- VCF --------------------------------------------------------------------------------
+int swo_load_genome_2bit(swo_ctx *c, const uint8_t *packed, size_t packed_bytes, const int64_t *contig_off,
+                         const int64_t *contig_len, int n_contigs) {
+    if (!c || !packed || !contig_off || !contig_len || n_contigs <= 0) return SWO_E_ARG;
+    for (Device &d : c->dev) {
+        CK(c, cudaSetDevice(d.ordinal));
+        int rc;
+        CK(c, d.g_packed.reserve(packed_bytes + 16));
+        CK(c, cudaMemcpyAsync(d.g_packed.p, packed, packed_bytes, cudaMemcpyHostToDevice, d.s_comp));
+        if ((rc = upload(c, d.g_off, contig_off, (size_t)n_contigs, d.s_comp))) return rc;
+        if ((rc = upload(c, d.g_len, contig_len, (size_t)n_contigs, d.s_comp))) return rc;
+        CK(c, cudaStreamSynchronize(d.s_comp));
+        d.g_n = n_contigs;
+    }
+    return SWO_OK;
+}
+
+int swo_lift_vcf_points(swo_ctx *c, size_t n, const int32_t *tcid, const int32_t *pos, const int32_t *reflen,
+                        const uint64_t *ref_off, const char *ref_bytes, size_t ref_bytes_len, int32_t *out_qcid,
+                        int32_t *out_pos, uint8_t *flags, int32_t *out_reflen, char *out_ref) {
+    if (!c || (n && (!tcid || !pos || !reflen || !ref_off || !out_qcid || !out_pos || !flags || !out_reflen)))
+        return SWO_E_ARG;
+    if (c->dev.empty()) return fail(c, SWO_E_CUDA, "inspection-only context: no CUDA device, and there is no CPU fallback");
+    if (!c->have_chain) return fail(c, SWO_E_STATE, "no chain loaded");
+    Device &d = c->dev[0];
+    if (!d.g_n) return fail(c, SWO_E_STATE, "no genome loaded");
+    if (n >= 0xFFFFFFFFull) return fail(c, SWO_E_ARG, "n must be < 2^32-1 per call");
+    if (!n) return SWO_OK;
+    CK(c, cudaSetDevice(d.ordinal));
+    cudaStream_t st = d.s_comp;
+    const size_t na = (n * 4 + 15) & ~(size_t)15, n8 = (n * 8 + 15) & ~(size_t)15,
+                 nr = (ref_bytes_len + 15) & ~(size_t)15;
+    CK(c, d.b_in.reserve(na * 6 + n8 + 2 * nr + n + 64));
+    char *base = d.b_in.as<char>();
+    int32_t *d_tcid = (int32_t *)base, *d_pos = (int32_t *)(base + na), *d_rl = (int32_t *)(base + 2 * na),
+            *d_oq = (int32_t *)(base + 3 * na), *d_op = (int32_t *)(base + 4 * na), *d_orl = (int32_t *)(base + 5 * na);
+    uint64_t *d_ro = (uint64_t *)(base + 6 * na);
+    char *d_ref = base + 6 * na + n8, *d_oref = d_ref + nr;
+    uint8_t *d_fl = (uint8_t *)(d_oref + nr);
+    CK(c, cudaMemcpyAsync(d_tcid, tcid, n * 4, cudaMemcpyHostToDevice, st));
+    CK(c, cudaMemcpyAsync(d_pos, pos, n * 4, cudaMemcpyHostToDevice, st));
+    CK(c, cudaMemcpyAsync(d_rl, reflen, n * 4, cudaMemcpyHostToDevice, st));
+    CK(c, cudaMemcpyAsync(d_ro, ref_off, n * 8, cudaMemcpyHostToDevice, st));
+    if (ref_bytes_len) CK(c, cudaMemcpyAsync(d_ref, ref_bytes, ref_bytes_len, cudaMemcpyHostToDevice, st));
+    VcfArgs A;
+    A.T = d.T;
+    A.packed = d.g_packed.as<uint8_t>();
+    A.g_off = d.g_off.as<int64_t>();
+    A.g_len = d.g_len.as<int64_t>();
+    A.g_n = d.g_n;
+    A.n = (uint32_t)n;
+    A.tcid = d_tcid;
+    A.pos = d_pos;
+    A.reflen = d_rl;
+    A.ref_off = d_ro;
+    A.ref = d_ref;
+    A.out_qcid = d_oq;
+    A.out_pos = d_op;
+    A.flags = d_fl;
+    A.out_reflen = d_orl;
+    A.out_ref = d_oref;
+    const int grid = (int)std::min<size_t>((n + 255) / 256, (size_t)d.sms * 8);
+    lift_vcf_points_kernel<<<grid, 256, 0, st>>>(A);
+    c->launches++;
+    CK(c, cudaGetLastError());
+    CK(c, cudaMemcpyAsync(out_qcid, d_oq, n * 4, cudaMemcpyDeviceToHost, st));
+    CK(c, cudaMemcpyAsync(out_pos, d_op, n * 4, cudaMemcpyDeviceToHost, st));
+    CK(c, cudaMemcpyAsync(out_reflen, d_orl, n * 4, cudaMemcpyDeviceToHost, st));
+    CK(c, cudaMemcpyAsync(flags, d_fl, n, cudaMemcpyDeviceToHost, st));
+    if (out_ref && ref_bytes_len) CK(c, cudaMemcpyAsync(out_ref, d_oref, ref_bytes_len, cudaMemcpyDeviceToHost, st));
+    CK(c, cudaStreamSynchronize(st));
+    return SWO_OK;
+}
+
+}  // extern "C"
+
+int swo_internal_tname_table(swo_ctx *c, const uint32_t **d_off, const char **d_chars) {
+    if (!c) return SWO_E_ARG;
+    if (c->dev.empty()) return fail(c, SWO_E_CUDA, "inspection-only context: no CUDA device, and there is no CPU fallback");
+    if (!c->have_chain) return fail(c, SWO_E_STATE, "no chain loaded");
+    *d_off = c->dev[0].tnoff.as<uint32_t>();
+    *d_chars = c->dev[0].tchars.as<char>();
+    return SWO_OK;
+}

@@ -99,6 +99,8 @@ class Oracle:
         L.orc_lift_intervals.argtypes = [C.c_void_p, C.c_size_t] + [C.c_void_p] * 6 + [C.POINTER(OrcRows)]
         L.orc_rows_free.argtypes = [C.POINTER(OrcRows)]
         L.orc_lift_vcf_points.argtypes = [C.c_void_p] * 4 + [C.c_int, C.c_size_t] + [C.c_void_p] * 10
+        L.orc_format_bed3.restype = C.c_size_t
+        L.orc_format_bed3.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
         L.orc_link_qend.restype = C.c_int64
         L.orc_link_qend.argtypes = [C.POINTER(OrcLink)]
         L.orc_link_size.restype = C.c_int64
@@ -214,6 +216,19 @@ class OracleChain:
         if rc:
             raise OracleError(rc, err.value.decode())
         return res
+
+    def format_bed3(self, tcid, start, end):
+        """bench helper: BED3 text (numpy uint8 array) of the records."""
+        tcid = np.ascontiguousarray(tcid, np.int32)
+        start = np.ascontiguousarray(start, np.int32)
+        end = np.ascontiguousarray(end, np.int32)
+        out = np.empty(len(tcid) * 64 + 64, np.uint8)
+        m = self.L.orc_format_bed3(self.h, len(tcid), tcid.ctypes.data, start.ctypes.data, end.ctypes.data,
+                                   out.ctypes.data, out.nbytes)
+        return out[:m]
+
+    def tcontig_size_from(self, sizes_by_name):
+        return [sizes_by_name[n] for n in self.tcontigs]
 
     def lift_intervals(self, tcid, start, end, strand=None, thick_start=None, thick_end=None):
         tcid = np.ascontiguousarray(tcid, np.int32)
