@@ -189,7 +189,7 @@ void *swo_host_alloc(size_t bytes);
 void swo_host_free(void *p);
 
 /* tuning knobs: "chunk_bytes" = bytes of text per H2D/kernel/D2H pipeline stage
- * (default 64 MiB; the tests shrink it to exercise chunk boundaries) */
+ * (default 32 MiB, 4 in flight; the tests shrink it to exercise chunk boundaries) */
 int swo_set_option(swo_ctx *ctx, const char *key, int64_t value);
 
 /* number of kernel launches issued by this ctx since creation (bench.py's

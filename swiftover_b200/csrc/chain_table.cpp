@@ -159,6 +159,39 @@ int ChainTable::tcontig_id(std::string_view name) const {
     return it == tindex.end() ? -1 : it->second;
 }
 
+// In-order fill of the implicit tree rooted at k (1-based) over m sorted samples.
+static void ey_fill(const ChainTable &tab, int a, int S, int m, int k, int &next, int32_t *key, int32_t *idx) {
+    if (k > m) return;
+    ey_fill(tab, a, S, m, 2 * k, next, key, idx);
+    const int j = a + next * S + S - 1;
+    key[k - 1] = tab.pmaxKey[j];
+    idx[k - 1] = j;
+    next++;
+    ey_fill(tab, a, S, m, 2 * k + 1, next, key, idx);
+}
+
+static void build_eytzinger(ChainTable &tab) {
+    int sh = 0;
+    for (;; sh++) {
+        size_t tot = 0;
+        for (int c = 0; c < tab.ntc(); c++) tot += (size_t)(tab.toff[c + 1] - tab.toff[c]) >> sh;
+        if (tot <= (size_t)ChainTable::EY_CAP) break;
+    }
+    tab.eyShift = sh;
+    tab.eyKey.clear();
+    tab.eyIdx.clear();
+    tab.eyoff.assign(1, 0);
+    for (int c = 0; c < tab.ntc(); c++) {
+        const int a = tab.toff[c], m = (tab.toff[c + 1] - a) >> sh;
+        const size_t base = tab.eyKey.size();
+        tab.eyKey.resize(base + m);
+        tab.eyIdx.resize(base + m);
+        int next = 0;
+        ey_fill(tab, a, 1 << sh, m, 1, next, tab.eyKey.data() + base, tab.eyIdx.data() + base);
+        tab.eyoff.push_back((int32_t)tab.eyKey.size());
+    }
+}
+
 bool parse_chain_text(std::string_view text, ChainTable &tab, std::string &err) {
     tab = ChainTable();
     // byLineCopy (chain.d:520): '\n'-terminated, no empty line after a final '\n'
@@ -217,6 +250,7 @@ bool parse_chain_text(std::string_view text, ChainTable &tab, std::string &err) 
         }
         tab.toff.push_back((int32_t)tab.blocks.size());
     }
+    build_eytzinger(tab);
     return true;
 }
 

@@ -35,6 +35,16 @@ struct ChainTable {
     std::vector<int32_t> pmaxKey;   // [B] prefix max of tEnd inside the contig
     bool disjoint = true;           // no two blocks of a contig overlap
 
+    // Upper search levels (staged in shared memory by the kernels): for every
+    // contig the maxima pmaxKey[a + i*S + S-1] of its full groups of S = 1<<eyShift
+    // consecutive blocks, stored in Eytzinger (BFS) order as {key, block index}
+    // pairs at ey[eyoff[c] ...].  S is the smallest power of two for which all
+    // samples fit in EY_CAP entries.
+    static constexpr int EY_CAP = 2048;
+    int eyShift = 0;
+    std::vector<int32_t> eyKey, eyIdx;  // [nsamples] each
+    std::vector<int32_t> eyoff;         // [ntc+1]
+
     // destination ("query") contigs: ChainFile.contigNames (chain.d:500)
     std::vector<std::string> qnames;
     // ChainFile.qContigSizes (chain.d:504), first-insertion order

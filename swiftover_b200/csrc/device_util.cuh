@@ -78,18 +78,19 @@ __device__ __forceinline__ T block_exclusive_scan(T v, T *scratch, T *total) {
 constexpr uint64_t LB_EMPTY = 0ull, LB_AGG = 1ull << 62, LB_INC = 2ull << 62;
 constexpr uint64_t LB_STATE = 3ull << 62, LB_VALUE = ~LB_STATE;
 
-// Called by ONE full warp.  Publishes this tile's aggregate, walks the
-// predecessors' descriptors 32 at a time until an inclusive prefix is found,
-// publishes the inclusive prefix and returns the EXCLUSIVE prefix (all lanes).
-// Tiles must have been handed out by an atomic ticket so that every
-// predecessor is already running (forward progress).
-__device__ __forceinline__ uint64_t lookback_exclusive(uint64_t *desc, int tile, uint64_t aggregate) {
+// Called by ONE full warp, in two steps so that a tile can publish its aggregate
+// as soon as it is known and resolve its own prefix later (successors then never
+// wait on this tile's remaining work).  Tiles must have been handed out by an
+// atomic ticket so that every predecessor is already running (forward progress).
+__device__ __forceinline__ void lookback_publish(uint64_t *desc, int tile, uint64_t aggregate) {
+    if (lane_id() == 0) st_relaxed_u64(desc + tile, (tile == 0 ? LB_INC : LB_AGG) | aggregate);
+}
+// Walks the predecessors' descriptors 32 at a time until an inclusive prefix is
+// found, publishes this tile's inclusive prefix and returns the EXCLUSIVE prefix
+// (all lanes).
+__device__ __forceinline__ uint64_t lookback_resolve(uint64_t *desc, int tile, uint64_t aggregate) {
     const int lane = lane_id();
-    if (tile == 0) {
-        if (lane == 0) st_relaxed_u64(desc, LB_INC | aggregate);
-        return 0;
-    }
-    if (lane == 0) st_relaxed_u64(desc + tile, LB_AGG | aggregate);
+    if (tile == 0) return 0;
     uint64_t excl = 0;
     int look = tile - 1;
     for (;;) {
@@ -111,6 +112,10 @@ __device__ __forceinline__ uint64_t lookback_exclusive(uint64_t *desc, int tile,
     }
     if (lane == 0) st_relaxed_u64(desc + tile, LB_INC | (excl + aggregate));
     return excl;
+}
+__device__ __forceinline__ uint64_t lookback_exclusive(uint64_t *desc, int tile, uint64_t aggregate) {
+    lookback_publish(desc, tile, aggregate);
+    return lookback_resolve(desc, tile, aggregate);
 }
 
 }  // namespace swo

@@ -48,13 +48,13 @@ struct LiftArgs {
 // position (rank by (key, candidate index)), the cumulative strand byte and
 // the thick clamp, and writes its row.  Work is strided by (first, stride) so
 // the same code serves one thread, one warp or one block.
-__device__ __forceinline__ void expand_query(const LiftArgs &A, uint32_t q, int lo, int ncand, uint64_t rowbase,
-                                             int first, int stride) {
+__device__ __forceinline__ void expand_query(const LiftArgs &A, const int2 *ey, uint32_t q, int lo, int ncand,
+                                             uint64_t rowbase, int first, int stride) {
     const TableView &T = A.T;
     const int start = __ldg(A.start + q), end = __ldg(A.end + q);
     const unsigned char orig = A.strand ? __ldg(A.strand + q) : 0;
     Thick th{0, 0, 0};
-    if (A.thick_s) th = lift_thick(T, __ldg(A.tcid + q), __ldg(A.thick_s + q), __ldg(A.thick_e + q));
+    if (A.thick_s) th = lift_thick(T, ey, __ldg(A.tcid + q), __ldg(A.thick_s + q), __ldg(A.thick_e + q));
     for (int c = first; c < ncand; c += stride) {
         const Block bj = load_block(T, lo + c);
         if (!T.disjoint && !block_hits(bj, start)) continue;
@@ -102,9 +102,12 @@ __global__ void __launch_bounds__(LI_TPB) lift_intervals_kernel(const LiftArgs A
     __shared__ int s_wl_lo[LI_WL_CAP];
     __shared__ int s_wl_cnt[LI_WL_CAP];
     __shared__ uint32_t s_wl_off[LI_WL_CAP];
+    __shared__ int2 s_ey[ChainTable::EY_CAP];  // upper search levels (Eytzinger order)
 
     const int tid = threadIdx.x;
     const TableView &T = A.T;
+    for (int i = tid; i < T.ey_n; i += LI_TPB) s_ey[i] = __ldg(T.ey + i);
+    const int2 *const ey = s_ey;
 
     for (;;) {
         __syncthreads();
@@ -137,7 +140,7 @@ __global__ void __launch_bounds__(LI_TPB) lift_intervals_kernel(const LiftArgs A
         uint32_t tsum = 0, unm = 0;
 #pragma unroll
         for (int k = 0; k < LI_IPT; k++) {
-            cd[k] = find_candidates(T, tc[k], st[k], en[k]);
+            cd[k] = find_candidates(T, ey, tc[k], st[k], en[k]);
             nh[k] = count_hits(T, cd[k], st[k]);
             tsum += (uint32_t)nh[k];
             unm += (q0 + k < A.n && nh[k] == 0) ? 1u : 0u;
@@ -191,7 +194,7 @@ __global__ void __launch_bounds__(LI_TPB) lift_intervals_kernel(const LiftArgs A
                     const unsigned char sb = A.strand ? strand_flip(__ldg(A.strand + q), r.inv) : 0;
                     st_stream_v4(A.rows + run64, make_int4(r.qcid | ((int)sb << 16), r.s, r.e, (int)q));
                     if (A.thick_s) {
-                        const Thick th = lift_thick(T, tc[k], __ldg(A.thick_s + q), __ldg(A.thick_e + q));
+                        const Thick th = lift_thick(T, ey, tc[k], __ldg(A.thick_s + q), __ldg(A.thick_e + q));
                         swo_thick t;
                         thick_clamp(th, r.s, r.e, t.thick_start, t.thick_end);
                         A.thick[run64] = t;
@@ -206,7 +209,7 @@ __global__ void __launch_bounds__(LI_TPB) lift_intervals_kernel(const LiftArgs A
                     s_wl_off[slot] = (uint32_t)(run64 - gbase);
                 } else {
                     // work list full: expand serially in this thread
-                    expand_query(A, q, cd[k].lo, cd[k].hi - cd[k].lo, run64, 0, 1);
+                    expand_query(A, ey, q, cd[k].lo, cd[k].hi - cd[k].lo, run64, 0, 1);
                 }
             }
             run64 += (uint64_t)nh[k];
@@ -216,12 +219,12 @@ __global__ void __launch_bounds__(LI_TPB) lift_intervals_kernel(const LiftArgs A
         // light and medium fan-out: one warp per query
         for (int e = warp_id(); e < nwl; e += LI_NW) {
             if (s_wl_cnt[e] < LI_HEAVY_MIN)
-                expand_query(A, s_wl_q[e], s_wl_lo[e], s_wl_cnt[e], gbase + s_wl_off[e], lane_id(), 32);
+                expand_query(A, ey, s_wl_q[e], s_wl_lo[e], s_wl_cnt[e], gbase + s_wl_off[e], lane_id(), 32);
         }
         // heavy fan-out: the whole block per query
         for (int e = 0; e < nwl; e++) {
             if (s_wl_cnt[e] >= LI_HEAVY_MIN)
-                expand_query(A, s_wl_q[e], s_wl_lo[e], s_wl_cnt[e], gbase + s_wl_off[e], tid, LI_TPB);
+                expand_query(A, ey, s_wl_q[e], s_wl_lo[e], s_wl_cnt[e], gbase + s_wl_off[e], tid, LI_TPB);
         }
     }
 }
@@ -232,7 +235,7 @@ __global__ void __launch_bounds__(256) lift_points_kernel(const TableView T, uin
                                                           int32_t *__restrict__ out_pos, uint8_t *__restrict__ hit) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int c = pos[i];
-        const int j = point_hit(T, tcid[i], c);
+        const int j = point_hit(T, T.ey, tcid[i], c);
         if (j < 0) {
             out_qcid[i] = -1;
             out_pos[i] = c;

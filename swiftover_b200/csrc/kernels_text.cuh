@@ -9,15 +9,28 @@
 //   unmatched: fields joined by '\t'               bed.d:150-151
 //   rows sorted by qStart, strand table, thick clamp, joined by '\t'   bed.d:156-199
 //
-// ONE persistent kernel, every input byte read once from HBM and every output
-// byte written once.  A tile is 16 KiB of input text staged in shared memory
-// with 128-bit loads; a tile owns the lines that START inside it.  Each thread
-// owns the lines starting in its 64-byte segment.  Pass A parses + searches and
-// sums the exact output byte counts of both streams; the tile aggregates are
-// chained with a decoupled look-back (two independent chains, one per output
-// stream); pass B formats into a shared-memory stage that is then copied out
-// with aligned 128-bit stores.  Lines with >= 2 hits are expanded cooperatively
-// (warp / block), each row computing its own sorted position and byte offset.
+// ONE persistent kernel; every input byte is read from HBM once and every output
+// byte written once.  A tile is 16 KiB of text staged in shared memory with
+// 128-bit loads; a tile owns the lines that START inside it.
+//   1. line starts: word-wide (SWAR) newline masks of the staged window, block
+//      scan, table of line-start offsets in shared memory;
+//   2. lines are handed to threads round-robin, 256 at a time ("batch").  A
+//      thread parses its line ONCE, looks the contig name up, searches the block
+//      table (upper levels = Eytzinger-ordered group maxima staged in shared
+//      memory, then a bisection inside one group), computes the exact byte
+//      length of its output; one packed block scan per batch places lifted and
+//      unmatched text; the thread then formats straight from its registers
+//      into a shared-memory stage holding the tile's whole output;
+//   3. the tile totals are chained to the previous tiles with a decoupled
+//      look-back (two streams packed in one descriptor pair) and the stages are
+//      copied out with aligned 128-bit stores.
+// Fast path = canonical lines (single tabs, plain digits, inside the window).
+// Anything else (other white space, signs, >9 digits, lines longer than the
+// look-ahead, malformed lines) takes the generic per-line path below, which
+// follows the reference's tokenizer exactly.  Records with >= 2 hits are expanded
+// cooperatively (warp / block), each row computing its own sorted position, byte
+// offset and cumulative strand byte.  If a tile's output does not fit its stage
+// the tile is re-run writing directly to global memory at the chained offsets.
 #pragma once
 #include "device_util.cuh"
 #include "lift_core.cuh"
@@ -26,15 +39,19 @@ namespace swo {
 
 constexpr int TX_TPB = 256;
 constexpr int TX_NW = TX_TPB / 32;
-constexpr int TX_SEG = 64;                   // bytes of input owned per thread
+constexpr int TX_SEG = 64;                   // bytes per newline-mask word
 constexpr int TX_TILE = TX_TPB * TX_SEG;     // 16384
-constexpr int TX_PRE = 16;                   // bytes staged before the tile
+constexpr int TX_PRE = 64;                   // bytes staged before the tile
 constexpr int TX_LOOK = 1024;                // bytes staged after the tile
 constexpr int TX_WIN = TX_PRE + TX_TILE + TX_LOOK;
+constexpr int TX_PAD = 32;                   // always '\n' after the window
+constexpr int TX_NSEG = TX_WIN / TX_SEG;     // 273
 constexpr int TX_OUT_STAGE = 20480;          // lifted bytes staged per tile
-constexpr int TX_UNM_STAGE = 4096;           // unmatched bytes staged per tile
+constexpr int TX_UNM_STAGE = 6144;           // unmatched bytes staged per tile
+constexpr int TX_LCAP = 4096;                // line-start table entries
 constexpr int TX_WL_CAP = 128;
 constexpr int TX_HEAVY_MIN = 256;
+constexpr int TX_EY_CAP = ChainTable::EY_CAP;
 
 // open-addressing name table entry (source contig name -> tcid)
 struct NameEnt {
@@ -62,7 +79,9 @@ struct TextArgs {
     uint64_t *sizes;            // [6], zeroed: lifted, unmatched, records, rows, unmatched recs, error
 };
 
-// ---- input access ------------------------------------------------------------
+// =====================================================================================
+// Generic per-line path (exact tokenizer; any white space; lines of any length)
+// =====================================================================================
 struct Reader {
     const unsigned char *win;  // shared-memory window
     uint64_t ws;               // absolute offset of win[0]
@@ -145,8 +164,7 @@ struct LineInfo {
     uint32_t post_len;      // sum over fields 8.. of (1+len)
 };
 
-__device__ __forceinline__ LineInfo scan_line(const TextArgs &A, const Reader &R, uint64_t p0) {
-    LineInfo L;
+__device__ __noinline__ void scan_line(const TextArgs &A, const Reader &R, uint64_t p0, LineInfo &L) {
     L.status = LN_SKIP;
     L.numf = 0;
     L.tcid = -1;
@@ -156,7 +174,7 @@ __device__ __forceinline__ LineInfo scan_line(const TextArgs &A, const Reader &R
     L.head_len = L.pre_len = L.f6len = L.f7len = L.post_len = 0;
     {  // bed.d:115-116 (tests on the raw line)
         const int c0 = R.at(p0);
-        if (c0 == '#') return L;
+        if (c0 == '#') return;
         if (c0 == 't' || c0 == 'b') {
             const int c1 = R.at(p0 + 1);
             if (c1 != '\n') {
@@ -166,8 +184,8 @@ __device__ __forceinline__ LineInfo scan_line(const TextArgs &A, const Reader &R
                     if (c3 != '\n') {
                         const int c4 = R.at(p0 + 4);
                         if (c4 != '\n') {
-                            if (c0 == 't' && c1 == 'r' && c2 == 'a' && c3 == 'c' && c4 == 'k') return L;
-                            if (c0 == 'b' && c1 == 'r' && c2 == 'o' && c3 == 'w' && c4 == 's') return L;
+                            if (c0 == 't' && c1 == 'r' && c2 == 'a' && c3 == 'c' && c4 == 'k') return;
+                            if (c0 == 'b' && c1 == 'r' && c2 == 'o' && c3 == 'w' && c4 == 's') return;
                         }
                     }
                 }
@@ -176,14 +194,14 @@ __device__ __forceinline__ LineInfo scan_line(const TextArgs &A, const Reader &R
     }
     L.status = LN_ERROR;
     uint64_t a, b;
-    if (!next_field(R, p0, a, b)) return L;  // blank line: < 3 fields
+    if (!next_field(R, p0, a, b)) return;  // blank line: < 3 fields
     L.tcid = lookup_tcontig(A, R, a, b);
     L.head_len = (uint32_t)(b - a);
-    if (!next_field(R, b, a, b)) return L;
-    if (!field_i32(R, a, b, L.start)) return L;
+    if (!next_field(R, b, a, b)) return;
+    if (!field_i32(R, a, b, L.start)) return;
     L.head_len += (uint32_t)(b - a);
-    if (!next_field(R, b, a, b)) return L;
-    if (!field_i32(R, a, b, L.end)) return L;
+    if (!next_field(R, b, a, b)) return;
+    if (!field_i32(R, a, b, L.end)) return;
     L.head_len += (uint32_t)(b - a);
     L.numf = 3;
     L.off3 = b;
@@ -208,16 +226,14 @@ __device__ __forceinline__ LineInfo scan_line(const TextArgs &A, const Reader &R
         if (L.numf < 8) L.numf++;
     }
     if (L.numf >= 8) {  // bed.d:134-136
-        if (!field_i32(R, a6, b6, L.ts) || !field_i32(R, a7, b7, L.te)) return L;
+        if (!field_i32(R, a6, b6, L.ts) || !field_i32(R, a7, b7, L.te)) return;
     }
     L.status = LN_RECORD;
-    return L;
 }
 
 // ---- formatting ----------------------------------------------------------------
-__device__ __forceinline__ int ndigits_i32(int v) {  // length of the decimal text of v
-    unsigned u = v < 0 ? 0u - (unsigned)v : (unsigned)v;
-    int n = v < 0 ? 2 : 1;
+__device__ __forceinline__ int ndigits_u32(unsigned u) {
+    int n = 1;
     if (u >= 100000u) {
         if (u >= 10000000u) n += u >= 1000000000u ? 9 : (u >= 100000000u ? 8 : 7);
         else n += u >= 1000000u ? 6 : 5;
@@ -226,6 +242,9 @@ __device__ __forceinline__ int ndigits_i32(int v) {  // length of the decimal te
         else n += u >= 100u ? 2 : (u >= 10u ? 1 : 0);
     }
     return n;
+}
+__device__ __forceinline__ int ndigits_i32(int v) {  // length of the decimal text of v
+    return ndigits_u32(v < 0 ? 0u - (unsigned)v : (unsigned)v) + (v < 0 ? 1 : 0);
 }
 __device__ __forceinline__ char *put_i32(char *d, int v) {
     const int n = ndigits_i32(v);
@@ -269,12 +288,15 @@ __device__ __forceinline__ char *copy_field(char *d, const Reader &R, uint64_t a
     return d;
 }
 
+__device__ __forceinline__ char *emit_qname(char *d, const TextArgs &A, int qcid) {
+    const uint32_t o = __ldg(A.qname_off + qcid), e = __ldg(A.qname_off + qcid + 1);
+    for (uint32_t i = o; i < e; i++) *d++ = __ldg(A.qname_chars + i);  // bed.d:163
+    return d;
+}
+
 __device__ __forceinline__ char *emit_row(char *d, const TextArgs &A, const Reader &R, const LineInfo &L,
                                           const Thick &th, const RowCore &r, unsigned char strand_byte) {
-    {
-        const uint32_t o = __ldg(A.qname_off + r.qcid), e = __ldg(A.qname_off + r.qcid + 1);
-        for (uint32_t i = o; i < e; i++) *d++ = __ldg(A.qname_chars + i);  // bed.d:163
-    }
+    d = emit_qname(d, A, r.qcid);
     *d++ = '\t';
     d = put_i32(d, r.s);  // bed.d:169
     *d++ = '\t';
@@ -315,15 +337,67 @@ __device__ __forceinline__ char *emit_unmatched(char *d, const Reader &R, uint64
     return d;
 }
 
+// Generic line, count side: output byte counts of both streams.
+struct SlowCount {
+    int status;
+    uint32_t len_l, len_u;
+    int lo, ncand, nhits;
+};
+__device__ __noinline__ void slow_count(const TextArgs &A, const int2 *ey, const Reader &R, uint64_t p0, SlowCount &C) {
+    const TableView &T = A.T;
+    LineInfo L;
+    scan_line(A, R, p0, L);
+    C.status = L.status;
+    C.len_l = C.len_u = 0;
+    C.lo = C.ncand = C.nhits = 0;
+    if (L.status != LN_RECORD) return;
+    const Cand cd = find_candidates(T, ey, L.tcid, L.start, L.end);
+    const int n = count_hits(T, cd, L.start);
+    C.lo = cd.lo;
+    C.ncand = cd.hi - cd.lo;
+    C.nhits = n;
+    if (n == 0) {
+        C.len_u = unmatched_len(L);
+        return;
+    }
+    Thick th{0, 0, 0};
+    if (L.numf >= 8) th = lift_thick(T, ey, L.tcid, L.ts, L.te);
+    for (int j = cd.lo; j < cd.hi; j++) {
+        const Block b = load_block(T, j);
+        if (!T.disjoint && !block_hits(b, L.start)) continue;
+        C.len_l += row_len(A, L, th, make_row(b, L.start, L.end));
+    }
+}
+// Generic line, emit side for 0 or 1 hit (>= 2 hits go through expand_line).
+__device__ __noinline__ void slow_emit(const TextArgs &A, const int2 *ey, const Reader &R, uint64_t p0, int lo, int nhits,
+                                       char *dst) {
+    const TableView &T = A.T;
+    if (nhits == 0) {
+        emit_unmatched(dst, R, p0);
+        return;
+    }
+    LineInfo L;
+    scan_line(A, R, p0, L);
+    Thick th{0, 0, 0};
+    if (L.numf >= 8) th = lift_thick(T, ey, L.tcid, L.ts, L.te);
+    int j = lo;
+    Block b = load_block(T, j);
+    if (!T.disjoint)
+        while (!block_hits(b, L.start)) b = load_block(T, ++j);
+    const RowCore r = make_row(b, L.start, L.end);
+    emit_row(dst, A, R, L, th, r, strand_flip(L.strand, r.inv));
+}
+
 // Expand one multi-hit line: each candidate block computes its rank, its byte
 // offset inside the record's output (sum of the lengths of the rows sorted before
 // it) and its strand byte, then formats its row.  (first,stride) = work split.
-__device__ __forceinline__ void expand_line(const TextArgs &A, const Reader &R, uint64_t p0, int lo, int ncand,
-                                            char *dst, int first, int stride) {
+__device__ __noinline__ void expand_line(const TextArgs &A, const int2 *ey, const Reader &R, uint64_t p0, int lo,
+                                         int ncand, char *dst, int first, int stride) {
     const TableView &T = A.T;
-    const LineInfo L = scan_line(A, R, p0);
+    LineInfo L;
+    scan_line(A, R, p0, L);
     Thick th{0, 0, 0};
-    if (L.numf >= 8) th = lift_thick(T, L.tcid, L.ts, L.te);
+    if (L.numf >= 8) th = lift_thick(T, ey, L.tcid, L.ts, L.te);
     for (int c = first; c < ncand; c += stride) {
         const Block bj = load_block(T, lo + c);
         if (!T.disjoint && !block_hits(bj, L.start)) continue;
@@ -353,6 +427,164 @@ __device__ __forceinline__ void expand_line(const TextArgs &A, const Reader &R, 
     }
 }
 
+// =====================================================================================
+// Fast path: canonical line, parsed once, kept in registers between count and emit
+// =====================================================================================
+enum { FL_NONE = 0, FL_FAST = 1, FL_SLOW = 2 };
+
+struct FastLine {
+    int numf;             // 3..8 (saturated)
+    int tcid, start, end;
+    uint32_t q;           // window offset of the terminating '\n'
+    uint32_t e2;          // window offset of the separator after field 2 (== q when numf == 3)
+    uint32_t a5, a6, b7;  // first byte of field 5, first byte of field 6, end of field 7
+    int v6, v7;           // thickStart, thickEnd
+    unsigned char strand;
+};
+
+__device__ __forceinline__ int lookup_tcontig_win(const TextArgs &A, const unsigned char *win, uint32_t p, uint32_t len,
+                                                  uint32_t h) {
+    for (uint32_t s = h & A.thash_mask;; s = (s + 1) & A.thash_mask) {
+        const int4 raw = __ldg(reinterpret_cast<const int4 *>(A.thash) + s);
+        if (raw.y < 0) return -1;
+        if ((uint32_t)raw.x == h && (uint32_t)raw.w == len) {
+            const char *nm = A.tname_chars + (uint32_t)raw.z;
+            uint32_t i = 0;
+            while (i < len && (unsigned char)__ldg(nm + i) == win[p + i]) i++;
+            if (i == len) return raw.y;
+        }
+    }
+}
+
+// digits at win[i...]: value, returns the offset of the first non-digit
+__device__ __forceinline__ uint32_t parse_digits(const unsigned char *win, uint32_t i, uint32_t &v) {
+    uint32_t x = 0, d;
+    while ((d = (uint32_t)win[i] - '0') <= 9u) {
+        x = x * 10u + d;
+        i++;
+    }
+    v = x;
+    return i;
+}
+
+// Parse the line starting at window offset p.  `limit`: a terminator at or beyond
+// this offset is not a real line end (the line runs out of the staged window).
+__device__ __forceinline__ int fast_parse(const TextArgs &A, const unsigned char *win, uint32_t p, uint32_t limit,
+                                          FastLine &F) {
+    uint32_t i = p;
+    uint32_t c = win[i];
+    if (c == '#') return FL_NONE;  // bed.d:115
+    if (c == 't' || c == 'b') {    // bed.d:116 ("track" / "brows"); the window is padded, the reads are safe
+        const uint32_t c1 = win[i + 1], c2 = win[i + 2], c3 = win[i + 3], c4 = win[i + 4];
+        if (c == 't' && c1 == 'r' && c2 == 'a' && c3 == 'c' && c4 == 'k') return FL_NONE;
+        if (c == 'b' && c1 == 'r' && c2 == 'o' && c3 == 'w' && c4 == 's') return FL_NONE;
+    }
+    uint32_t h = 0x9E3779B9u;
+    while (c > 0x20u) {
+        h = (h ^ c) * 0x01000193u;
+        c = win[++i];
+    }
+    if (c != '\t' || i == p) return FL_SLOW;
+    h ^= h >> 15;
+    const uint32_t len0 = i - p;
+    uint32_t v, j;
+    j = parse_digits(win, i + 1, v);
+    if (win[j] != '\t' || j == i + 1 || j - (i + 1) > 9u) return FL_SLOW;
+    F.start = (int)v;
+    i = j;
+    j = parse_digits(win, i + 1, v);
+    if (j == i + 1 || j - (i + 1) > 9u) return FL_SLOW;
+    F.end = (int)v;
+    F.e2 = j;
+    F.a5 = F.a6 = F.b7 = 0;
+    F.v6 = F.v7 = 0;
+    F.strand = 0;
+    c = win[j];
+    int f = 3;
+    bool ok67 = true;
+    while (c == '\t') {
+        const uint32_t a = j + 1;
+        if (f == 6 || f == 7) {
+            j = parse_digits(win, a, v);
+            c = win[j];
+            if (c > 0x20u || j - a > 9u) ok67 = false;  // sign, junk or too long: generic path decides
+            while (c > 0x20u) c = win[++j];
+            if (f == 6) {
+                F.a6 = a;
+                F.v6 = (int)v;
+            } else {
+                F.b7 = j;
+                F.v7 = (int)v;
+            }
+        } else {
+            j = a;
+            c = win[j];
+            while (c > 0x20u) c = win[++j];
+            if (f == 5) {
+                F.a5 = a;
+                F.strand = win[a];
+            }
+        }
+        if (j == a) return FL_SLOW;  // empty field: white-space run, generic tokenizer
+        f++;
+    }
+    if (c != '\n' || j >= limit) return FL_SLOW;
+    F.q = j;
+    F.numf = f < 8 ? f : 8;
+    if (F.numf >= 8 && !ok67) return FL_SLOW;
+    F.tcid = lookup_tcontig_win(A, win, p, len0, h);
+    return FL_FAST;
+}
+
+// bytes of a fast-path row that do not depend on the block
+__device__ __forceinline__ uint32_t fast_fixed_len(const FastLine &F) {
+    uint32_t n = 3 + (F.q - F.e2);  // two tabs, '\n', pass-through tail (with its leading tab)
+    if (F.numf >= 8) n -= F.b7 - F.a6;
+    return n;
+}
+__device__ __forceinline__ uint32_t fast_row_len(const TextArgs &A, const FastLine &F, uint32_t fixed, const Thick &th,
+                                                 const RowCore &r) {
+    uint32_t n = fixed + qname_len(A, r.qcid) + ndigits_i32(r.s) + ndigits_i32(r.e);
+    if (F.numf >= 8) {
+        int c7, c8;
+        thick_clamp(th, r.s, r.e, c7, c8);
+        n += 1 + ndigits_i32(c7) + ndigits_i32(c8);
+    }
+    return n;
+}
+__device__ __forceinline__ char *copy_span(char *d, const unsigned char *win, uint32_t a, uint32_t b) {
+    for (; a < b; a++) *d++ = (char)win[a];
+    return d;
+}
+__device__ __forceinline__ void fast_emit_row(char *d, const TextArgs &A, const unsigned char *win, const FastLine &F,
+                                              const Thick &th, const RowCore &r, unsigned char strand_byte) {
+    d = emit_qname(d, A, r.qcid);
+    *d++ = '\t';
+    d = put_i32(d, r.s);
+    *d++ = '\t';
+    d = put_i32(d, r.e);
+    if (F.numf > 3) {
+        if (F.numf < 6) {
+            d = copy_span(d, win, F.e2, F.q);
+        } else {
+            d = copy_span(d, win, F.e2, F.a5);
+            *d++ = (char)strand_byte;  // bed.d:173
+            if (F.numf < 8) {
+                d = copy_span(d, win, F.a5 + 1, F.q);
+            } else {
+                int c7, c8;
+                thick_clamp(th, r.s, r.e, c7, c8);  // bed.d:175-196
+                d = copy_span(d, win, F.a5 + 1, F.a6);
+                d = put_i32(d, c7);
+                *d++ = '\t';
+                d = put_i32(d, c8);
+                d = copy_span(d, win, F.b7, F.q);
+            }
+        }
+    }
+    *d = '\n';
+}
+
 // copy n bytes from shared memory (4-byte aligned base) to global dst with
 // 16-byte aligned vector stores in the middle
 __device__ __forceinline__ void copy_out(char *dst, const uint32_t *s_words, uint32_t n) {
@@ -377,26 +609,262 @@ __device__ __forceinline__ void copy_out(char *dst, const uint32_t *s_words, uin
     for (uint32_t i = done + threadIdx.x; i < n; i += blockDim.x) dst[i] = (char)s[i];
 }
 
+// 4-bit mask of the bytes of x equal to '\n' (bit b = byte b)
+__device__ __forceinline__ uint32_t nl_mask4(uint32_t x) {
+    x ^= 0x0A0A0A0Au;
+    uint32_t t = ((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x;  // bit 7 of a byte clear <=> byte == 0
+    t = ~t & 0x80808080u;
+    return ((t >> 7) * 0x00204081u) >> 21 & 0xFu;
+}
+
+constexpr int TX_NB = 3;  // batches of 256 lines whose parse results stay in registers
+
 struct TextSmem {
-    uint32_t in_words[TX_WIN / 4 + 4];
+    uint32_t in_words[(TX_WIN + TX_PAD) / 4];
     uint32_t out_words[TX_OUT_STAGE / 4 + 8];
     uint32_t unm_words[TX_UNM_STAGE / 4 + 8];
-    uint32_t scan_a[TX_NW + 1];
-    uint32_t scan_b[TX_NW + 1];
+    unsigned long long nlm[TX_NSEG + 1];
+    int2 ey[TX_EY_CAP];
+    uint16_t lstart[TX_LCAP];
+    unsigned long long scan64[TX_NB * TX_NW];
+    uint32_t scan32[TX_NW + 1];
     uint64_t base_l, base_u;
     int tile;
     int wl_n;
-    uint32_t wl_p0[TX_WL_CAP];   // line start relative to tile start
+    uint32_t wl_p0[TX_WL_CAP];   // line start, window offset
     int wl_lo[TX_WL_CAP];
     int wl_cnt[TX_WL_CAP];
     uint32_t wl_off[TX_WL_CAP];  // byte offset inside the tile's lifted output
 };
 
-__global__ void __launch_bounds__(TX_TPB) lift_bed_text_kernel(const TextArgs A) {
+// What a thread keeps about one line between the count and the emit phase.
+struct LineState {
+    uint32_t pq;    // p | q << 16 : window offsets of the line start and of its '\n'
+    uint32_t e2a5;  // FastLine.e2 | a5 << 16
+    uint32_t a6b7;  // FastLine.a6 | b7 << 16
+    uint32_t meta;  // bits 0-1 kind, 2-5 numf, 6-13 strand byte, 14 invert<0, 15 thick.has, 16-31 qcid
+    int a, b;       // nh == 1: row start,end ; nh >= 2 (fast line): query start,end
+    int lo, ncand;  // candidate blocks
+    int nh;         // overlapping blocks
+    int ths, the;   // lifted thickStart/thickEnd
+};
+
+// per-tile constants shared by the helpers
+struct TileCtx {
+    const unsigned char *win;
+    const int2 *ey;
+    Reader R;
+    uint64_t g0;     // absolute offset of window offset s0
+    uint32_t s0;
+    uint32_t limit;  // see fast_parse
+};
+
+// Count side of one line: parse, look up, search, exact output lengths.
+__device__ __forceinline__ void line_count(const TextArgs &A, const TileCtx &X, uint32_t p, LineState &st,
+                                           uint32_t &len_l, uint32_t &len_u, bool &is_err) {
+    const TableView &T = A.T;
+    len_l = len_u = 0;
+    is_err = false;
+    st.pq = p;
+    st.e2a5 = st.a6b7 = 0;
+    st.a = st.b = st.lo = st.ncand = st.nh = st.ths = st.the = 0;
+    FastLine F;
+    int kind = fast_parse(A, X.win, p, X.limit, F);
+    uint32_t meta = 0;
+    if (kind == FL_FAST) {
+        const Cand cd = find_candidates(T, X.ey, F.tcid, F.start, F.end);
+        const int nh = count_hits(T, cd, F.start);
+        st.pq = p | (F.q << 16);
+        st.e2a5 = F.e2 | (F.a5 << 16);
+        st.a6b7 = F.a6 | (F.b7 << 16);
+        st.lo = cd.lo;
+        st.ncand = cd.hi - cd.lo;
+        st.nh = nh;
+        meta = ((uint32_t)F.numf << 2) | ((uint32_t)F.strand << 6);
+        if (nh == 0) {
+            len_u = F.q - p + 1;
+        } else {
+            const uint32_t fixed = fast_fixed_len(F);
+            Thick th{0, 0, 0};
+            if (F.numf >= 8) th = lift_thick(T, X.ey, F.tcid, F.v6, F.v7);
+            RowCore r;
+            r.key = r.s = r.e = r.qcid = 0;
+            r.inv = 1;
+            for (int j = cd.lo; j < cd.hi; j++) {
+                const Block b = load_block(T, j);
+                if (!T.disjoint && !block_hits(b, F.start)) continue;
+                r = make_row(b, F.start, F.end);
+                len_l += fast_row_len(A, F, fixed, th, r);
+            }
+            st.ths = th.ts;
+            st.the = th.te;
+            meta |= th.has ? (1u << 15) : 0u;
+            if (nh == 1) {
+                st.a = r.s;
+                st.b = r.e;
+                meta |= (r.inv < 0 ? (1u << 14) : 0u) | ((uint32_t)r.qcid << 16);
+            } else {
+                st.a = F.start;
+                st.b = F.end;
+            }
+        }
+    } else if (kind == FL_SLOW) {
+        SlowCount C;
+        slow_count(A, X.ey, X.R, X.g0 + (p - X.s0), C);
+        if (C.status == LN_ERROR) {
+            is_err = true;
+            kind = FL_NONE;
+        } else if (C.status == LN_SKIP) {
+            kind = FL_NONE;
+        } else {
+            len_l = C.len_l;
+            len_u = C.len_u;
+            st.lo = C.lo;
+            st.ncand = C.ncand;
+            st.nh = C.nhits;
+        }
+    }
+    st.meta = meta | (uint32_t)kind;
+}
+
+__device__ __forceinline__ void state_to_fast(const LineState &st, FastLine &F, Thick &th) {
+    F.numf = (int)((st.meta >> 2) & 15u);
+    F.strand = (unsigned char)((st.meta >> 6) & 255u);
+    F.q = st.pq >> 16;
+    F.e2 = st.e2a5 & 0xFFFFu;
+    F.a5 = st.e2a5 >> 16;
+    F.a6 = st.a6b7 & 0xFFFFu;
+    F.b7 = st.a6b7 >> 16;
+    F.tcid = 0;
+    F.start = st.a;
+    F.end = st.b;
+    F.v6 = F.v7 = 0;
+    th.has = (int)((st.meta >> 15) & 1u);
+    th.ts = st.ths;
+    th.te = st.the;
+}
+
+// A fast line with a handful of hits, expanded by its own thread: every row's sorted
+// position (qStart, then block order: bed.d:156-157), byte offset and cumulative
+// strand byte (bed.d:173) are computed directly.
+__device__ __forceinline__ void fast_expand_small(const TextArgs &A, const unsigned char *win, const FastLine &F,
+                                                  const Thick &th, int lo, int ncand, char *dst) {
+    const TableView &T = A.T;
+    const uint32_t fixed = fast_fixed_len(F);
+    for (int c = 0; c < ncand; c++) {
+        const Block bj = load_block(T, lo + c);
+        if (!T.disjoint && !block_hits(bj, F.start)) continue;
+        const RowCore rj = make_row(bj, F.start, F.end);
+        int rank = 0, negs = rj.inv < 0 ? 1 : 0;
+        uint32_t off = 0;
+        int best_key = rj.key, best_k = c, best_inv = rj.inv;
+        for (int k = 0; k < ncand; k++) {
+            if (k == c) continue;
+            const Block bk = load_block(T, lo + k);
+            if (!T.disjoint && !block_hits(bk, F.start)) continue;
+            const RowCore rk = make_row(bk, F.start, F.end);
+            const bool before = rk.key < rj.key || (rk.key == rj.key && k < c);
+            if (before) {
+                rank++;
+                negs += rk.inv < 0 ? 1 : 0;
+                off += fast_row_len(A, F, fixed, th, rk);
+            }
+            if (rk.key < best_key || (rk.key == best_key && k < best_k)) {
+                best_key = rk.key;
+                best_k = k;
+                best_inv = rk.inv;
+            }
+        }
+        const unsigned char sb = F.numf >= 6 ? strand_at_rank(F.strand, best_inv, rank, negs) : 0;
+        fast_emit_row(dst + off, A, win, F, th, rj, sb);
+    }
+}
+
+constexpr int TX_SMALL_FANOUT = 6;
+
+// Emit side of one line.  dst_l / dst_u = where this line's lifted / unmatched text goes
+// (nullptr: that stream is not written, e.g. the caller's buffer is too small).
+__device__ __forceinline__ void line_emit(const TextArgs &A, const TileCtx &X, TextSmem &S, const LineState &st,
+                                          char *dst_l, char *dst_u, uint32_t o_l) {
+    const int kind = (int)(st.meta & 3u);
+    if (kind == FL_NONE) return;
+    const uint32_t p = st.pq & 0xFFFFu;
+    if (st.nh == 0) {
+        if (!dst_u) return;
+        if (kind == FL_FAST) copy_span(dst_u, X.win, p, (st.pq >> 16) + 1);
+        else slow_emit(A, X.ey, X.R, X.g0 + (p - X.s0), st.lo, 0, dst_u);
+        return;
+    }
+    if (!dst_l) return;
+    if (kind == FL_FAST && st.nh == 1) {
+        FastLine F;
+        Thick th;
+        state_to_fast(st, F, th);
+        RowCore r;
+        r.s = st.a;
+        r.e = st.b;
+        r.qcid = (int)(st.meta >> 16);
+        r.inv = (st.meta >> 14) & 1u ? -1 : 1;
+        r.key = 0;
+        fast_emit_row(dst_l, A, X.win, F, th, r, strand_flip(F.strand, r.inv));
+    } else if (kind == FL_FAST && st.ncand <= TX_SMALL_FANOUT) {
+        FastLine F;
+        Thick th;
+        state_to_fast(st, F, th);
+        fast_expand_small(A, X.win, F, th, st.lo, st.ncand, dst_l);
+    } else if (st.nh == 1) {
+        slow_emit(A, X.ey, X.R, X.g0 + (p - X.s0), st.lo, 1, dst_l);
+    } else {
+        const int slot = atomicAdd(&S.wl_n, 1);
+        if (slot < TX_WL_CAP) {
+            S.wl_p0[slot] = p;
+            S.wl_lo[slot] = st.lo;
+            S.wl_cnt[slot] = st.ncand;
+            S.wl_off[slot] = o_l;
+        } else {
+            expand_line(A, X.ey, X.R, X.g0 + (p - X.s0), st.lo, st.ncand, dst_l, 0, 1);
+        }
+    }
+}
+
+// NB independent exclusive block scans with one pair of barriers.
+template <int NB>
+__device__ __forceinline__ void block_scan_multi(const unsigned long long (&v)[NB], unsigned long long (&ex)[NB],
+                                                 unsigned long long (&tot)[NB], unsigned long long *scratch) {
+    unsigned long long inc[NB];
+#pragma unroll
+    for (int b = 0; b < NB; b++) inc[b] = warp_inclusive_scan(v[b]);
+    __syncthreads();
+    if (lane_id() == 31) {
+#pragma unroll
+        for (int b = 0; b < NB; b++) scratch[b * TX_NW + warp_id()] = inc[b];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+        unsigned long long wbase = 0, t = 0;
+#pragma unroll
+        for (int w = 0; w < TX_NW; w++) {
+            const unsigned long long s = scratch[b * TX_NW + w];
+            if (w < warp_id()) wbase += s;
+            t += s;
+        }
+        ex[b] = wbase + inc[b] - v[b];
+        tot[b] = t;
+    }
+}
+
+__global__ void __launch_bounds__(TX_TPB, 3) lift_bed_text_kernel(const TextArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TextSmem &S = *reinterpret_cast<TextSmem *>(smem_raw);
     const int tid = threadIdx.x;
     const TableView &T = A.T;
+    unsigned char *const win = reinterpret_cast<unsigned char *>(S.in_words);
+    char *const stage_l = reinterpret_cast<char *>(S.out_words);
+    char *const stage_u = reinterpret_cast<char *>(S.unm_words);
+
+    // upper search levels -> shared memory (once per persistent CTA)
+    for (int i = tid; i < T.ey_n; i += TX_TPB) S.ey[i] = __ldg(T.ey + i);
 
     for (;;) {
         __syncthreads();
@@ -409,155 +877,229 @@ __global__ void __launch_bounds__(TX_TPB) lift_bed_text_kernel(const TextArgs A)
         if (tile >= A.ntiles) break;
         const uint64_t t0 = (uint64_t)tile * TX_TILE;
 
-        // ---- stage the window [t0-16, t0+TILE+LOOK) -------------------------
-        Reader R;
-        R.win = reinterpret_cast<const unsigned char *>(S.in_words);
-        R.ws = tile == 0 ? 0 : t0 - TX_PRE;
+        // ---- stage the window [t0-PRE, t0+TILE+LOOK); everything else reads as '\n' ----
+        TileCtx X;
+        X.win = win;
+        X.ey = S.ey;
+        X.g0 = tile == 0 ? 0 : t0 - TX_PRE;  // absolute offset of the first staged byte
+        X.s0 = tile == 0 ? TX_PRE : 0;       // its window offset
+        const uint64_t gend = min(A.in_len, t0 + TX_TILE + TX_LOOK);
+        const uint32_t nst = (uint32_t)(gend - X.g0);
+        const uint32_t wv = X.s0 + nst;  // window offsets < wv hold input bytes
         {
-            const uint64_t wend = min(A.in_len, t0 + TX_TILE + TX_LOOK);
-            R.wlen = (uint32_t)(wend - R.ws);
-        }
-        R.g = reinterpret_cast<const unsigned char *>(A.in);
-        R.in_len = A.in_len;
-        {
-            const uint32_t nvec = R.wlen >> 4;
-            const int4 *src = reinterpret_cast<const int4 *>(A.in + R.ws);
-            int4 *dstv = reinterpret_cast<int4 *>(S.in_words);
+            const uint32_t nvec = nst >> 4;
+            const int4 *src = reinterpret_cast<const int4 *>(A.in + X.g0);
+            int4 *dstv = reinterpret_cast<int4 *>(win + X.s0);
             for (uint32_t v = tid; v < nvec; v += TX_TPB) dstv[v] = ld_stream_v4(src + v);
-            unsigned char *sb = reinterpret_cast<unsigned char *>(S.in_words);
-            for (uint32_t i = (nvec << 4) + tid; i < R.wlen; i += TX_TPB) sb[i] = R.g[R.ws + i];
+            for (uint32_t i = (nvec << 4) + tid; i < nst; i += TX_TPB) win[X.s0 + i] = (unsigned char)A.in[X.g0 + i];
+            for (uint32_t i = tid; i < X.s0; i += TX_TPB) win[i] = '\n';
+            for (uint32_t i = wv + tid; i < TX_WIN + TX_PAD; i += TX_TPB) win[i] = '\n';
         }
+        X.R.win = win + X.s0;
+        X.R.ws = X.g0;
+        X.R.wlen = nst;
+        X.R.g = reinterpret_cast<const unsigned char *>(A.in);
+        X.R.in_len = A.in_len;
+        // a terminator found at or beyond this window offset is not the line's real end
+        X.limit = gend == A.in_len ? wv + 1 : wv;
         __syncthreads();
 
-        // ---- pass A: parse + search + exact output byte counts -------------------
-        const uint64_t seg = t0 + (uint64_t)tid * TX_SEG;
-        uint64_t starts = 0;  // bit i: a line starts at seg+i
-        if (seg < A.in_len) {
+        // ---- newline masks of the window, 64 bytes per word -----------------------------
+        for (int sg = tid; sg < TX_NSEG; sg += TX_TPB) {
+            const uint4 *w = reinterpret_cast<const uint4 *>(win + sg * TX_SEG);
+            unsigned long long m = 0;
 #pragma unroll
-            for (int w = 0; w < TX_SEG / 4; w++) {
-                // bytes seg-1+4w .. seg+2+4w  (a '\n' at p-1 means a line starts at p)
-                uint32_t x = 0;
+            for (int k = 0; k < 4; k++) {
+                const uint4 x = w[k];
+                const uint32_t m16 = nl_mask4(x.x) | (nl_mask4(x.y) << 4) | (nl_mask4(x.z) << 8) | (nl_mask4(x.w) << 12);
+                m |= (unsigned long long)m16 << (16 * k);
+            }
+            S.nlm[sg] = m;
+        }
+        __syncthreads();
+        // line starts inside this thread's 64 bytes of the tile: the byte before is '\n'
+        const unsigned long long starts = (S.nlm[tid + 1] << 1) | (S.nlm[tid] >> 63);
+        unsigned long long valid = starts;
+        {
+            const long long rem = (long long)A.in_len - (long long)(t0 + (uint64_t)tid * TX_SEG);
+            if (rem <= 0) valid = 0;
+            else if (rem < 64) valid &= (1ull << rem) - 1ull;
+        }
+        // line index = prefix over ALL starts (the valid ones are a prefix of them)
+        uint32_t packed_tot;
+        const uint32_t packed_ex = block_exclusive_scan<uint32_t, TX_NW>(
+            (uint32_t)__popcll(starts) | ((uint32_t)__popcll(valid) << 16), S.scan32, &packed_tot);
+        const int my_first = (int)(packed_ex & 0xFFFFu);
+        const int nlines = (int)(packed_tot >> 16);  // lines owned by this tile
+        auto build_table = [&](int wbase) {
+            __syncthreads();  // previous users of the table are done
+            int j = my_first;
+            for (unsigned long long m = starts; m; m &= m - 1, j++) {
+                const int slot = j - wbase;
+                if (slot >= 0 && slot < TX_LCAP)
+                    S.lstart[slot] = (uint16_t)(TX_PRE + tid * TX_SEG + __ffsll((long long)m) - 1);
+            }
+            __syncthreads();
+        };
+        build_table(0);
+
+        // ---- phase C: parse + search + exact output lengths; no barrier inside ---------
+        uint32_t c_rec = 0, c_rows = 0, c_unm = 0;
+        LineState st[TX_NB];
+        unsigned long long v[TX_NB], ex[TX_NB], bt[TX_NB];
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const uint64_t p = seg + 4 * w + k;
-                    const bool st = p < A.in_len && (p == 0 || R.at(p - 1) == '\n');
-                    x |= st ? (1u << k) : 0u;
+        for (int b = 0; b < TX_NB; b++) {
+            const int li = b * TX_TPB + tid;
+            st[b].meta = FL_NONE;
+            st[b].nh = 0;
+            v[b] = 0;
+            if (li < nlines) {
+                uint32_t ll, lu;
+                bool err;
+                line_count(A, X, S.lstart[li], st[b], ll, lu, err);
+                v[b] = ((unsigned long long)ll << 32) | lu;
+                if (err)  // max(~p0) == first bad line
+                    atomicMax((unsigned long long *)(A.sizes + 5),
+                              ~(unsigned long long)(X.g0 + ((st[b].pq & 0xFFFFu) - X.s0)));
+                if ((st[b].meta & 3u) != FL_NONE) {
+                    c_rec++;
+                    c_rows += (uint32_t)st[b].nh;
+                    c_unm += st[b].nh == 0 ? 1u : 0u;
                 }
-                starts |= (uint64_t)x << (4 * w);
             }
         }
-        uint32_t a_l = 0, a_u = 0, a_rec = 0, a_rows = 0, a_unm = 0;
-        for (uint64_t m = starts; m; m &= m - 1) {
-            const uint64_t p0 = seg + (uint64_t)(__ffsll((long long)m) - 1);
-            const LineInfo L = scan_line(A, R, p0);
-            if (L.status == LN_SKIP) continue;
-            if (L.status == LN_ERROR) {
-                atomicMax((unsigned long long *)(A.sizes + 5), ~(unsigned long long)p0);  // max(~p0) == first bad line
-                continue;
-            }
-            a_rec++;
-            const Cand cd = find_candidates(T, L.tcid, L.start, L.end);
-            const int n = count_hits(T, cd, L.start);
-            if (n == 0) {
-                a_u += unmatched_len(L);
-                a_unm++;
-                continue;
-            }
-            a_rows += (uint32_t)n;
-            Thick th{0, 0, 0};
-            if (L.numf >= 8) th = lift_thick(T, L.tcid, L.ts, L.te);
-            for (int j = cd.lo; j < cd.hi; j++) {
-                const Block b = load_block(T, j);
-                if (!T.disjoint && !block_hits(b, L.start)) continue;
-                a_l += row_len(A, L, th, make_row(b, L.start, L.end));
-            }
+        block_scan_multi<TX_NB>(v, ex, bt, S.scan64);
+        uint32_t run_l = 0, run_u = 0;
+#pragma unroll
+        for (int b = 0; b < TX_NB; b++) {
+            ex[b] += ((unsigned long long)run_l << 32) | run_u;
+            run_l += (uint32_t)(bt[b] >> 32);
+            run_u += (uint32_t)bt[b];
         }
-        uint32_t tot_l, tot_u;
-        const uint32_t ex_l = block_exclusive_scan<uint32_t, TX_NW>(a_l, S.scan_a, &tot_l);
-        const uint32_t ex_u = block_exclusive_scan<uint32_t, TX_NW>(a_u, S.scan_b, &tot_u);
-        if (warp_id() == 0) {
-            const uint64_t b = lookback_exclusive(A.desc_l, tile, (uint64_t)tot_l);
-            if (tid == 0) S.base_l = b;
-        } else if (warp_id() == 1) {
-            const uint64_t b = lookback_exclusive(A.desc_u, tile, (uint64_t)tot_u);
-            if (lane_id() == 0) S.base_u = b;
+        // tiles with more than TX_NB*256 lines (very short lines): count the rest now, redo them when emitting
+        if (nlines > TX_NB * TX_TPB) {
+            int wbase = 0;
+            for (int lb = TX_NB * TX_TPB; lb < nlines; lb += TX_TPB) {
+                if (lb >= wbase + TX_LCAP) {
+                    wbase += TX_LCAP;
+                    build_table(wbase);
+                }
+                const int li = lb + tid;
+                uint32_t ll = 0, lu = 0;
+                if (li < nlines) {
+                    LineState t;
+                    bool err;
+                    line_count(A, X, S.lstart[li - wbase], t, ll, lu, err);
+                    if (err)
+                        atomicMax((unsigned long long *)(A.sizes + 5),
+                                  ~(unsigned long long)(X.g0 + ((t.pq & 0xFFFFu) - X.s0)));
+                    if ((t.meta & 3u) != FL_NONE) {
+                        c_rec++;
+                        c_rows += (uint32_t)t.nh;
+                        c_unm += t.nh == 0 ? 1u : 0u;
+                    }
+                }
+                unsigned long long t1;
+                block_exclusive_scan<unsigned long long, TX_NW>(((unsigned long long)ll << 32) | lu, S.scan64, &t1);
+                run_l += (uint32_t)(t1 >> 32);
+                run_u += (uint32_t)t1;
+            }
+            if (wbase) build_table(0);
         }
-        {  // record counters (every warp)
-            const uint32_t r = warp_sum(a_rec), w = warp_sum(a_rows), u = warp_sum(a_unm);
+        const uint32_t tot_l = run_l, tot_u = run_u;
+
+        // ---- publish the tile aggregates now; successors never wait on our formatting ---
+        if (warp_id() == 0) lookback_publish(A.desc_l, tile, (uint64_t)tot_l);
+        else if (warp_id() == 1) lookback_publish(A.desc_u, tile, (uint64_t)tot_u);
+        {  // record counters
+            const uint32_t rr = warp_sum(c_rec), w = warp_sum(c_rows), u = warp_sum(c_unm);
             if (lane_id() == 0) {
-                if (r) atomicAdd((unsigned long long *)(A.sizes + 2), (unsigned long long)r);
+                if (rr) atomicAdd((unsigned long long *)(A.sizes + 2), (unsigned long long)rr);
                 if (w) atomicAdd((unsigned long long *)(A.sizes + 3), (unsigned long long)w);
                 if (u) atomicAdd((unsigned long long *)(A.sizes + 4), (unsigned long long)u);
             }
         }
+        // a stream that does not fit its stage is written straight to global memory,
+        // which needs the chained offset before formatting
+        const bool direct_l = tot_l > TX_OUT_STAGE, direct_u = tot_u > TX_UNM_STAGE;
+        uint64_t gb_l = 0, gb_u = 0;
+        bool have_base = false;
+        auto resolve_base = [&]() {
+            if (warp_id() == 0) {
+                const uint64_t b = lookback_resolve(A.desc_l, tile, (uint64_t)tot_l);
+                if (tid == 0) S.base_l = b;
+            } else if (warp_id() == 1) {
+                const uint64_t b = lookback_resolve(A.desc_u, tile, (uint64_t)tot_u);
+                if (lane_id() == 0) S.base_u = b;
+            }
+            __syncthreads();
+            gb_l = S.base_l;
+            gb_u = S.base_u;
+            have_base = true;
+        };
+        if (direct_l || direct_u) resolve_base();
+        char *const base_l = direct_l ? (gb_l + tot_l <= A.lifted_cap ? A.lifted + gb_l : nullptr) : stage_l;
+        char *const base_u = direct_u ? (gb_u + tot_u <= A.unm_cap ? A.unm + gb_u : nullptr) : stage_u;
+
+        // ---- phase E: format from the cached state; no barrier inside -------------------
+#pragma unroll
+        for (int b = 0; b < TX_NB; b++) {
+            const uint32_t o_l = (uint32_t)(ex[b] >> 32), o_u = (uint32_t)ex[b];
+            line_emit(A, X, S, st[b], base_l ? base_l + o_l : nullptr, base_u ? base_u + o_u : nullptr, o_l);
+        }
+        if (nlines > TX_NB * TX_TPB) {
+            int wbase = 0;
+            uint32_t r_l = 0, r_u = 0;
+#pragma unroll
+            for (int b = 0; b < TX_NB; b++) {
+                r_l += (uint32_t)(bt[b] >> 32);
+                r_u += (uint32_t)bt[b];
+            }
+            for (int lb = TX_NB * TX_TPB; lb < nlines; lb += TX_TPB) {
+                if (lb >= wbase + TX_LCAP) {
+                    wbase += TX_LCAP;
+                    build_table(wbase);
+                }
+                const int li = lb + tid;
+                uint32_t ll = 0, lu = 0;
+                LineState t;
+                t.meta = FL_NONE;
+                t.nh = 0;
+                if (li < nlines) {
+                    bool err;
+                    line_count(A, X, S.lstart[li - wbase], t, ll, lu, err);
+                }
+                unsigned long long t1;
+                const unsigned long long e1 =
+                    block_exclusive_scan<unsigned long long, TX_NW>(((unsigned long long)ll << 32) | lu, S.scan64, &t1);
+                const uint32_t o_l = r_l + (uint32_t)(e1 >> 32), o_u = r_u + (uint32_t)e1;
+                r_l += (uint32_t)(t1 >> 32);
+                r_u += (uint32_t)t1;
+                line_emit(A, X, S, t, base_l ? base_l + o_l : nullptr, base_u ? base_u + o_u : nullptr, o_l);
+            }
+        }
         __syncthreads();
-        const uint64_t gb_l = S.base_l, gb_u = S.base_u;
+        if (base_l) {  // cooperative expansion of the queued multi-hit lines
+            const int nwl = min(S.wl_n, TX_WL_CAP);
+            for (int e = warp_id(); e < nwl; e += TX_NW)
+                if (S.wl_cnt[e] < TX_HEAVY_MIN)
+                    expand_line(A, X.ey, X.R, X.g0 + (S.wl_p0[e] - X.s0), S.wl_lo[e], S.wl_cnt[e], base_l + S.wl_off[e],
+                                lane_id(), 32);
+            for (int e = 0; e < nwl; e++)
+                if (S.wl_cnt[e] >= TX_HEAVY_MIN)
+                    expand_line(A, X.ey, X.R, X.g0 + (S.wl_p0[e] - X.s0), S.wl_lo[e], S.wl_cnt[e], base_l + S.wl_off[e], tid,
+                                TX_TPB);
+        }
+        __syncthreads();
+
+        // ---- chained offsets (predecessors published long ago), then copy the stages out ---
+        if (!have_base) resolve_base();
         if (tile == A.ntiles - 1 && tid == 0) {
             A.sizes[0] = gb_l + tot_l;
             A.sizes[1] = gb_u + tot_u;
         }
-        const bool fit_l = gb_l + tot_l <= A.lifted_cap, fit_u = gb_u + tot_u <= A.unm_cap;
-        const bool stage_l = tot_l <= TX_OUT_STAGE, stage_u = tot_u <= TX_UNM_STAGE;
-        char *base_l = stage_l ? reinterpret_cast<char *>(S.out_words) : A.lifted + gb_l;
-        char *base_u = stage_u ? reinterpret_cast<char *>(S.unm_words) : A.unm + gb_u;
-
-        // ---- pass B: format ---------------------------------------------------------
-        uint32_t o_l = ex_l, o_u = ex_u;
-        for (uint64_t m = starts; m; m &= m - 1) {
-            const uint64_t p0 = seg + (uint64_t)(__ffsll((long long)m) - 1);
-            const LineInfo L = scan_line(A, R, p0);
-            if (L.status != LN_RECORD) continue;
-            const Cand cd = find_candidates(T, L.tcid, L.start, L.end);
-            const int n = count_hits(T, cd, L.start);
-            if (n == 0) {
-                if (fit_u) emit_unmatched(base_u + o_u, R, p0);
-                o_u += unmatched_len(L);
-                continue;
-            }
-            Thick th{0, 0, 0};
-            if (L.numf >= 8) th = lift_thick(T, L.tcid, L.ts, L.te);
-            if (n == 1) {
-                int j = cd.lo;
-                Block b = load_block(T, j);
-                if (!T.disjoint)
-                    while (!block_hits(b, L.start)) b = load_block(T, ++j);
-                const RowCore r = make_row(b, L.start, L.end);
-                if (fit_l) emit_row(base_l + o_l, A, R, L, th, r, strand_flip(L.strand, r.inv));
-                o_l += row_len(A, L, th, r);
-                continue;
-            }
-            // n >= 2: total length again (cheap relative to the expansion), queue the expansion
-            uint32_t len = 0;
-            for (int j = cd.lo; j < cd.hi; j++) {
-                const Block b = load_block(T, j);
-                if (!T.disjoint && !block_hits(b, L.start)) continue;
-                len += row_len(A, L, th, make_row(b, L.start, L.end));
-            }
-            if (fit_l) {
-                const int slot = atomicAdd(&S.wl_n, 1);
-                if (slot < TX_WL_CAP) {
-                    S.wl_p0[slot] = (uint32_t)(p0 - t0);
-                    S.wl_lo[slot] = cd.lo;
-                    S.wl_cnt[slot] = cd.hi - cd.lo;
-                    S.wl_off[slot] = o_l;
-                } else {
-                    expand_line(A, R, p0, cd.lo, cd.hi - cd.lo, base_l + o_l, 0, 1);
-                }
-            }
-            o_l += len;
-        }
-        __syncthreads();
-        const int nwl = min(S.wl_n, TX_WL_CAP);
-        for (int e = warp_id(); e < nwl; e += TX_NW)
-            if (S.wl_cnt[e] < TX_HEAVY_MIN)
-                expand_line(A, R, t0 + S.wl_p0[e], S.wl_lo[e], S.wl_cnt[e], base_l + S.wl_off[e], lane_id(), 32);
-        for (int e = 0; e < nwl; e++)
-            if (S.wl_cnt[e] >= TX_HEAVY_MIN)
-                expand_line(A, R, t0 + S.wl_p0[e], S.wl_lo[e], S.wl_cnt[e], base_l + S.wl_off[e], tid, TX_TPB);
-        __syncthreads();
-        // ---- copy the stages out ---------------------------------------------------
-        if (stage_l && fit_l && tot_l) copy_out(A.lifted + gb_l, S.out_words, tot_l);
-        if (stage_u && fit_u && tot_u) copy_out(A.unm + gb_u, S.unm_words, tot_u);
+        if (!direct_l && tot_l && gb_l + tot_l <= A.lifted_cap) copy_out(A.lifted + gb_l, S.out_words, tot_l);
+        if (!direct_u && tot_u && gb_u + tot_u <= A.unm_cap) copy_out(A.unm + gb_u, S.unm_words, tot_u);
     }
 }
 

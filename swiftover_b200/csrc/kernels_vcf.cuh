@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(256) lift_vcf_points_kernel(const VcfArgs A) {
         const int c0 = A.pos[i];
         const int rl = A.reflen[i];
         const uint64_t ro = A.ref_off[i];
-        const int j = point_hit(A.T, A.tcid[i], c0);
+        const int j = point_hit(A.T, A.T.ey, A.tcid[i], c0);
         if (j < 0) {  // vcf.d:134-137: record goes to the unmatched file unchanged
             A.out_qcid[i] = -1;
             A.out_pos[i] = c0;

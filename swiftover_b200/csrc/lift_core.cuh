@@ -28,6 +28,10 @@ struct TableView {
     const int32_t *__restrict__ tStartKey;  // [B]
     const int32_t *__restrict__ pmaxKey;    // [B] prefix max of tEnd per contig
     const int32_t *__restrict__ toff;       // [ntc+1]
+    const int4 *__restrict__ cmeta;         // [ntc] {first block, end block, Eytzinger offset, samples}
+    const int2 *__restrict__ ey;            // Eytzinger upper levels {key, block index} (global copy)
+    int ey_n;                               // total samples (<= ChainTable::EY_CAP)
+    int ey_shift;                           // group size S = 1 << ey_shift
     int ntc;
     int disjoint;  // pmaxKey == tEnd: candidates need no tEnd filter
 };
@@ -70,6 +74,42 @@ SWO_HD int gallop_ge(const int32_t *__restrict__ key, int lo, int b, int x) {
     return b;
 }
 
+// first j in [a,b) with pmaxKey[j] > x, else b.  Upper levels: branch-free
+// descent of the contig's Eytzinger-ordered group maxima (`ey` = shared-memory
+// or global copy of T.ey), then a bisection inside one group of S blocks.
+SWO_HD int lower_gt_ey(const TableView &T, const int2 *__restrict__ ey, const int4 cm, int x) {
+    const int a = cm.x, b = cm.y, m = cm.w;
+    const int2 *__restrict__ e = ey + cm.z - 1;  // 1-based
+    int k = 1;
+    while (k <= m) k = 2 * k + (e[k].x <= x ? 1 : 0);
+#if defined(__CUDA_ARCH__)
+    k >>= __ffs(~k);
+#else
+    k >>= __builtin_ffs(~k);
+#endif
+    int lo, hi;  // answer in [lo,hi], hi == b means "none"
+    if (k) {
+        hi = e[k].y;  // pmaxKey[hi] > x
+        lo = hi - ((1 << T.ey_shift) - 1);
+    } else {
+        lo = a + (m << T.ey_shift);
+        hi = b;
+    }
+    while (lo < hi) {
+        const int mid = (int)(((unsigned)lo + (unsigned)hi) >> 1);
+        if (SWO_LDG(T.pmaxKey + mid) > x) hi = mid;
+        else lo = mid + 1;
+    }
+    return lo;
+}
+SWO_HD int4 load_cmeta(const TableView &T, int tcid) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(T.cmeta + tcid);
+#else
+    return T.cmeta[tcid];
+#endif
+}
+
 // Candidate block range of the half-open query [start,end) on contig tcid:
 // every block j in [lo,hi) has tStart < end and prefix-max(tEnd) > start; the
 // overlap set is { j in [lo,hi) : tEnd[j] > start } (all of them when the
@@ -77,12 +117,12 @@ SWO_HD int gallop_ge(const int32_t *__restrict__ key, int lo, int b, int x) {
 struct Cand {
     int lo, hi;
 };
-SWO_HD Cand find_candidates(const TableView &T, int tcid, int start, int end) {
+SWO_HD Cand find_candidates(const TableView &T, const int2 *__restrict__ ey, int tcid, int start, int end) {
     Cand c{0, 0};
     if (tcid < 0 || tcid >= T.ntc) return c;
-    const int a = SWO_LDG(T.toff + tcid), b = SWO_LDG(T.toff + tcid + 1);
-    c.lo = lower_gt(T.pmaxKey, a, b, start);
-    c.hi = gallop_ge(T.tStartKey, c.lo, b, end);
+    const int4 cm = load_cmeta(T, tcid);
+    c.lo = lower_gt_ey(T, ey, cm, start);
+    c.hi = gallop_ge(T.tStartKey, c.lo, cm.y, end);
     return c;
 }
 
@@ -144,10 +184,11 @@ SWO_HD unsigned char strand_at_rank(unsigned char orig, int inv_first, int rank,
 
 // liftCoordOnly / liftDirectly (chain.d:604-654): first block covering c.
 // Returns block index or -1.
-SWO_HD int point_hit(const TableView &T, int tcid, int c) {
+SWO_HD int point_hit(const TableView &T, const int2 *__restrict__ ey, int tcid, int c) {
     if (tcid < 0 || tcid >= T.ntc) return -1;
-    const int a = SWO_LDG(T.toff + tcid), b = SWO_LDG(T.toff + tcid + 1);
-    int j = lower_gt(T.pmaxKey, a, b, c);
+    const int4 cm = load_cmeta(T, tcid);
+    const int b = cm.y;
+    int j = lower_gt_ey(T, ey, cm, c);
     for (; j < b; j++) {
         if (SWO_LDG(T.tStartKey + j) > c) return -1;
         if (T.disjoint || SWO_LDG(&T.blk[j].tEnd) > c) return j;
@@ -163,12 +204,12 @@ struct Thick {
     int has;  // hasThickInterval
     int ts, te;
 };
-SWO_HD Thick lift_thick(const TableView &T, int tcid, int ts, int te) {
+SWO_HD Thick lift_thick(const TableView &T, const int2 *__restrict__ ey, int tcid, int ts, int te) {
     Thick k{0, ts, te};
     if (ts == te) return k;
-    const int j0 = point_hit(T, tcid, ts);
+    const int j0 = point_hit(T, ey, tcid, ts);
     if (j0 < 0) return k;  // short-circuit: thickEnd is not looked up
-    const int j1 = point_hit(T, tcid, te);
+    const int j1 = point_hit(T, ey, tcid, te);
     if (j1 < 0) return k;
     const int a = point_coord(load_block(T, j0), ts);
     const int b = point_coord(load_block(T, j1), te);

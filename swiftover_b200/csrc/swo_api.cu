@@ -74,7 +74,7 @@ struct PinBuf {
     T *as() const { return reinterpret_cast<T *>(p); }
 };
 
-constexpr int N_SLOTS = 2;  // chunk double-buffering
+constexpr int N_SLOTS = 4;  // chunks in flight per device (H2D / kernel / D2H overlap)
 
 // Everything one device (or logical shard) owns.
 struct Device {
@@ -82,7 +82,7 @@ struct Device {
     int sms = 148;
     cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
     // chain table replica
-    DevBuf blk, tkey, pkey, toff, thash, tchars, tnoff, qoff, qchars;
+    DevBuf blk, tkey, pkey, toff, cmeta, ey, thash, tchars, tnoff, qoff, qchars;
     TableView T{};
     uint32_t thash_mask = 0;
     // genome replica
@@ -111,7 +111,7 @@ struct swo_ctx {
     uint64_t launches = 0;
     // pinned result arenas handed to the caller
     PinBuf r_lifted, r_unm, r_off, r_rows, r_thick;
-    size_t chunk_bytes = 64u << 20;
+    size_t chunk_bytes = 32u << 20;
 };
 
 namespace {
@@ -151,6 +151,13 @@ int upload_table(swo_ctx *c, Device &d) {
     if ((rc = upload(c, d.tkey, t.tStartKey.data(), t.tStartKey.size(), d.s_comp))) return rc;
     if ((rc = upload(c, d.pkey, t.pmaxKey.data(), t.pmaxKey.size(), d.s_comp))) return rc;
     if ((rc = upload(c, d.toff, t.toff.data(), t.toff.size(), d.s_comp))) return rc;
+    std::vector<int4> cmeta(t.ntc());
+    for (int i = 0; i < t.ntc(); i++)
+        cmeta[i] = make_int4(t.toff[i], t.toff[i + 1], t.eyoff[i], t.eyoff[i + 1] - t.eyoff[i]);
+    std::vector<int2> ey(t.eyKey.size());
+    for (size_t i = 0; i < ey.size(); i++) ey[i] = make_int2(t.eyKey[i], t.eyIdx[i]);
+    if ((rc = upload(c, d.cmeta, cmeta.data(), cmeta.size(), d.s_comp))) return rc;
+    if ((rc = upload(c, d.ey, ey.data(), ey.size(), d.s_comp))) return rc;
     // source-contig name table (device text parser)
     uint32_t hs = 16;
     while (hs < (uint32_t)t.ntc() * 4u) hs <<= 1;
@@ -185,6 +192,10 @@ int upload_table(swo_ctx *c, Device &d) {
     d.T.tStartKey = d.tkey.as<int32_t>();
     d.T.pmaxKey = d.pkey.as<int32_t>();
     d.T.toff = d.toff.as<int32_t>();
+    d.T.cmeta = d.cmeta.as<int4>();
+    d.T.ey = d.ey.as<int2>();
+    d.T.ey_n = (int)t.eyKey.size();
+    d.T.ey_shift = t.eyShift;
     d.T.ntc = t.ntc();
     d.T.disjoint = t.disjoint ? 1 : 0;
     return SWO_OK;
@@ -322,10 +333,13 @@ int run_shard(swo_ctx *c, Device &d, const char *in, size_t a, size_t b, PinBuf 
         return SWO_OK;
     };
     int rc;
-    if (nch > 0 && (rc = issue(0))) return rc;
+    int next_issue = 0;
     for (int k = 0; k < nch; k++) {
         const int s = k % N_SLOTS;
-        if (k + 1 < nch && (rc = issue(k + 1))) return rc;
+        // keep N_SLOTS chunks in flight; chunk j reuses the slot of chunk j - N_SLOTS, whose
+        // D2H was queued in an earlier iteration
+        while (next_issue < nch && next_issue < k + N_SLOTS)
+            if ((rc = issue(next_issue++))) return rc;
         CK(c, cudaEventSynchronize(d.ev_comp[s]));
         uint64_t sz[6];
         memcpy(sz, hs + 6 * s, 48);
@@ -422,7 +436,7 @@ void swo_destroy(swo_ctx *c) {
     for (Device &d : c->dev) {
         cudaSetDevice(d.ordinal);
         cudaDeviceSynchronize();
-        for (DevBuf *b : {&d.blk, &d.tkey, &d.pkey, &d.toff, &d.thash, &d.tchars, &d.tnoff, &d.qoff, &d.qchars, &d.g_packed,
+        for (DevBuf *b : {&d.blk, &d.tkey, &d.pkey, &d.toff, &d.cmeta, &d.ey, &d.thash, &d.tchars, &d.tnoff, &d.qoff, &d.qchars, &d.g_packed,
                           &d.g_off, &d.g_len, &d.scratch, &d.b_in, &d.b_off, &d.b_rows, &d.b_thick, &d.b_tot})
             b->release();
         for (int s = 0; s < N_SLOTS; s++) {
