@@ -189,7 +189,8 @@ void *swo_host_alloc(size_t bytes);
 void swo_host_free(void *p);
 
 /* tuning knobs: "chunk_bytes" = bytes of text per H2D/kernel/D2H pipeline stage
- * (default 32 MiB, 4 in flight; the tests shrink it to exercise chunk boundaries) */
+ * (default 64 MiB, up to 8 in flight; the tests shrink it to exercise chunk boundaries);
+ * "zero_copy_input" = 1: pinned input is read by the kernel over PCIe instead of being staged (default 0) */
 int swo_set_option(swo_ctx *ctx, const char *key, int64_t value);
 
 /* number of kernel launches issued by this ctx since creation (bench.py's

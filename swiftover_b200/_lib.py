@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libswiftover_cuda.so")
+# SWO_LIB: alternative build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get("SWO_LIB") or os.path.join(HERE, "libswiftover_cuda.so")
 
 SWO_OK, SWO_E_IO, SWO_E_PARSE, SWO_E_CUDA, SWO_E_OOM, SWO_E_ARG, SWO_E_STATE, SWO_E_CAPACITY = 0, -1, -2, -3, -4, -5, -6, -7
 

@@ -40,7 +40,7 @@ struct ChainTable {
     // consecutive blocks, stored in Eytzinger (BFS) order as {key, block index}
     // pairs at ey[eyoff[c] ...].  S is the smallest power of two for which all
     // samples fit in EY_CAP entries.
-    static constexpr int EY_CAP = 2048;
+    static constexpr int EY_CAP = 4096;
     int eyShift = 0;
     std::vector<int32_t> eyKey, eyIdx;  // [nsamples] each
     std::vector<int32_t> eyoff;         // [ntc+1]
@@ -58,11 +58,32 @@ struct ChainTable {
 // Returns true on success; on failure `err` holds the message.
 bool parse_chain_text(std::string_view text, ChainTable &out, std::string &err);
 
-// Name hash shared by host table construction and the device text parser.
+// Name hash shared by host table construction and the device text parser: the first 16
+// bytes enter as four little-endian words (zero padded), longer names add an FNV tail.
+#if defined(__CUDACC__)
+#define SWO_HASH_HD __host__ __device__ inline
+#else
+#define SWO_HASH_HD inline
+#endif
+SWO_HASH_HD uint32_t name_hash_head(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t len) {
+    return (w0 * 0x9E3779B1u) ^ (w1 * 0x85EBCA77u) ^ (w2 * 0xC2B2AE3Du) ^ (w3 * 0x27D4EB2Fu) ^ (len * 0x165667B1u);
+}
+SWO_HASH_HD uint32_t name_hash_tail(uint32_t h, uint8_t c) { return (h ^ c) * 0x01000193u; }
+SWO_HASH_HD uint32_t name_hash_fin(uint32_t h) {
+    h ^= h >> 15;
+    h *= 0x2C1B3C6Du;
+    return h ^ (h >> 12);
+}
+inline void name_words(const char *s, size_t n, uint32_t w[4]) {
+    w[0] = w[1] = w[2] = w[3] = 0;
+    for (size_t i = 0; i < n && i < 16; i++) w[i >> 2] |= (uint32_t)(uint8_t)s[i] << (8 * (i & 3));
+}
 inline uint32_t name_hash(const char *s, size_t n) {
-    uint32_t h = 0x9E3779B9u;
-    for (size_t i = 0; i < n; i++) h = (h ^ (uint8_t)s[i]) * 0x01000193u;
-    return h ^ (h >> 15);
+    uint32_t w[4];
+    name_words(s, n, w);
+    uint32_t h = name_hash_head(w[0], w[1], w[2], w[3], (uint32_t)n);
+    for (size_t i = 16; i < n; i++) h = name_hash_tail(h, (uint8_t)s[i]);
+    return name_hash_fin(h);
 }
 
 }  // namespace swo

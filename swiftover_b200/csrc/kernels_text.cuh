@@ -37,6 +37,12 @@
 
 namespace swo {
 
+#ifndef TX_USE_BRACKET
+#define TX_USE_BRACKET 0  // per-tile block bracket in shared memory (sorted input); off: its serial set-up costs more than it saves
+#endif
+#ifndef TX_MIN_CTAS
+#define TX_MIN_CTAS 2  // resident CTAs per SM the register budget is sized for
+#endif
 constexpr int TX_TPB = 256;
 constexpr int TX_NW = TX_TPB / 32;
 constexpr int TX_SEG = 64;                   // bytes per newline-mask word
@@ -47,18 +53,24 @@ constexpr int TX_WIN = TX_PRE + TX_TILE + TX_LOOK;
 constexpr int TX_PAD = 32;                   // always '\n' after the window
 constexpr int TX_NSEG = TX_WIN / TX_SEG;     // 273
 constexpr int TX_OUT_STAGE = 20480;          // lifted bytes staged per tile
-constexpr int TX_UNM_STAGE = 6144;           // unmatched bytes staged per tile
-constexpr int TX_LCAP = 4096;                // line-start table entries
-constexpr int TX_WL_CAP = 128;
+constexpr int TX_UNM_STAGE = TX_TILE + TX_LOOK;  // unmatched bytes staged per tile: a tile's unmatched text never exceeds its input
+constexpr int TX_LCAP = 2048;                // line-start table entries
+constexpr int TX_BR_CAP = 64;                // blocks of the tile's bracket staged in shared memory
+constexpr int TX_QN_MAX = 256;               // destination contig names kept in shared memory ...
+constexpr int TX_QCHARS = 3072;              // ... if their characters fit here
+constexpr int TX_WL_CAP = 256;
 constexpr int TX_HEAVY_MIN = 256;
 constexpr int TX_EY_CAP = ChainTable::EY_CAP;
 
-// open-addressing name table entry (source contig name -> tcid)
+// open-addressing name table entry (source contig name -> tcid): two 128-bit loads, the
+// first 16 bytes of the name inline so that the usual verification needs no further load
 struct NameEnt {
     uint32_t hash;
     int32_t id;  // -1 = empty
     uint32_t off, len;
+    uint32_t w[4];  // name bytes 0..15, little endian, zero padded
 };
+constexpr int TX_CM_CAP = 256;  // per-contig table entries kept in shared memory
 
 struct TextArgs {
     TableView T;
@@ -67,8 +79,10 @@ struct TextArgs {
     const char *tname_chars;
     const uint32_t *qname_off;  // [nq+1]
     const char *qname_chars;
-    const char *in;
-    uint64_t in_len;
+    int nq;
+    const char *in;   // 16-byte aligned
+    uint64_t in_len;  // includes `skip`
+    uint32_t skip;    // leading bytes (< 16) that belong to the previous chunk; the text starts at in + skip
     int ntiles;
     char *lifted;
     uint64_t lifted_cap;
@@ -133,20 +147,35 @@ __device__ __forceinline__ bool field_i32(const Reader &R, uint64_t a, uint64_t 
     return true;
 }
 
-__device__ __forceinline__ int lookup_tcontig(const TextArgs &A, const Reader &R, uint64_t a, uint64_t b) {
-    uint32_t h = 0x9E3779B9u;
-    for (uint64_t p = a; p < b; p++) h = (h ^ (uint32_t)R.at(p)) * 0x01000193u;
-    h ^= h >> 15;
-    const uint32_t len = (uint32_t)(b - a);
+// name table probe: hash h, length len, first 16 bytes w0..w3; `tail_eq(off)` compares
+// the bytes from 16 on against the stored name at tname_chars + off (names longer than 16)
+template <typename TailEq>
+__device__ __forceinline__ int probe_tcontig(const TextArgs &A, uint32_t h, uint32_t len, uint32_t w0, uint32_t w1,
+                                             uint32_t w2, uint32_t w3, TailEq tail_eq) {
+    const int4 *tab = reinterpret_cast<const int4 *>(A.thash);
     for (uint32_t s = h & A.thash_mask;; s = (s + 1) & A.thash_mask) {
-        const NameEnt e = A.thash[s];
-        if (e.id < 0) return -1;
-        if (e.hash == h && e.len == len) {
-            uint32_t i = 0;
-            while (i < len && __ldg(A.tname_chars + e.off + i) == (char)R.at(a + i)) i++;
-            if (i == len) return e.id;
-        }
+        const int4 e0 = __ldg(tab + 2 * s), e1 = __ldg(tab + 2 * s + 1);
+        if (e0.y < 0) return -1;
+        if ((uint32_t)e0.x == h && (uint32_t)e0.w == len && (uint32_t)e1.x == w0 && (uint32_t)e1.y == w1 &&
+            (uint32_t)e1.z == w2 && (uint32_t)e1.w == w3 && (len <= 16u || tail_eq((uint32_t)e0.z)))
+            return e0.y;
     }
+}
+
+__device__ __forceinline__ int lookup_tcontig(const TextArgs &A, const Reader &R, uint64_t a, uint64_t b) {
+    const uint32_t len = (uint32_t)(b - a);
+    uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 16; i++)
+        if ((uint32_t)i < len) w[i >> 2] |= (uint32_t)R.at(a + i) << (8 * (i & 3));
+    uint32_t h = name_hash_head(w[0], w[1], w[2], w[3], len);
+    for (uint64_t p = a + 16; p < b; p++) h = name_hash_tail(h, (uint8_t)R.at(p));
+    h = name_hash_fin(h);
+    return probe_tcontig(A, h, len, w[0], w[1], w[2], w[3], [&](uint32_t off) {
+        uint32_t i = 16;
+        while (i < len && __ldg(A.tname_chars + off + i) == (char)R.at(a + i)) i++;
+        return i == len;
+    });
 }
 
 enum { LN_RECORD = 0, LN_SKIP = 1, LN_ERROR = 2 };
@@ -260,8 +289,9 @@ __device__ __forceinline__ char *put_i32(char *d, int v) {
     return e;
 }
 
+// (plain loads: inside the text kernel the destination-name table usually lives in shared memory)
 __device__ __forceinline__ uint32_t qname_len(const TextArgs &A, int qcid) {
-    return __ldg(A.qname_off + qcid + 1) - __ldg(A.qname_off + qcid);
+    return A.qname_off[qcid + 1] - A.qname_off[qcid];
 }
 
 // bytes of one lifted row (bed.d:161-199)
@@ -289,8 +319,8 @@ __device__ __forceinline__ char *copy_field(char *d, const Reader &R, uint64_t a
 }
 
 __device__ __forceinline__ char *emit_qname(char *d, const TextArgs &A, int qcid) {
-    const uint32_t o = __ldg(A.qname_off + qcid), e = __ldg(A.qname_off + qcid + 1);
-    for (uint32_t i = o; i < e; i++) *d++ = __ldg(A.qname_chars + i);  // bed.d:163
+    const uint32_t o = A.qname_off[qcid], e = A.qname_off[qcid + 1];
+    for (uint32_t i = o; i < e; i++) *d++ = A.qname_chars[i];  // bed.d:163
     return d;
 }
 
@@ -435,6 +465,7 @@ enum { FL_NONE = 0, FL_FAST = 1, FL_SLOW = 2 };
 struct FastLine {
     int numf;             // 3..8 (saturated)
     int tcid, start, end;
+    uint32_t len0;        // length of the contig name
     uint32_t q;           // window offset of the terminating '\n'
     uint32_t e2;          // window offset of the separator after field 2 (== q when numf == 3)
     uint32_t a5, a6, b7;  // first byte of field 5, first byte of field 6, end of field 7
@@ -442,73 +473,127 @@ struct FastLine {
     unsigned char strand;
 };
 
-__device__ __forceinline__ int lookup_tcontig_win(const TextArgs &A, const unsigned char *win, uint32_t p, uint32_t len,
-                                                  uint32_t h) {
-    for (uint32_t s = h & A.thash_mask;; s = (s + 1) & A.thash_mask) {
-        const int4 raw = __ldg(reinterpret_cast<const int4 *>(A.thash) + s);
-        if (raw.y < 0) return -1;
-        if ((uint32_t)raw.x == h && (uint32_t)raw.w == len) {
-            const char *nm = A.tname_chars + (uint32_t)raw.z;
-            uint32_t i = 0;
-            while (i < len && (unsigned char)__ldg(nm + i) == win[p + i]) i++;
-            if (i == len) return raw.y;
-        }
-    }
+// ---- word-wide access to the staged window -----------------------------------------
+// 16 bytes starting at window offset i (any alignment): five aligned word loads and four
+// funnel shifts, issued together (one shared-memory latency for the whole chunk)
+__device__ __forceinline__ void load16(const uint32_t *W, uint32_t i, uint32_t &x0, uint32_t &x1, uint32_t &x2,
+                                       uint32_t &x3) {
+    const uint32_t wi = i >> 2, sh = (i & 3u) * 8u;
+    const uint32_t a = W[wi], b = W[wi + 1], c = W[wi + 2], d = W[wi + 3], e = W[wi + 4];
+    x0 = __funnelshift_r(a, b, sh);
+    x1 = __funnelshift_r(b, c, sh);
+    x2 = __funnelshift_r(c, d, sh);
+    x3 = __funnelshift_r(d, e, sh);
 }
-
-// digits at win[i...]: value, returns the offset of the first non-digit
-__device__ __forceinline__ uint32_t parse_digits(const unsigned char *win, uint32_t i, uint32_t &v) {
-    uint32_t x = 0, d;
-    while ((d = (uint32_t)win[i] - '0') <= 9u) {
-        x = x * 10u + d;
-        i++;
-    }
-    v = x;
-    return i;
+__device__ __forceinline__ void load12(const uint32_t *W, uint32_t i, uint32_t &x0, uint32_t &x1, uint32_t &x2) {
+    const uint32_t wi = i >> 2, sh = (i & 3u) * 8u;
+    const uint32_t a = W[wi], b = W[wi + 1], c = W[wi + 2], d = W[wi + 3];
+    x0 = __funnelshift_r(a, b, sh);
+    x1 = __funnelshift_r(b, c, sh);
+    x2 = __funnelshift_r(c, d, sh);
+}
+// bit 7 of every byte of x that is <= 0x20 (field separators and other control bytes)
+__device__ __forceinline__ uint32_t le20_marks(uint32_t x) {
+    return ~(((x & 0x7F7F7F7Fu) + 0x5F5F5F5Fu) | x) & 0x80808080u;
+}
+// bit 7 of every byte of x that is not an ASCII digit
+__device__ __forceinline__ uint32_t nondigit_marks(uint32_t x) {
+    const uint32_t t = x ^ 0x30303030u;
+    return (((t & 0x7F7F7F7Fu) + 0x76767676u) | t) & 0x80808080u;
+}
+// byte k (0..11) of the 12-byte chunk x0,x1,x2
+__device__ __forceinline__ uint32_t chunk_byte(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t k) {
+    const uint32_t w = k < 4u ? x0 : (k < 8u ? x1 : x2);
+    return (w >> ((k & 3u) * 8u)) & 0xFFu;
+}
+// Unsigned decimal of 1..9 digits at window offset i: value, digit count and the byte that
+// follows.  false: no digit, or more than 9 digits (generic path decides).
+__device__ __forceinline__ bool parse_uint_swar(const uint32_t *W, uint32_t i, uint32_t &val, uint32_t &n,
+                                                uint32_t &term) {
+    uint32_t x0, x1, x2;
+    load12(W, i, x0, x1, x2);
+    const uint32_t m0 = nondigit_marks(x0), m1 = nondigit_marks(x1), m2 = nondigit_marks(x2);
+    if (m0) n = (uint32_t)(__ffs((int)m0) - 1) >> 3;
+    else if (m1) n = 4u + ((uint32_t)(__ffs((int)m1) - 1) >> 3);
+    else if (m2) n = 8u + ((uint32_t)(__ffs((int)m2) - 1) >> 3);
+    else return false;
+    if (n == 0u || n > 9u) return false;
+    term = chunk_byte(x0, x1, x2, n);
+    const uint32_t k = n < 8u ? n : 8u;
+    // the first k digits, as 8 text positions with leading zeros
+    unsigned long long tt = ((unsigned long long)(x1 ^ 0x30303030u) << 32) | (x0 ^ 0x30303030u);
+    tt <<= 8u * (8u - k);
+    const uint32_t lo = (uint32_t)tt, hi = (uint32_t)(tt >> 32);
+    const uint32_t ul = (lo * 10u + (lo >> 8)) & 0x00FF00FFu, uh = (hi * 10u + (hi >> 8)) & 0x00FF00FFu;
+    const uint32_t vl = (ul & 0xFFFFu) * 100u + (ul >> 16), vh = (uh & 0xFFFFu) * 100u + (uh >> 16);
+    val = vl * 10000u + vh;
+    if (n == 9u) val = val * 10u + ((x2 ^ 0x30u) & 0xFFu);
+    return true;
 }
 
 // Parse the line starting at window offset p.  `limit`: a terminator at or beyond
 // this offset is not a real line end (the line runs out of the staged window).
+// On FL_FAST the first 16 name bytes are left in nw[4] (zero padded) for the lookup.
 __device__ __forceinline__ int fast_parse(const TextArgs &A, const unsigned char *win, uint32_t p, uint32_t limit,
-                                          FastLine &F) {
-    uint32_t i = p;
-    uint32_t c = win[i];
-    if (c == '#') return FL_NONE;  // bed.d:115
-    if (c == 't' || c == 'b') {    // bed.d:116 ("track" / "brows"); the window is padded, the reads are safe
-        const uint32_t c1 = win[i + 1], c2 = win[i + 2], c3 = win[i + 3], c4 = win[i + 4];
-        if (c == 't' && c1 == 'r' && c2 == 'a' && c3 == 'c' && c4 == 'k') return FL_NONE;
-        if (c == 'b' && c1 == 'r' && c2 == 'o' && c3 == 'w' && c4 == 's') return FL_NONE;
+                                          FastLine &F, uint32_t (&nw)[4]) {
+    const uint32_t *W = reinterpret_cast<const uint32_t *>(win);
+    load16(W, p, nw[0], nw[1], nw[2], nw[3]);
+    {
+        const uint32_t c = nw[0] & 0xFFu;
+        if (c == '#') return FL_NONE;  // bed.d:115
+        if ((nw[0] == 0x63617274u && (nw[1] & 0xFFu) == 'k') || (nw[0] == 0x776F7262u && (nw[1] & 0xFFu) == 's'))
+            return FL_NONE;  // bed.d:116 "track" / "brows"
     }
-    uint32_t h = 0x9E3779B9u;
-    while (c > 0x20u) {
-        h = (h ^ c) * 0x01000193u;
-        c = win[++i];
+    // contig name: up to the first byte <= 0x20, which must be a tab
+    uint32_t len0;
+    {
+        const uint32_t m0 = le20_marks(nw[0]), m1 = le20_marks(nw[1]), m2 = le20_marks(nw[2]), m3 = le20_marks(nw[3]);
+        if (m0) len0 = (uint32_t)(__ffs((int)m0) - 1) >> 3;
+        else if (m1) len0 = 4u + ((uint32_t)(__ffs((int)m1) - 1) >> 3);
+        else if (m2) len0 = 8u + ((uint32_t)(__ffs((int)m2) - 1) >> 3);
+        else if (m3) len0 = 12u + ((uint32_t)(__ffs((int)m3) - 1) >> 3);
+        else {  // 16 bytes or more
+            len0 = 16;
+            while (win[p + len0] > 0x20u) len0++;
+        }
     }
-    if (c != '\t' || i == p) return FL_SLOW;
-    h ^= h >> 15;
-    const uint32_t len0 = i - p;
-    uint32_t v, j;
-    j = parse_digits(win, i + 1, v);
-    if (win[j] != '\t' || j == i + 1 || j - (i + 1) > 9u) return FL_SLOW;
+    if (len0 == 0u || win[p + len0] != '\t') return FL_SLOW;
+    if (len0 < 16u) {  // zero the bytes after the name
+        const uint32_t keep = len0 & 3u ? 0xFFFFFFFFu >> (32u - 8u * (len0 & 3u)) : 0u;
+        const uint32_t wi = len0 >> 2;
+        nw[0] = wi == 0 ? nw[0] & keep : nw[0];
+        nw[1] = wi == 1 ? nw[1] & keep : (wi < 1 ? 0u : nw[1]);
+        nw[2] = wi == 2 ? nw[2] & keep : (wi < 2 ? 0u : nw[2]);
+        nw[3] = wi == 3 ? nw[3] & keep : (wi < 3 ? 0u : nw[3]);
+    }
+    F.len0 = len0;
+    uint32_t v, n, term;
+    uint32_t i = p + len0 + 1;
+    if (!parse_uint_swar(W, i, v, n, term) || term != '\t') return FL_SLOW;
     F.start = (int)v;
-    i = j;
-    j = parse_digits(win, i + 1, v);
-    if (j == i + 1 || j - (i + 1) > 9u) return FL_SLOW;
+    i += n + 1;
+    if (!parse_uint_swar(W, i, v, n, term)) return FL_SLOW;
     F.end = (int)v;
+    uint32_t j = i + n;
     F.e2 = j;
     F.a5 = F.a6 = F.b7 = 0;
     F.v6 = F.v7 = 0;
     F.strand = 0;
-    c = win[j];
+    uint32_t c = term;
     int f = 3;
     bool ok67 = true;
     while (c == '\t') {
         const uint32_t a = j + 1;
         if (f == 6 || f == 7) {
-            j = parse_digits(win, a, v);
-            c = win[j];
-            if (c > 0x20u || j - a > 9u) ok67 = false;  // sign, junk or too long: generic path decides
-            while (c > 0x20u) c = win[++j];
+            if (parse_uint_swar(W, a, v, n, term) && term <= 0x20u) {
+                j = a + n;
+                c = term;
+            } else {  // sign, junk or too long: generic path decides
+                ok67 = false;
+                j = a;
+                c = win[j];
+                while (c > 0x20u) c = win[++j];
+            }
             if (f == 6) {
                 F.a6 = a;
                 F.v6 = (int)v;
@@ -532,8 +617,20 @@ __device__ __forceinline__ int fast_parse(const TextArgs &A, const unsigned char
     F.q = j;
     F.numf = f < 8 ? f : 8;
     if (F.numf >= 8 && !ok67) return FL_SLOW;
-    F.tcid = lookup_tcontig_win(A, win, p, len0, h);
     return FL_FAST;
+}
+
+// contig lookup for a fast-path line: nw = first 16 name bytes (zero padded)
+__device__ __forceinline__ int lookup_tcontig_win(const TextArgs &A, const unsigned char *win, uint32_t p, uint32_t len,
+                                                  const uint32_t (&nw)[4]) {
+    uint32_t h = name_hash_head(nw[0], nw[1], nw[2], nw[3], len);
+    for (uint32_t i = 16; i < len; i++) h = name_hash_tail(h, win[p + i]);
+    h = name_hash_fin(h);
+    return probe_tcontig(A, h, len, nw[0], nw[1], nw[2], nw[3], [&](uint32_t off) {
+        uint32_t i = 16;
+        while (i < len && (unsigned char)__ldg(A.tname_chars + off + i) == win[p + i]) i++;
+        return i == len;
+    });
 }
 
 // bytes of a fast-path row that do not depend on the block
@@ -556,8 +653,8 @@ __device__ __forceinline__ char *copy_span(char *d, const unsigned char *win, ui
     for (; a < b; a++) *d++ = (char)win[a];
     return d;
 }
-__device__ __forceinline__ void fast_emit_row(char *d, const TextArgs &A, const unsigned char *win, const FastLine &F,
-                                              const Thick &th, const RowCore &r, unsigned char strand_byte) {
+__device__ __forceinline__ char *fast_emit_row(char *d, const TextArgs &A, const unsigned char *win, const FastLine &F,
+                                               const Thick &th, const RowCore &r, unsigned char strand_byte) {
     d = emit_qname(d, A, r.qcid);
     *d++ = '\t';
     d = put_i32(d, r.s);
@@ -583,6 +680,7 @@ __device__ __forceinline__ void fast_emit_row(char *d, const TextArgs &A, const 
         }
     }
     *d = '\n';
+    return d + 1;
 }
 
 // copy n bytes from shared memory (4-byte aligned base) to global dst with
@@ -629,58 +727,104 @@ struct TextSmem {
     unsigned long long scan64[TX_NB * TX_NW];
     uint32_t scan32[TX_NW + 1];
     uint64_t base_l, base_u;
+    unsigned long long lb_part[TX_NW][2];
+    int lb_found[TX_NW][2];
     int tile;
     int wl_n;
+    // bracket of a sorted tile: the blocks overlapping [first line start, last line end)
+    int br_cnt;  // -1: none
+    int br_tcid, br_lo_q, br_hi_q, br_blo;
+    uint32_t br_name_off, br_name_len;
+    int4 br_blk[TX_BR_CAP];
+    int4 cmeta[TX_CM_CAP];  // per-contig {first block, end block, Eytzinger offset, samples}
+    // destination contig names
+    uint32_t qoff[TX_QN_MAX + 1];
+    char qchars[TX_QCHARS];
     uint32_t wl_p0[TX_WL_CAP];   // line start, window offset
     int wl_lo[TX_WL_CAP];
     int wl_cnt[TX_WL_CAP];
     uint32_t wl_off[TX_WL_CAP];  // byte offset inside the tile's lifted output
 };
 
-// What a thread keeps about one line between the count and the emit phase.
+// What a thread keeps about one line between the count and the emit phase (8 words).
+//   meta: bits 0-1 kind, 2-3 hit class (0, 1, 2 = two or more), 4-6 numf-3, 7-14 strand byte,
+//         one hit:  15 invert<0, 16 thick.has, 17-31 qcid
+//         >= 2 hits: 15 rows already ascending in qStart, 16 strictly descending, 17-31 tcid
 struct LineState {
     uint32_t pq;    // p | q << 16 : window offsets of the line start and of its '\n'
     uint32_t e2a5;  // FastLine.e2 | a5 << 16
     uint32_t a6b7;  // FastLine.a6 | b7 << 16
-    uint32_t meta;  // bits 0-1 kind, 2-5 numf, 6-13 strand byte, 14 invert<0, 15 thick.has, 16-31 qcid
-    int a, b;       // nh == 1: row start,end ; nh >= 2 (fast line): query start,end
-    int lo, ncand;  // candidate blocks
-    int nh;         // overlapping blocks
-    int ths, the;   // lifted thickStart/thickEnd
+    uint32_t meta;
+    int a, b;       // fast line, 1 hit: row start,end ; fast line, >= 2 hits: query start,end
+    int x, y;       // fast line, 1 hit: lifted thickStart,thickEnd ; otherwise: first candidate block, candidates
 };
+__device__ __forceinline__ int st_kind(const LineState &st) { return (int)(st.meta & 3u); }
+__device__ __forceinline__ int st_hits(const LineState &st) { return (int)((st.meta >> 2) & 3u); }
 
 // per-tile constants shared by the helpers
 struct TileCtx {
     const unsigned char *win;
     const int2 *ey;
+    const TextSmem *S;
     Reader R;
     uint64_t g0;     // absolute offset of window offset s0
     uint32_t s0;
     uint32_t limit;  // see fast_parse
 };
 
-// Count side of one line: parse, look up, search, exact output lengths.
-__device__ __forceinline__ void line_count(const TextArgs &A, const TileCtx &X, uint32_t p, LineState &st,
-                                           uint32_t &len_l, uint32_t &len_u, bool &is_err) {
+// Count side of one line: parse, look up, search, exact output lengths.  Returns the
+// number of overlapping blocks, -1 for a line that is not a record, -2 for a malformed one.
+__device__ __forceinline__ int line_count(const TextArgs &A, const TileCtx &X, uint32_t p, LineState &st,
+                                          uint32_t &len_l, uint32_t &len_u) {
     const TableView &T = A.T;
     len_l = len_u = 0;
-    is_err = false;
     st.pq = p;
     st.e2a5 = st.a6b7 = 0;
-    st.a = st.b = st.lo = st.ncand = st.nh = st.ths = st.the = 0;
+    st.a = st.b = st.x = st.y = 0;
+    st.meta = FL_NONE;
     FastLine F;
-    int kind = fast_parse(A, X.win, p, X.limit, F);
-    uint32_t meta = 0;
+    uint32_t nw[4];
+    const int kind = fast_parse(A, X.win, p, X.limit, F, nw);
+    if (kind == FL_NONE) return -1;
     if (kind == FL_FAST) {
-        const Cand cd = find_candidates(T, X.ey, F.tcid, F.start, F.end);
+        const TextSmem &S = *X.S;
+        // sorted tiles: the query usually falls inside the tile's bracket, whose blocks are
+        // in shared memory -> contig lookup and block search without a global load
+        bool inb = S.br_cnt >= 0 && F.len0 == S.br_name_len && F.start >= S.br_lo_q && F.end <= S.br_hi_q &&
+                   F.end > F.start;
+        if (inb) {
+            uint32_t i = 0;
+            while (i < F.len0 && X.win[p + i] == X.win[S.br_name_off + i]) i++;
+            inb = i == F.len0;
+        }
+        Cand cd;
+        Block b0{0, 0, 0, 0};
+        if (inb) {
+            F.tcid = S.br_tcid;
+            int lo = 0, hi = S.br_cnt;
+            while (lo < hi) {  // first block with tEnd > start
+                const int mid = (lo + hi) >> 1;
+                if (S.br_blk[mid].y > F.start) hi = mid;
+                else lo = mid + 1;
+            }
+            int k = lo;
+            while (k < S.br_cnt && S.br_blk[k].x < F.end) k++;
+            cd.lo = S.br_blo + lo;
+            cd.hi = S.br_blo + k;
+            if (k > lo) {
+                const int4 v = S.br_blk[lo];
+                b0 = Block{v.x, v.y, v.z, v.w};
+            }
+        } else {
+            F.tcid = lookup_tcontig_win(A, X.win, p, F.len0, nw);
+            cd = find_candidates_b0(T, X.ey, F.tcid, F.start, F.end, b0);
+        }
         const int nh = count_hits(T, cd, F.start);
         st.pq = p | (F.q << 16);
         st.e2a5 = F.e2 | (F.a5 << 16);
         st.a6b7 = F.a6 | (F.b7 << 16);
-        st.lo = cd.lo;
-        st.ncand = cd.hi - cd.lo;
-        st.nh = nh;
-        meta = ((uint32_t)F.numf << 2) | ((uint32_t)F.strand << 6);
+        uint32_t meta = FL_FAST | ((uint32_t)(nh < 2 ? nh : 2) << 2) | ((uint32_t)(F.numf - 3) << 4) |
+                        ((uint32_t)F.strand << 7);
         if (nh == 0) {
             len_u = F.q - p + 1;
         } else {
@@ -690,46 +834,62 @@ __device__ __forceinline__ void line_count(const TextArgs &A, const TileCtx &X, 
             RowCore r;
             r.key = r.s = r.e = r.qcid = 0;
             r.inv = 1;
+            bool asc = true, desc = true, first = true;
+            int prev_key = 0;
             for (int j = cd.lo; j < cd.hi; j++) {
-                const Block b = load_block(T, j);
+                Block b = b0;
+                if (j > cd.lo) {
+                    if (inb) {
+                        const int4 v = S.br_blk[j - S.br_blo];
+                        b = Block{v.x, v.y, v.z, v.w};
+                    } else {
+                        b = load_block(T, j);
+                    }
+                }
                 if (!T.disjoint && !block_hits(b, F.start)) continue;
                 r = make_row(b, F.start, F.end);
                 len_l += fast_row_len(A, F, fixed, th, r);
+                if (!first) {  // are the rows already in output order (bed.d:156-157), or exactly reversed?
+                    asc = asc && r.key >= prev_key;
+                    desc = desc && r.key < prev_key;
+                }
+                first = false;
+                prev_key = r.key;
             }
-            st.ths = th.ts;
-            st.the = th.te;
-            meta |= th.has ? (1u << 15) : 0u;
             if (nh == 1) {
                 st.a = r.s;
                 st.b = r.e;
-                meta |= (r.inv < 0 ? (1u << 14) : 0u) | ((uint32_t)r.qcid << 16);
+                st.x = th.ts;
+                st.y = th.te;
+                meta |= (r.inv < 0 ? (1u << 15) : 0u) | (th.has ? (1u << 16) : 0u) | ((uint32_t)r.qcid << 17);
             } else {
                 st.a = F.start;
                 st.b = F.end;
+                st.x = cd.lo;
+                st.y = cd.hi - cd.lo;
+                // bits 15/16: candidate order is ascending / strictly descending in qStart; 17-31: tcid
+                meta |= (asc ? (1u << 15) : 0u) | (!asc && desc ? (1u << 16) : 0u) |
+                        ((uint32_t)(F.tcid < 0x7FFF ? F.tcid : 0x7FFF) << 17);
             }
         }
-    } else if (kind == FL_SLOW) {
-        SlowCount C;
-        slow_count(A, X.ey, X.R, X.g0 + (p - X.s0), C);
-        if (C.status == LN_ERROR) {
-            is_err = true;
-            kind = FL_NONE;
-        } else if (C.status == LN_SKIP) {
-            kind = FL_NONE;
-        } else {
-            len_l = C.len_l;
-            len_u = C.len_u;
-            st.lo = C.lo;
-            st.ncand = C.ncand;
-            st.nh = C.nhits;
-        }
+        st.meta = meta;
+        return nh;
     }
-    st.meta = meta | (uint32_t)kind;
+    SlowCount C;
+    slow_count(A, X.ey, X.R, X.g0 + (p - X.s0), C);
+    if (C.status == LN_ERROR) return -2;
+    if (C.status == LN_SKIP) return -1;
+    len_l = C.len_l;
+    len_u = C.len_u;
+    st.x = C.lo;
+    st.y = C.ncand;
+    st.meta = FL_SLOW | ((uint32_t)(C.nhits < 2 ? C.nhits : 2) << 2);
+    return C.nhits;
 }
 
-__device__ __forceinline__ void state_to_fast(const LineState &st, FastLine &F, Thick &th) {
-    F.numf = (int)((st.meta >> 2) & 15u);
-    F.strand = (unsigned char)((st.meta >> 6) & 255u);
+__device__ __forceinline__ void state_to_fast(const LineState &st, FastLine &F) {
+    F.numf = (int)((st.meta >> 4) & 7u) + 3;
+    F.strand = (unsigned char)((st.meta >> 7) & 255u);
     F.q = st.pq >> 16;
     F.e2 = st.e2a5 & 0xFFFFu;
     F.a5 = st.e2a5 >> 16;
@@ -739,18 +899,16 @@ __device__ __forceinline__ void state_to_fast(const LineState &st, FastLine &F, 
     F.start = st.a;
     F.end = st.b;
     F.v6 = F.v7 = 0;
-    th.has = (int)((st.meta >> 15) & 1u);
-    th.ts = st.ths;
-    th.te = st.the;
 }
 
-// A fast line with a handful of hits, expanded by its own thread: every row's sorted
-// position (qStart, then block order: bed.d:156-157), byte offset and cumulative
-// strand byte (bed.d:173) are computed directly.
-__device__ __forceinline__ void fast_expand_small(const TextArgs &A, const unsigned char *win, const FastLine &F,
-                                                  const Thick &th, int lo, int ncand, char *dst) {
+// A fast line (fewer than 8 columns) with a handful of hits, expanded by its own thread:
+// every row's sorted position (qStart, then block order: bed.d:156-157), byte offset and
+// cumulative strand byte (bed.d:173) are computed directly.
+__device__ __forceinline__ void fast_expand_small(const TextArgs &A, const unsigned char *win, const FastLine &F, int lo,
+                                                  int ncand, char *dst) {
     const TableView &T = A.T;
     const uint32_t fixed = fast_fixed_len(F);
+    const Thick th{0, 0, 0};
     for (int c = 0; c < ncand; c++) {
         const Block bj = load_block(T, lo + c);
         if (!T.disjoint && !block_hits(bj, F.start)) continue;
@@ -780,49 +938,82 @@ __device__ __forceinline__ void fast_expand_small(const TextArgs &A, const unsig
     }
 }
 
+// A fast line whose hits are already in output order (or exactly reversed, '-' chains):
+// one sequential pass, the strand byte flipping cumulatively as the reference's in-place
+// update does (bed.d:173).
+__device__ __forceinline__ void fast_expand_sorted(const TextArgs &A, const TileCtx &X, const FastLine &F, int tcid,
+                                                   int lo, int ncand, bool reversed, char *dst) {
+    const TableView &T = A.T;
+    Thick th{0, 0, 0};
+    if (F.numf >= 8) {  // thickStart / thickEnd are re-read from the line (not kept between the phases)
+        const uint32_t *W = reinterpret_cast<const uint32_t *>(X.win);
+        uint32_t v6 = 0, v7 = 0, n6 = 0, n7 = 0, term;
+        parse_uint_swar(W, F.a6, v6, n6, term);
+        parse_uint_swar(W, F.a6 + n6 + 1, v7, n7, term);
+        th = lift_thick(T, X.ey, tcid, (int)v6, (int)v7);
+    }
+    unsigned char sb = F.strand;
+    char *d = dst;
+    for (int c = 0; c < ncand; c++) {
+        const Block b = load_block(T, reversed ? lo + ncand - 1 - c : lo + c);
+        if (!T.disjoint && !block_hits(b, F.start)) continue;
+        const RowCore r = make_row(b, F.start, F.end);
+        if (F.numf >= 6) sb = strand_flip(sb, r.inv);
+        d = fast_emit_row(d, A, X.win, F, th, r, sb);
+    }
+}
+
 constexpr int TX_SMALL_FANOUT = 6;
+constexpr int TX_SEQ_FANOUT = 48;  // sorted multi-hit lines up to this many candidates stay with their thread
 
 // Emit side of one line.  dst_l / dst_u = where this line's lifted / unmatched text goes
 // (nullptr: that stream is not written, e.g. the caller's buffer is too small).
 __device__ __forceinline__ void line_emit(const TextArgs &A, const TileCtx &X, TextSmem &S, const LineState &st,
                                           char *dst_l, char *dst_u, uint32_t o_l) {
-    const int kind = (int)(st.meta & 3u);
+    const int kind = st_kind(st);
     if (kind == FL_NONE) return;
+    const int nhc = st_hits(st);
     const uint32_t p = st.pq & 0xFFFFu;
-    if (st.nh == 0) {
+    if (nhc == 0) {
         if (!dst_u) return;
         if (kind == FL_FAST) copy_span(dst_u, X.win, p, (st.pq >> 16) + 1);
-        else slow_emit(A, X.ey, X.R, X.g0 + (p - X.s0), st.lo, 0, dst_u);
+        else slow_emit(A, X.ey, X.R, X.g0 + (p - X.s0), st.x, 0, dst_u);
         return;
     }
     if (!dst_l) return;
-    if (kind == FL_FAST && st.nh == 1) {
+    if (kind == FL_FAST && nhc == 1) {
         FastLine F;
+        state_to_fast(st, F);
         Thick th;
-        state_to_fast(st, F, th);
+        th.has = (int)((st.meta >> 16) & 1u);
+        th.ts = st.x;
+        th.te = st.y;
         RowCore r;
         r.s = st.a;
         r.e = st.b;
-        r.qcid = (int)(st.meta >> 16);
-        r.inv = (st.meta >> 14) & 1u ? -1 : 1;
+        r.qcid = (int)(st.meta >> 17);
+        r.inv = (st.meta >> 15) & 1u ? -1 : 1;
         r.key = 0;
         fast_emit_row(dst_l, A, X.win, F, th, r, strand_flip(F.strand, r.inv));
-    } else if (kind == FL_FAST && st.ncand <= TX_SMALL_FANOUT) {
+    } else if (kind == FL_FAST && (st.meta & (3u << 15)) && st.y <= TX_SEQ_FANOUT && (st.meta >> 17) != 0x7FFFu) {
         FastLine F;
-        Thick th;
-        state_to_fast(st, F, th);
-        fast_expand_small(A, X.win, F, th, st.lo, st.ncand, dst_l);
-    } else if (st.nh == 1) {
-        slow_emit(A, X.ey, X.R, X.g0 + (p - X.s0), st.lo, 1, dst_l);
+        state_to_fast(st, F);
+        fast_expand_sorted(A, X, F, (int)(st.meta >> 17), st.x, st.y, (st.meta >> 16) & 1u, dst_l);
+    } else if (kind == FL_FAST && st.y <= TX_SMALL_FANOUT && ((st.meta >> 4) & 7u) < 5u) {
+        FastLine F;
+        state_to_fast(st, F);
+        fast_expand_small(A, X.win, F, st.x, st.y, dst_l);
+    } else if (nhc == 1) {
+        slow_emit(A, X.ey, X.R, X.g0 + (p - X.s0), st.x, 1, dst_l);
     } else {
         const int slot = atomicAdd(&S.wl_n, 1);
         if (slot < TX_WL_CAP) {
             S.wl_p0[slot] = p;
-            S.wl_lo[slot] = st.lo;
-            S.wl_cnt[slot] = st.ncand;
+            S.wl_lo[slot] = st.x;
+            S.wl_cnt[slot] = st.y;
             S.wl_off[slot] = o_l;
         } else {
-            expand_line(A, X.ey, X.R, X.g0 + (p - X.s0), st.lo, st.ncand, dst_l, 0, 1);
+            expand_line(A, X.ey, X.R, X.g0 + (p - X.s0), st.x, st.y, dst_l, 0, 1);
         }
     }
 }
@@ -854,10 +1045,125 @@ __device__ __forceinline__ void block_scan_multi(const unsigned long long (&v)[N
     }
 }
 
-__global__ void __launch_bounds__(TX_TPB, 3) lift_bed_text_kernel(const TextArgs A) {
+// digits at win[i...]: value, returns the offset of the first non-digit
+__device__ __forceinline__ uint32_t parse_digits(const unsigned char *win, uint32_t i, uint32_t &v) {
+    uint32_t x = 0, d;
+    while ((d = (uint32_t)win[i] - '0') <= 9u) {
+        x = x * 10u + d;
+        i++;
+    }
+    v = x;
+    return i;
+}
+// first three fields of a canonical line (used for the tile bracket)
+__device__ __forceinline__ bool parse_head(const unsigned char *win, uint32_t p, uint32_t limit, uint32_t &name_len,
+                                           int &start, int &end) {
+    uint32_t i = p;
+    while (win[i] > 0x20u) i++;
+    if (win[i] != '\t' || i == p) return false;
+    name_len = i - p;
+    uint32_t v, j = parse_digits(win, i + 1, v);
+    if (win[j] != '\t' || j == i + 1 || j - (i + 1) > 9u) return false;
+    start = (int)v;
+    i = j;
+    j = parse_digits(win, i + 1, v);
+    if (j == i + 1 || j - (i + 1) > 9u || j >= limit || (win[j] != '\t' && win[j] != '\n')) return false;
+    end = (int)v;
+    return true;
+}
+
+// Block-wide resolve of both look-back chains: 256 predecessors per round instead of 32.
+// Every thread of the block calls it; returns the exclusive prefixes in S.base_l / S.base_u.
+__device__ __forceinline__ void lookback_resolve2_block(TextSmem &S, uint64_t *desc_l, uint64_t *desc_u, int tile,
+                                                        uint64_t agg_l, uint64_t agg_u) {
+    uint64_t ex_l = 0, ex_u = 0;
+    bool done_l = tile == 0, done_u = tile == 0;
+    int look = tile - 1;
+    while (!(done_l && done_u)) {
+        const int idx = look - (int)threadIdx.x;
+        uint64_t vl = LB_INC, vu = LB_INC;  // virtual tile before tile 0: inclusive prefix 0
+        if (idx >= 0) {
+            if (!done_l) {
+                vl = ld_relaxed_u64(desc_l + idx);
+                while ((vl & LB_STATE) == LB_EMPTY) {
+                    __nanosleep(20);
+                    vl = ld_relaxed_u64(desc_l + idx);
+                }
+            }
+            if (!done_u) {
+                vu = ld_relaxed_u64(desc_u + idx);
+                while ((vu & LB_STATE) == LB_EMPTY) {
+                    __nanosleep(20);
+                    vu = ld_relaxed_u64(desc_u + idx);
+                }
+            }
+        }
+        {
+            const unsigned ml = __ballot_sync(FULL, (vl & LB_STATE) == LB_INC);
+            const int fl = ml ? (__ffs(ml) - 1) : 32;
+            const uint64_t sl = warp_sum((lane_id() <= fl) ? (vl & LB_VALUE) : 0ull);
+            const unsigned mu = __ballot_sync(FULL, (vu & LB_STATE) == LB_INC);
+            const int fu = mu ? (__ffs(mu) - 1) : 32;
+            const uint64_t su = warp_sum((lane_id() <= fu) ? (vu & LB_VALUE) : 0ull);
+            __syncthreads();  // previous round's readers are done
+            if (lane_id() == 0) {
+                S.lb_part[warp_id()][0] = sl;
+                S.lb_part[warp_id()][1] = su;
+                S.lb_found[warp_id()][0] = ml != 0;
+                S.lb_found[warp_id()][1] = mu != 0;
+            }
+            __syncthreads();
+        }
+        if (!done_l) {
+            for (int w = 0; w < TX_NW; w++) {  // warps are ordered by distance from the tile
+                ex_l += S.lb_part[w][0];
+                if (S.lb_found[w][0]) {
+                    done_l = true;
+                    break;
+                }
+            }
+        }
+        if (!done_u) {
+            for (int w = 0; w < TX_NW; w++) {
+                ex_u += S.lb_part[w][1];
+                if (S.lb_found[w][1]) {
+                    done_u = true;
+                    break;
+                }
+            }
+        }
+        look -= TX_TPB;
+    }
+    if (threadIdx.x == 0) {
+        if (tile > 0) {
+            st_relaxed_u64(desc_l + tile, LB_INC | (ex_l + agg_l));
+            st_relaxed_u64(desc_u + tile, LB_INC | (ex_u + agg_u));
+        }
+        S.base_l = ex_l;
+        S.base_u = ex_u;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(TX_TPB, TX_MIN_CTAS) lift_bed_text_kernel(const TextArgs A0) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TextSmem &S = *reinterpret_cast<TextSmem *>(smem_raw);
     const int tid = threadIdx.x;
+    TextArgs A = A0;
+    {  // destination contig names -> shared memory when they fit (once per persistent CTA)
+        const int nq = A0.nq;
+        if (nq <= TX_QN_MAX && A0.qname_off[nq] <= (uint32_t)TX_QCHARS) {
+            for (int i = tid; i <= nq; i += TX_TPB) S.qoff[i] = A0.qname_off[i];
+            const uint32_t nc = A0.qname_off[nq];
+            for (uint32_t i = tid; i < nc; i += TX_TPB) S.qchars[i] = A0.qname_chars[i];
+            A.qname_off = S.qoff;
+            A.qname_chars = S.qchars;
+        }
+    }
+    if (A0.T.ntc <= TX_CM_CAP) {  // per-contig table -> shared memory
+        for (int i = tid; i < A0.T.ntc; i += TX_TPB) S.cmeta[i] = A0.T.cmeta[i];
+        A.T.cmeta = S.cmeta;
+    }
     const TableView &T = A.T;
     unsigned char *const win = reinterpret_cast<unsigned char *>(S.in_words);
     char *const stage_l = reinterpret_cast<char *>(S.out_words);
@@ -865,6 +1171,31 @@ __global__ void __launch_bounds__(TX_TPB, 3) lift_bed_text_kernel(const TextArgs
 
     // upper search levels -> shared memory (once per persistent CTA)
     for (int i = tid; i < T.ey_n; i += TX_TPB) S.ey[i] = __ldg(T.ey + i);
+
+    // The formatted tile stays in the stages while the NEXT tile is staged, parsed and
+    // counted (none of which touches the stages); only then is its chained offset resolved
+    // and the stage copied out.  Predecessor tiles therefore have a whole extra count phase
+    // to publish their aggregates and the look-back practically never waits.
+    bool pend = false, p_have_base = false, p_direct_l = false, p_direct_u = false;
+    int p_tile = 0;
+    uint32_t p_tot_l = 0, p_tot_u = 0;
+    uint64_t p_gb_l = 0, p_gb_u = 0;
+    auto flush = [&]() {  // block-uniform
+        if (!pend) return;
+        if (!p_have_base) {
+            lookback_resolve2_block(S, A.desc_l, A.desc_u, p_tile, (uint64_t)p_tot_l, (uint64_t)p_tot_u);
+            p_gb_l = S.base_l;
+            p_gb_u = S.base_u;
+        }
+        if (p_tile == A.ntiles - 1 && tid == 0) {
+            A.sizes[0] = p_gb_l + p_tot_l;
+            A.sizes[1] = p_gb_u + p_tot_u;
+        }
+        if (!p_direct_l && p_tot_l && p_gb_l + p_tot_l <= A.lifted_cap) copy_out(A.lifted + p_gb_l, S.out_words, p_tot_l);
+        if (!p_direct_u && p_tot_u && p_gb_u + p_tot_u <= A.unm_cap) copy_out(A.unm + p_gb_u, S.unm_words, p_tot_u);
+        pend = false;
+        __syncthreads();  // the stages may be overwritten now
+    };
 
     for (;;) {
         __syncthreads();
@@ -881,6 +1212,7 @@ __global__ void __launch_bounds__(TX_TPB, 3) lift_bed_text_kernel(const TextArgs
         TileCtx X;
         X.win = win;
         X.ey = S.ey;
+        X.S = &S;
         X.g0 = tile == 0 ? 0 : t0 - TX_PRE;  // absolute offset of the first staged byte
         X.s0 = tile == 0 ? TX_PRE : 0;       // its window offset
         const uint64_t gend = min(A.in_len, t0 + TX_TILE + TX_LOOK);
@@ -918,7 +1250,9 @@ __global__ void __launch_bounds__(TX_TPB, 3) lift_bed_text_kernel(const TextArgs
         }
         __syncthreads();
         // line starts inside this thread's 64 bytes of the tile: the byte before is '\n'
-        const unsigned long long starts = (S.nlm[tid + 1] << 1) | (S.nlm[tid] >> 63);
+        unsigned long long starts = (S.nlm[tid + 1] << 1) | (S.nlm[tid] >> 63);
+        if (tile == 0 && tid == 0)  // the text starts (with a line) at offset `skip`
+            starts = (starts & ~((1ull << A.skip) - 1ull)) | (1ull << A.skip);
         unsigned long long valid = starts;
         {
             const long long rem = (long long)A.in_len - (long long)(t0 + (uint64_t)tid * TX_SEG);
@@ -943,6 +1277,45 @@ __global__ void __launch_bounds__(TX_TPB, 3) lift_bed_text_kernel(const TextArgs
         };
         build_table(0);
 
+        // ---- bracket of a sorted tile: blocks overlapping [first line start, last line end) ----
+        if (tid == 0) {
+            int cnt = -1;
+            if (TX_USE_BRACKET && T.disjoint && nlines > 0) {
+                const uint32_t p0 = S.lstart[0], p1 = S.lstart[min(nlines, TX_LCAP) - 1];
+                uint32_t n0 = 0, n1 = 0;
+                int s_first = 0, e_first = 0, s_last = 0, e_last = 0;
+                if (parse_head(win, p0, X.limit, n0, s_first, e_first) &&
+                    parse_head(win, p1, X.limit, n1, s_last, e_last) && n0 == n1 && e_last > s_first) {
+                    uint32_t i = 0;
+                    while (i < n0 && win[p0 + i] == win[p1 + i]) i++;
+                    uint32_t nw0[4] = {0, 0, 0, 0};
+                    for (uint32_t k = 0; k < n0 && k < 16u; k++) nw0[k >> 2] |= (uint32_t)win[p0 + k] << (8u * (k & 3u));
+                    const int tcid = i == n0 ? lookup_tcontig_win(A, win, p0, n0, nw0) : -1;
+                    if (tcid >= 0) {
+                        const int4 cm = load_cmeta(T, tcid);
+                        const int blo = lower_gt_ey(T, S.ey, cm, s_first);
+                        const int bhi = gallop_ge(T.tStartKey, blo, cm.y, e_last);
+                        if (bhi - blo <= TX_BR_CAP) {
+                            cnt = bhi - blo;
+                            S.br_tcid = tcid;
+                            S.br_lo_q = s_first;
+                            S.br_hi_q = e_last;
+                            S.br_blo = blo;
+                            S.br_name_off = p0;
+                            S.br_name_len = n0;
+                        }
+                    }
+                }
+            }
+            S.br_cnt = cnt;
+        }
+        __syncthreads();
+        for (int i = tid; i < S.br_cnt; i += TX_TPB) {
+            const Block b = load_block(T, S.br_blo + i);
+            S.br_blk[i] = make_int4(b.tStart, b.tEnd, b.qStart, b.meta);
+        }
+        __syncthreads();
+
         // ---- phase C: parse + search + exact output lengths; no barrier inside ---------
         uint32_t c_rec = 0, c_rows = 0, c_unm = 0;
         LineState st[TX_NB];
@@ -951,20 +1324,18 @@ __global__ void __launch_bounds__(TX_TPB, 3) lift_bed_text_kernel(const TextArgs
         for (int b = 0; b < TX_NB; b++) {
             const int li = b * TX_TPB + tid;
             st[b].meta = FL_NONE;
-            st[b].nh = 0;
             v[b] = 0;
             if (li < nlines) {
                 uint32_t ll, lu;
-                bool err;
-                line_count(A, X, S.lstart[li], st[b], ll, lu, err);
+                const int nh = line_count(A, X, S.lstart[li], st[b], ll, lu);
                 v[b] = ((unsigned long long)ll << 32) | lu;
-                if (err)  // max(~p0) == first bad line
+                if (nh == -2)  // max(~p0) == first bad line
                     atomicMax((unsigned long long *)(A.sizes + 5),
                               ~(unsigned long long)(X.g0 + ((st[b].pq & 0xFFFFu) - X.s0)));
-                if ((st[b].meta & 3u) != FL_NONE) {
+                if (nh >= 0) {
                     c_rec++;
-                    c_rows += (uint32_t)st[b].nh;
-                    c_unm += st[b].nh == 0 ? 1u : 0u;
+                    c_rows += (uint32_t)nh;
+                    c_unm += nh == 0 ? 1u : 0u;
                 }
             }
         }
@@ -988,15 +1359,14 @@ __global__ void __launch_bounds__(TX_TPB, 3) lift_bed_text_kernel(const TextArgs
                 uint32_t ll = 0, lu = 0;
                 if (li < nlines) {
                     LineState t;
-                    bool err;
-                    line_count(A, X, S.lstart[li - wbase], t, ll, lu, err);
-                    if (err)
+                    const int nh = line_count(A, X, S.lstart[li - wbase], t, ll, lu);
+                    if (nh == -2)
                         atomicMax((unsigned long long *)(A.sizes + 5),
                                   ~(unsigned long long)(X.g0 + ((t.pq & 0xFFFFu) - X.s0)));
-                    if ((t.meta & 3u) != FL_NONE) {
+                    if (nh >= 0) {
                         c_rec++;
-                        c_rows += (uint32_t)t.nh;
-                        c_unm += t.nh == 0 ? 1u : 0u;
+                        c_rows += (uint32_t)nh;
+                        c_unm += nh == 0 ? 1u : 0u;
                     }
                 }
                 unsigned long long t1;
@@ -1024,20 +1394,13 @@ __global__ void __launch_bounds__(TX_TPB, 3) lift_bed_text_kernel(const TextArgs
         const bool direct_l = tot_l > TX_OUT_STAGE, direct_u = tot_u > TX_UNM_STAGE;
         uint64_t gb_l = 0, gb_u = 0;
         bool have_base = false;
-        auto resolve_base = [&]() {
-            if (warp_id() == 0) {
-                const uint64_t b = lookback_resolve(A.desc_l, tile, (uint64_t)tot_l);
-                if (tid == 0) S.base_l = b;
-            } else if (warp_id() == 1) {
-                const uint64_t b = lookback_resolve(A.desc_u, tile, (uint64_t)tot_u);
-                if (lane_id() == 0) S.base_u = b;
-            }
-            __syncthreads();
+        flush();  // previous tile: resolve + copy out, frees the stages
+        if (direct_l || direct_u) {
+            lookback_resolve2_block(S, A.desc_l, A.desc_u, tile, (uint64_t)tot_l, (uint64_t)tot_u);
             gb_l = S.base_l;
             gb_u = S.base_u;
             have_base = true;
-        };
-        if (direct_l || direct_u) resolve_base();
+        }
         char *const base_l = direct_l ? (gb_l + tot_l <= A.lifted_cap ? A.lifted + gb_l : nullptr) : stage_l;
         char *const base_u = direct_u ? (gb_u + tot_u <= A.unm_cap ? A.unm + gb_u : nullptr) : stage_u;
 
@@ -1064,11 +1427,7 @@ __global__ void __launch_bounds__(TX_TPB, 3) lift_bed_text_kernel(const TextArgs
                 uint32_t ll = 0, lu = 0;
                 LineState t;
                 t.meta = FL_NONE;
-                t.nh = 0;
-                if (li < nlines) {
-                    bool err;
-                    line_count(A, X, S.lstart[li - wbase], t, ll, lu, err);
-                }
+                if (li < nlines) line_count(A, X, S.lstart[li - wbase], t, ll, lu);
                 unsigned long long t1;
                 const unsigned long long e1 =
                     block_exclusive_scan<unsigned long long, TX_NW>(((unsigned long long)ll << 32) | lu, S.scan64, &t1);
@@ -1090,17 +1449,23 @@ __global__ void __launch_bounds__(TX_TPB, 3) lift_bed_text_kernel(const TextArgs
                     expand_line(A, X.ey, X.R, X.g0 + (S.wl_p0[e] - X.s0), S.wl_lo[e], S.wl_cnt[e], base_l + S.wl_off[e], tid,
                                 TX_TPB);
         }
-        __syncthreads();
-
-        // ---- chained offsets (predecessors published long ago), then copy the stages out ---
-        if (!have_base) resolve_base();
-        if (tile == A.ntiles - 1 && tid == 0) {
-            A.sizes[0] = gb_l + tot_l;
-            A.sizes[1] = gb_u + tot_u;
-        }
-        if (!direct_l && tot_l && gb_l + tot_l <= A.lifted_cap) copy_out(A.lifted + gb_l, S.out_words, tot_l);
-        if (!direct_u && tot_u && gb_u + tot_u <= A.unm_cap) copy_out(A.unm + gb_u, S.unm_words, tot_u);
+        // resolve + copy-out of this tile are deferred until the next tile has been counted
+        pend = true;
+        p_have_base = have_base;
+        p_direct_l = direct_l;
+        p_direct_u = direct_u;
+        p_tile = tile;
+        p_tot_l = tot_l;
+        p_tot_u = tot_u;
+        p_gb_l = gb_l;
+        p_gb_u = gb_u;
     }
+    flush();
+}
+
+// sizes of a finished chunk -> pinned host memory (stream-ordered after the lift kernel)
+__global__ void copy_sizes_kernel(const uint64_t *__restrict__ d_sizes, uint64_t *__restrict__ h_sizes) {
+    if (threadIdx.x < 6) h_sizes[threadIdx.x] = d_sizes[threadIdx.x];
 }
 
 }  // namespace swo

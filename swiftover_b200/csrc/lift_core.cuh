@@ -95,20 +95,29 @@ SWO_HD int lower_gt_ey(const TableView &T, const int2 *__restrict__ ey, const in
         lo = a + (m << T.ey_shift);
         hi = b;
     }
+    // inside the group: three independent probes per round (the loads of a round overlap)
     while (lo < hi) {
-        const int mid = (int)(((unsigned)lo + (unsigned)hi) >> 1);
-        if (SWO_LDG(T.pmaxKey + mid) > x) hi = mid;
-        else lo = mid + 1;
+        const int q = (hi - lo + 3) >> 2;
+        const int i1 = lo + q - 1;
+        const int i2 = i1 + q < hi ? i1 + q : hi - 1;
+        const int i3 = i2 + q < hi ? i2 + q : hi - 1;
+        const int k1 = SWO_LDG(T.pmaxKey + i1), k2 = SWO_LDG(T.pmaxKey + i2), k3 = SWO_LDG(T.pmaxKey + i3);
+        if (k1 > x) {
+            hi = i1;
+        } else if (k2 > x) {
+            lo = i1 + 1;
+            hi = i2;
+        } else if (k3 > x) {
+            lo = i2 + 1;
+            hi = i3;
+        } else {
+            lo = i3 + 1;
+        }
     }
     return lo;
 }
-SWO_HD int4 load_cmeta(const TableView &T, int tcid) {
-#if defined(__CUDA_ARCH__)
-    return __ldg(T.cmeta + tcid);
-#else
-    return T.cmeta[tcid];
-#endif
-}
+// (plain load: the text kernel keeps the per-contig table in shared memory)
+SWO_HD int4 load_cmeta(const TableView &T, int tcid) { return T.cmeta[tcid]; }
 
 // Candidate block range of the half-open query [start,end) on contig tcid:
 // every block j in [lo,hi) has tStart < end and prefix-max(tEnd) > start; the
@@ -126,6 +135,12 @@ SWO_HD Cand find_candidates(const TableView &T, const int2 *__restrict__ ey, int
     return c;
 }
 
+SWO_HD Block load_block(const TableView &T, int j);
+// Same, also returning the first candidate block (valid when hi > lo): blocks lo and
+// lo+1 are fetched together, which settles the common 0/1-hit cases in one round trip.
+SWO_HD Cand find_candidates_b0(const TableView &T, const int2 *__restrict__ ey, int tcid, int start, int end,
+                               Block &b0);
+
 SWO_HD Block load_block(const TableView &T, int j) {
 #if defined(__CUDA_ARCH__)
     const int4 v = __ldg(reinterpret_cast<const int4 *>(T.blk) + j);
@@ -133,6 +148,22 @@ SWO_HD Block load_block(const TableView &T, int j) {
 #else
     return T.blk[j];
 #endif
+}
+
+SWO_HD Cand find_candidates_b0(const TableView &T, const int2 *__restrict__ ey, int tcid, int start, int end,
+                               Block &b0) {
+    Cand c{0, 0};
+    b0 = Block{0, 0, 0, 0};
+    if (tcid < 0 || tcid >= T.ntc) return c;
+    const int4 cm = load_cmeta(T, tcid);
+    const int lo = lower_gt_ey(T, ey, cm, start);
+    c.lo = c.hi = lo;
+    if (lo >= cm.y) return c;
+    b0 = load_block(T, lo);
+    const int s1 = lo + 1 < cm.y ? SWO_LDG(T.tStartKey + lo + 1) : 0x7fffffff;
+    if (b0.tStart >= end) return c;
+    c.hi = s1 >= end ? lo + 1 : gallop_ge(T.tStartKey, lo + 2, cm.y, end);
+    return c;
 }
 
 SWO_HD bool block_hits(const Block &b, int start) { return b.tEnd > start; }

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <memory>
@@ -74,7 +75,7 @@ struct PinBuf {
     T *as() const { return reinterpret_cast<T *>(p); }
 };
 
-constexpr int N_SLOTS = 4;  // chunks in flight per device (H2D / kernel / D2H overlap)
+constexpr int N_SLOTS = 8;  // chunks in flight per device (H2D / kernel / D2H overlap)
 
 // Everything one device (or logical shard) owns.
 struct Device {
@@ -85,6 +86,7 @@ struct Device {
     DevBuf blk, tkey, pkey, toff, cmeta, ey, thash, tchars, tnoff, qoff, qchars;
     TableView T{};
     uint32_t thash_mask = 0;
+    int nq = 0;  // destination contigs
     // genome replica
     DevBuf g_packed, g_off, g_len;
     int g_n = 0;
@@ -111,7 +113,10 @@ struct swo_ctx {
     uint64_t launches = 0;
     // pinned result arenas handed to the caller
     PinBuf r_lifted, r_unm, r_off, r_rows, r_thick;
-    size_t chunk_bytes = 32u << 20;
+    size_t chunk_bytes = 64u << 20;
+    // read pinned input from the kernel over PCIe instead of staging it with H2D copies: as fast as the
+    // copy when nothing else uses the link, but slower than staging once D2H copies of the output overlap
+    bool zero_copy_input = false;
 };
 
 namespace {
@@ -161,12 +166,13 @@ int upload_table(swo_ctx *c, Device &d) {
     // source-contig name table (device text parser)
     uint32_t hs = 16;
     while (hs < (uint32_t)t.ntc() * 4u) hs <<= 1;
-    std::vector<NameEnt> ents(hs, NameEnt{0, -1, 0, 0});
+    std::vector<NameEnt> ents(hs, NameEnt{0, -1, 0, 0, {0, 0, 0, 0}});
     std::string chars;
     std::vector<uint32_t> tnoff(1, 0);
     for (int i = 0; i < t.ntc(); i++) {
         const std::string &nm = t.tnames[i];
-        NameEnt e{name_hash(nm.data(), nm.size()), i, (uint32_t)chars.size(), (uint32_t)nm.size()};
+        NameEnt e{name_hash(nm.data(), nm.size()), i, (uint32_t)chars.size(), (uint32_t)nm.size(), {0, 0, 0, 0}};
+        name_words(nm.data(), nm.size(), e.w);
         chars += nm;
         tnoff.push_back((uint32_t)chars.size());
         uint32_t s = e.hash & (hs - 1);
@@ -197,7 +203,24 @@ int upload_table(swo_ctx *c, Device &d) {
     d.T.ey_n = (int)t.eyKey.size();
     d.T.ey_shift = t.eyShift;
     d.T.ntc = t.ntc();
+    d.nq = (int)t.qnames.size();
     d.T.disjoint = t.disjoint ? 1 : 0;
+    return SWO_OK;
+}
+
+// Zeroing of the per-launch scratch (ticket + look-back descriptors) and totals.  A kernel,
+// not cudaMemsetAsync: memsets can be routed through a copy engine and then queue behind the
+// multi-MiB H2D/D2H transfers of the pipeline (seen as multi-ms stalls of single chunks).
+__global__ void zero_words_kernel(uint32_t *__restrict__ a, size_t na, uint32_t *__restrict__ b, size_t nb) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < na; i += stride) a[i] = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nb; i += stride) b[i] = 0;
+}
+int zero_async(swo_ctx *c, void *a, size_t abytes, void *b, size_t bbytes, cudaStream_t st) {
+    const size_t na = (abytes + 3) / 4, nb = (bbytes + 3) / 4;
+    const int grid = (int)std::min<size_t>(std::max<size_t>((std::max(na, nb) + 255) / 256, 1), 296);
+    zero_words_kernel<<<grid, 256, 0, st>>>((uint32_t *)a, na, (uint32_t *)b, nb);
+    CK(c, cudaGetLastError());
     return SWO_OK;
 }
 
@@ -210,11 +233,10 @@ int launch_lift_intervals(swo_ctx *c, Device &d, size_t n, const int32_t *tcid, 
                           cudaStream_t st) {
     const int ntiles = (int)((n + LI_TILE - 1) / LI_TILE);
     const size_t scratch_bytes = 16 + (size_t)ntiles * 8;
-    CK(c, d.scratch.reserve(scratch_bytes));
-    CK(c, cudaMemsetAsync(d.scratch.p, 0, scratch_bytes, st));
-    CK(c, cudaMemsetAsync(totals, 0, 16, st));
+    CK(c, d.scratch.reserve((scratch_bytes + 3) & ~(size_t)3));
+    if (int rc = zero_async(c, d.scratch.p, scratch_bytes, totals, 16, st)) return rc;
     if (n == 0) {
-        CK(c, cudaMemsetAsync(row_offset, 0, 4, st));
+        if (int rc = zero_async(c, row_offset, 4, nullptr, 0, st)) return rc;
         return SWO_OK;
     }
     LiftArgs A;
@@ -247,13 +269,13 @@ int launch_lift_intervals(swo_ctx *c, Device &d, size_t n, const int32_t *tcid, 
 }
 
 // ---- text path -------------------------------------------------------------------
+// d_in: 16-byte aligned; the text is d_in[skip, in_len) and starts with a line
 int launch_lift_text(swo_ctx *c, Device &d, const char *d_in, size_t in_len, char *d_lifted, size_t lifted_cap,
-                     char *d_unm, size_t unm_cap, uint64_t *d_sizes, cudaStream_t st) {
+                     char *d_unm, size_t unm_cap, uint64_t *d_sizes, cudaStream_t st, uint32_t skip = 0) {
     const int ntiles = (int)((in_len + TX_TILE - 1) / TX_TILE);
     const size_t scratch_bytes = 16 + (size_t)ntiles * 16;
-    CK(c, d.scratch.reserve(scratch_bytes));
-    CK(c, cudaMemsetAsync(d.scratch.p, 0, scratch_bytes, st));
-    CK(c, cudaMemsetAsync(d_sizes, 0, 48, st));
+    CK(c, d.scratch.reserve((scratch_bytes + 3) & ~(size_t)3));
+    if (int rc = zero_async(c, d.scratch.p, scratch_bytes, d_sizes, 48, st)) return rc;
     if (in_len == 0) return SWO_OK;
     TextArgs A;
     A.T = d.T;
@@ -262,7 +284,9 @@ int launch_lift_text(swo_ctx *c, Device &d, const char *d_in, size_t in_len, cha
     A.tname_chars = d.tchars.as<char>();
     A.qname_off = d.qoff.as<uint32_t>();
     A.qname_chars = d.qchars.as<char>();
+    A.nq = d.nq;
     A.in = d_in;
+    A.skip = skip;
     A.in_len = in_len;
     A.ntiles = ntiles;
     A.lifted = d_lifted;
@@ -302,35 +326,89 @@ int run_shard(swo_ctx *c, Device &d, const char *in, size_t a, size_t b, PinBuf 
     CK(c, cudaSetDevice(d.ordinal));
     CK(c, d.h_sizes.reserve(N_SLOTS * 48));
     uint64_t *hs = d.h_sizes.as<uint64_t>();
-    // chunk boundaries (line aligned)
+    // chunk boundaries (line aligned).  Sizes ramp up from chunk/16 so that the first kernel and the
+    // first D2H start early, and ramp down at the end so that little is left to drain.
     std::vector<size_t> cuts(1, a);
-    while (cuts.back() < b) {
-        size_t e = std::min(b, cuts.back() + c->chunk_bytes);
-        if (e < b) {
-            const void *nl = memchr(in + e, '\n', b - e);
-            e = nl ? (size_t)((const char *)nl - in) + 1 : b;
+    {
+        const size_t chunk = c->chunk_bytes, small = chunk / 16 + 1;
+        size_t step = small;
+        while (cuts.back() < b) {
+            const size_t pos = cuts.back(), left = b - pos;
+            size_t sz = std::min(step, chunk);
+            if (left < 2 * chunk) sz = std::min(sz, std::max(left / 2, small));
+            step = std::min(step * 2, chunk);
+            size_t e = std::min(b, pos + sz);
+            if (e < b) {
+                const void *nl = memchr(in + e, '\n', b - e);
+                e = nl ? (size_t)((const char *)nl - in) + 1 : b;
+            }
+            cuts.push_back(e);
         }
-        cuts.push_back(e);
     }
     const int nch = (int)cuts.size() - 1;
     size_t out_l = base_l, out_u = base_u;
-    auto issue = [&](int k) -> int {  // H2D + kernel + sizes readback for chunk k
+    // Pinned (or registered) host input is read by the kernel itself over PCIe (UVA zero-copy:
+    // measured at the full H2D memcpy rate), so there is no H2D copy and no staging buffer;
+    // pageable input is staged through t_in with cudaMemcpyAsync.
+    const char *zc_in = nullptr;
+    {
+        cudaPointerAttributes at;
+        if (c->zero_copy_input && cudaPointerGetAttributes(&at, in) == cudaSuccess && at.type == cudaMemoryTypeHost &&
+            at.devicePointer)
+            zc_in = static_cast<const char *>(at.devicePointer);
+        else
+            cudaGetLastError();
+    }
+    std::vector<uint32_t> skips(nch, 0);
+    // SWO_TRACE=1: per-chunk timeline (CUDA events on the three streams) printed to stderr
+    static const bool trace = getenv("SWO_TRACE") != nullptr;
+    struct Tr { cudaEvent_t h0, h1, k0, k1, o0, o1; };
+    std::vector<Tr> tr(trace ? nch : 0);
+    auto mark = [&](cudaEvent_t *e, cudaStream_t st) {
+        if (!trace) return;
+        cudaEventCreate(e);
+        cudaEventRecord(*e, st);
+    };
+    auto launch_chunk = [&](int k) -> int {
         const int s = k % N_SLOTS;
         const size_t off = cuts[k], len = cuts[k + 1] - cuts[k];
-        CK(c, d.t_in[s].reserve(len + 32));
+        if (zc_in) {
+            const uint32_t skip = (uint32_t)(reinterpret_cast<uintptr_t>(zc_in + off) & 15u);
+            skips[k] = skip;
+            return launch_lift_text(c, d, zc_in + off - skip, len + skip, d.t_out[s].as<char>(), d.t_out[s].cap,
+                                    d.t_unm[s].as<char>(), d.t_unm[s].cap, d.t_sizes[s].as<uint64_t>(), d.s_comp, skip);
+        }
+        return launch_lift_text(c, d, d.t_in[s].as<char>(), len, d.t_out[s].as<char>(), d.t_out[s].cap,
+                                d.t_unm[s].as<char>(), d.t_unm[s].cap, d.t_sizes[s].as<uint64_t>(), d.s_comp);
+    };
+    auto sizes_to_host = [&](int s) -> int {
+        copy_sizes_kernel<<<1, 32, 0, d.s_comp>>>(d.t_sizes[s].as<uint64_t>(), hs + 6 * s);
+        CK(c, cudaGetLastError());
+        CK(c, cudaEventRecord(d.ev_comp[s], d.s_comp));
+        return SWO_OK;
+    };
+    auto issue = [&](int k) -> int {  // (H2D +) kernel + sizes readback for chunk k
+        const int s = k % N_SLOTS;
+        const size_t off = cuts[k], len = cuts[k + 1] - cuts[k];
         CK(c, d.t_out[s].reserve(len + (len >> 1) + 65536));
         CK(c, d.t_unm[s].reserve(len + 64));
         CK(c, d.t_sizes[s].reserve(48));
-        CK(c, cudaStreamWaitEvent(d.s_h2d, d.ev_d2h[s], 0));  // slot's previous outputs are on the host
-        CK(c, cudaMemcpyAsync(d.t_in[s].p, in + off, len, cudaMemcpyHostToDevice, d.s_h2d));
-        CK(c, cudaEventRecord(d.ev_h2d[s], d.s_h2d));
-        CK(c, cudaStreamWaitEvent(d.s_comp, d.ev_h2d[s], 0));
-        int rc = launch_lift_text(c, d, d.t_in[s].as<char>(), len, d.t_out[s].as<char>(), d.t_out[s].cap,
-                                  d.t_unm[s].as<char>(), d.t_unm[s].cap, d.t_sizes[s].as<uint64_t>(), d.s_comp);
+        if (zc_in) {
+            CK(c, cudaStreamWaitEvent(d.s_comp, d.ev_d2h[s], 0));  // slot's previous outputs are on the host
+        } else {
+            CK(c, d.t_in[s].reserve(len + 32));
+            CK(c, cudaStreamWaitEvent(d.s_h2d, d.ev_d2h[s], 0));
+            if (trace) mark(&tr[k].h0, d.s_h2d);
+            CK(c, cudaMemcpyAsync(d.t_in[s].p, in + off, len, cudaMemcpyHostToDevice, d.s_h2d));
+            if (trace) mark(&tr[k].h1, d.s_h2d);
+            CK(c, cudaEventRecord(d.ev_h2d[s], d.s_h2d));
+            CK(c, cudaStreamWaitEvent(d.s_comp, d.ev_h2d[s], 0));
+        }
+        if (trace) mark(&tr[k].k0, d.s_comp);
+        int rc = launch_chunk(k);
         if (rc) return rc;
-        CK(c, cudaMemcpyAsync(hs + 6 * s, d.t_sizes[s].p, 48, cudaMemcpyDeviceToHost, d.s_comp));
-        CK(c, cudaEventRecord(d.ev_comp[s], d.s_comp));
-        return SWO_OK;
+        if (trace) mark(&tr[k].k1, d.s_comp);
+        return sizes_to_host(s);
     };
     int rc;
     int next_issue = 0;
@@ -348,17 +426,14 @@ int run_shard(swo_ctx *c, Device &d, const char *in, size_t a, size_t b, PinBuf 
             // fan-out larger than the guess: grow this slot's output and redo the chunk
             CK(c, cudaStreamSynchronize(d.s_comp));
             CK(c, d.t_out[s].reserve((size_t)sz[0] + 4096));
-            rc = launch_lift_text(c, d, d.t_in[s].as<char>(), len, d.t_out[s].as<char>(), d.t_out[s].cap,
-                                  d.t_unm[s].as<char>(), d.t_unm[s].cap, d.t_sizes[s].as<uint64_t>(), d.s_comp);
-            if (rc) return rc;
-            CK(c, cudaMemcpyAsync(hs + 6 * s, d.t_sizes[s].p, 48, cudaMemcpyDeviceToHost, d.s_comp));
-            CK(c, cudaEventRecord(d.ev_comp[s], d.s_comp));
+            if ((rc = launch_chunk(k))) return rc;
+            if ((rc = sizes_to_host(s))) return rc;
             CK(c, cudaEventSynchronize(d.ev_comp[s]));
             memcpy(sz, hs + 6 * s, 48);
         }
         if (sz[5] && !res.has_err) {
             res.has_err = true;
-            res.err_off = cuts[k] + (UINT64_MAX - sz[5]);
+            res.err_off = cuts[k] + (UINT64_MAX - sz[5]) - skips[k];
         }
         // grow the host arenas if needed (keeps what is already there)
         if (out_l + sz[0] > pl->cap) {
@@ -370,8 +445,10 @@ int run_shard(swo_ctx *c, Device &d, const char *in, size_t a, size_t b, PinBuf 
             CK(c, pu->reserve(out_u + sz[1], true, out_u));
         }
         CK(c, cudaStreamWaitEvent(d.s_d2h, d.ev_comp[s], 0));
+        if (trace) mark(&tr[k].o0, d.s_d2h);
         if (sz[0]) CK(c, cudaMemcpyAsync(pl->as<char>() + out_l, d.t_out[s].p, sz[0], cudaMemcpyDeviceToHost, d.s_d2h));
         if (sz[1]) CK(c, cudaMemcpyAsync(pu->as<char>() + out_u, d.t_unm[s].p, sz[1], cudaMemcpyDeviceToHost, d.s_d2h));
+        if (trace) mark(&tr[k].o1, d.s_d2h);
         CK(c, cudaEventRecord(d.ev_d2h[s], d.s_d2h));
         out_l += sz[0];
         out_u += sz[1];
@@ -380,6 +457,20 @@ int run_shard(swo_ctx *c, Device &d, const char *in, size_t a, size_t b, PinBuf 
         res.nunm += sz[4];
     }
     CK(c, cudaStreamSynchronize(d.s_d2h));
+    if (trace && nch && !zc_in) {
+        auto ms = [&](cudaEvent_t e) {
+            float f = 0;
+            cudaEventElapsedTime(&f, tr[0].h0, e);
+            return f;
+        };
+        fprintf(stderr, "chunk   h2d_start h2d_end  k_start  k_end    d2h_start d2h_end (ms)\n");
+        for (int k = 0; k < nch; k++) {
+            fprintf(stderr, "%5d %9.3f %8.3f %8.3f %8.3f %9.3f %8.3f\n", k, ms(tr[k].h0), ms(tr[k].h1), ms(tr[k].k0),
+                    ms(tr[k].k1), ms(tr[k].o0), ms(tr[k].o1));
+        }
+        for (int k = 0; k < nch; k++)
+            for (cudaEvent_t e : {tr[k].h0, tr[k].h1, tr[k].k0, tr[k].k1, tr[k].o0, tr[k].o1}) cudaEventDestroy(e);
+    }
     res.lifted = out_l - base_l;
     res.unm = out_u - base_u;
     return SWO_OK;
@@ -476,6 +567,10 @@ int swo_set_option(swo_ctx *c, const char *key, int64_t value) {
     if (!strcmp(key, "chunk_bytes")) {
         if (value < 64) return fail(c, SWO_E_ARG, "chunk_bytes must be >= 64");
         c->chunk_bytes = (size_t)value;
+        return SWO_OK;
+    }
+    if (!strcmp(key, "zero_copy_input")) {
+        c->zero_copy_input = value != 0;
         return SWO_OK;
     }
     return fail(c, SWO_E_ARG, "unknown option %s", key);
@@ -701,6 +796,7 @@ int swo_lift_bed_text(swo_ctx *c, const char *in, size_t in_len, swo_text_out *o
             th.emplace_back([&, k]() {
                 swo_ctx local;  // private error sink; run_shard only touches err/launches/chunk_bytes
                 local.chunk_bytes = c->chunk_bytes;
+                local.zero_copy_input = c->zero_copy_input;
                 Device &d = c->dev[k];
                 res[k].rc = run_shard(&local, d, in, cut[k], cut[k + 1], &d.a_lifted, 0, &d.a_unm, 0, res[k]);
                 emsg[k] = local.err;
