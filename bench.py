@@ -99,16 +99,13 @@ class ClockSampler:
 def run_cuda(args):
     import torch
     import torch.distributed as dist
-    from swiftover_b200 import ChainFile
+    from swiftover_b200 import ChainFile, shard
     from swiftover_b200 import synth as S
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, local, world = shard.env_rank_world()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    shard.init("nccl", device_id=dev)  # rendezvous only: the data path has no collective
     n = args.n
     cf = ChainFile(text=chain_bytes(), devices=[local])
 
@@ -120,8 +117,7 @@ def run_cuda(args):
     stream = torch.cuda.current_stream(dev)
 
     def barrier():
-        if world > 1:
-            dist.barrier()
+        shard.barrier()
         torch.cuda.synchronize(dev)
 
     # ---- kernel-only: text resident in HBM ---------------------------------------------------
@@ -170,10 +166,7 @@ def run_cuda(args):
     clocks = sampler.stop() if sampler else None
 
     # ---- max over ranks -------------------------------------------------------------------------
-    tt = torch.tensor([kern_ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    kern_ms_total, e2e_ms_total = tt.tolist()
+    kern_ms_total, e2e_ms_total = shard.max_over_ranks([kern_ms_total, e2e_s * 1e3], device=dev)
     ms_per_step = kern_ms_total / args.steps
     value = world * n / (ms_per_step * 1e-3)
     e2e_value = world * n / (e2e_ms_total * 1e-3 / e2e_steps)
@@ -208,12 +201,38 @@ def run_cuda(args):
                          "kernel_ms_median": med_ms},
             "clocks": clocks,
         }
+        if world == 1 and not args.no_binary:
+            result["binary_kernel"] = binary_kernel_line(cf, S, n, dev, peak)
         if not args.no_cpu_baseline and world == 1:
             result["cpu_baseline"] = cpu_baseline_from_text(text, n, args)
     cf.close()
     if world > 1:
         dist.destroy_process_group()
     return result
+
+
+def binary_kernel_line(cf, S, n, dev, peak):
+    """Secondary figure: the binary query kernel (swo_lift_intervals_dev) on the same records —
+    tcid/start/end int32 in, row_offset + 16-byte rows out (SURVEY.md §8d contract B)."""
+    import torch
+    iv = S.gen_intervals(cf, n, SEED_CFG2, len_lo=1, len_hi=10_000, device=dev, sort=True)
+    bufs = S.BinaryLiftBuffers(n, device=dev)
+    st = torch.cuda.current_stream(dev)
+    for _ in range(3):
+        S.lift_intervals_dev(cf, iv, bufs, st)
+    torch.cuda.synchronize(dev)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+    for a, b in evs:
+        a.record(st)
+        S.lift_intervals_dev(cf, iv, bufs, st)
+        b.record(st)
+    torch.cuda.synchronize(dev)
+    ms = statistics.median(a.elapsed_time(b) for a, b in evs)
+    rows, unm = bufs.totals.cpu().tolist()
+    alg = n * (12 + 4) + rows * 16
+    return {"kernel": "lift_intervals_kernel", "intervals_per_s": n / (ms * 1e-3), "ms": ms, "rows": rows,
+            "unmatched": unm, "algorithmic_bytes": alg, "achieved_GBs": alg / (ms * 1e-3) / 1e9,
+            "frac_of_hbm_peak": alg / (ms * 1e-3) / 1e9 / peak}
 
 
 def cpu_baseline_from_text(text, n, args):
@@ -329,6 +348,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=16_000_000, help="lines in the CPU baseline sample")
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-binary", action="store_true", help="skip the secondary binary-kernel measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else max(args.warmup, 1)
     res = run_reference(args) if args.impl == "reference" else run_cuda(args)

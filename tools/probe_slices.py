@@ -16,7 +16,8 @@ text = S.bed_text(cf, iv, ncols=3)
 nb = text.numel()
 st = torch.cuda.current_stream(dev)
 res = []
-for k in range(NS):
+ONLY = os.environ.get('ONLY')
+for k in ([int(ONLY)] if ONLY else range(NS)):
     a = nb * k // NS; b = nb * (k + 1) // NS
     a = (a + 15) & ~15
     sl = text[a:b]
