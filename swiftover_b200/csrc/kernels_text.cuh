@@ -14,23 +14,27 @@
 // 128-bit loads; a tile owns the lines that START inside it.
 //   1. line starts: word-wide (SWAR) newline masks of the staged window, block
 //      scan, table of line-start offsets in shared memory;
-//   2. lines are handed to threads round-robin, 256 at a time ("batch").  A
-//      thread parses its line ONCE, looks the contig name up, searches the block
-//      table (upper levels = Eytzinger-ordered group maxima staged in shared
-//      memory, then a bisection inside one group), computes the exact byte
-//      length of its output; one packed block scan per batch places lifted and
-//      unmatched text; the thread then formats straight from its registers
-//      into a shared-memory stage holding the tile's whole output;
-//   3. the tile totals are chained to the previous tiles with a decoupled
-//      look-back (two streams packed in one descriptor pair) and the stages are
-//      copied out with aligned 128-bit stores.
+//   2. count phase: lines are dealt to threads round-robin (up to TX_NB = 3 per
+//      thread, results cached in registers).  A thread parses its line ONCE with
+//      word-wide loads (SWAR separator / digit masks and decimal conversion),
+//      looks the contig name up, searches the block table (upper levels =
+//      Eytzinger-ordered group maxima in shared memory, then a quaternary search
+//      inside one group), and computes the exact byte length of its output;
+//   3. one packed multi-scan places lifted and unmatched text of all lines of the
+//      tile; the tile totals are published to the decoupled look-back chains;
+//   4. emit phase: rows are formatted from the cached state into shared-memory
+//      stages holding the tile's whole output;
+//   5. the resolve of the chained offsets and the copy-out (aligned 128-bit
+//      stores) of a tile are deferred until the NEXT tile has been counted, so
+//      that the look-back never waits for a predecessor's formatting.
 // Fast path = canonical lines (single tabs, plain digits, inside the window).
 // Anything else (other white space, signs, >9 digits, lines longer than the
 // look-ahead, malformed lines) takes the generic per-line path below, which
-// follows the reference's tokenizer exactly.  Records with >= 2 hits are expanded
-// cooperatively (warp / block), each row computing its own sorted position, byte
-// offset and cumulative strand byte.  If a tile's output does not fit its stage
-// the tile is re-run writing directly to global memory at the chained offsets.
+// follows the reference's tokenizer exactly.  Records with >= 2 hits: rows already
+// in qStart order (or exactly reversed) are written sequentially by the owning
+// thread; the rest are expanded cooperatively (warp / block), each row computing
+// its own sorted position, byte offset and cumulative strand byte.  A stream that
+// does not fit its stage is written directly to global memory at the chained offset.
 #pragma once
 #include "device_util.cuh"
 #include "lift_core.cuh"
