@@ -40,7 +40,7 @@ struct ChainTable {
     // consecutive blocks, stored in Eytzinger (BFS) order as {key, block index}
     // pairs at ey[eyoff[c] ...].  S is the smallest power of two for which all
     // samples fit in EY_CAP entries.
-    static constexpr int EY_CAP = 4096;
+    static constexpr int EY_CAP = 2048;
     int eyShift = 0;
     std::vector<int32_t> eyKey, eyIdx;  // [nsamples] each
     std::vector<int32_t> eyoff;         // [ntc+1]

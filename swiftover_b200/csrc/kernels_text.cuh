@@ -47,15 +47,23 @@ namespace swo {
 #ifndef TX_MIN_CTAS
 #define TX_MIN_CTAS 2  // resident CTAs per SM the register budget is sized for
 #endif
-constexpr int TX_TPB = 256;
+#ifndef TX_THREADS
+#define TX_THREADS 256
+#endif
+#ifndef TX_NB
+#define TX_NB 3  // batches of TX_THREADS lines whose parse results stay in registers
+#endif
+constexpr int TX_TPB = TX_THREADS;
 constexpr int TX_NW = TX_TPB / 32;
-constexpr int TX_SEG = 64;                   // bytes per newline-mask word
-constexpr int TX_TILE = TX_TPB * TX_SEG;     // 16384
+constexpr int TX_TILE = 16384;               // bytes of text per tile
+constexpr int TX_MSEG = 64;                  // bytes per newline-mask word
+constexpr int TX_SEG = TX_TILE / TX_TPB;     // bytes whose line starts a thread enumerates (64 or 32)
+static_assert(TX_SEG == 64 || TX_SEG == 32, "TX_THREADS must be 256 or 512");
 constexpr int TX_PRE = 64;                   // bytes staged before the tile
 constexpr int TX_LOOK = 1024;                // bytes staged after the tile
 constexpr int TX_WIN = TX_PRE + TX_TILE + TX_LOOK;
 constexpr int TX_PAD = 32;                   // always '\n' after the window
-constexpr int TX_NSEG = TX_WIN / TX_SEG;     // 273
+constexpr int TX_NSEG = TX_WIN / TX_MSEG;    // 273
 constexpr int TX_OUT_STAGE = 20480;          // lifted bytes staged per tile
 constexpr int TX_UNM_STAGE = TX_TILE + TX_LOOK;  // unmatched bytes staged per tile: a tile's unmatched text never exceeds its input
 constexpr int TX_LCAP = 2048;                // line-start table entries
@@ -63,7 +71,18 @@ constexpr int TX_BR_CAP = 64;                // blocks of the tile's bracket sta
 constexpr int TX_QN_MAX = 256;               // destination contig names kept in shared memory ...
 constexpr int TX_QCHARS = 3072;              // ... if their characters fit here
 constexpr int TX_WL_CAP = 256;
-constexpr int TX_HEAVY_MIN = 256;
+#ifndef TX_HEAVY_MIN_V
+#define TX_HEAVY_MIN_V 64
+#endif
+constexpr int TX_HEAVY_MIN = TX_HEAVY_MIN_V;            // candidates above which the whole block expands a line
+constexpr int TX_XSCR = 512;                 // shared-memory scratch entries (= TX_NW warp regions of TX_HEAVY_MIN)
+constexpr int TX_GSCR = 8192;                // per-CTA global scratch entries for heavier lines
+#ifndef TX_CW_MIN_V
+#define TX_CW_MIN_V 48
+#endif
+constexpr int TX_CW_MIN = TX_CW_MIN_V;                // candidates above which a line's output length is summed by the block
+constexpr int TX_CW_CAP = 64;                // such lines per tile
+static_assert(TX_NW * TX_HEAVY_MIN <= TX_XSCR, "one scratch region per warp");
 constexpr int TX_EY_CAP = ChainTable::EY_CAP;
 
 // open-addressing name table entry (source contig name -> tcid): two 128-bit loads, the
@@ -92,6 +111,7 @@ struct TextArgs {
     uint64_t lifted_cap;
     char *unm;
     uint64_t unm_cap;
+    unsigned long long *gscr;   // per-CTA scratch for very heavy lines: grid * TX_GSCR * 12 bytes (or null)
     uint64_t *desc_l, *desc_u;  // [ntiles] each, zeroed
     unsigned *ticket;           // zeroed
     uint64_t *sizes;            // [6], zeroed: lifted, unmatched, records, rows, unmatched recs, error
@@ -461,6 +481,92 @@ __device__ __noinline__ void expand_line(const TextArgs &A, const int2 *ey, cons
     }
 }
 
+// Cooperative form used for the queued multi-hit lines (one warp, or the whole block for
+// heavy fan-out).  Linear or n log^2 n, never quadratic:
+//   1. one 64-bit sort key (qStart, candidate index) per candidate goes to `scr`, its row
+//      length and invert to `aux` (shared memory, or a per-CTA global scratch for very heavy lines);
+//   2. if the keys are not already ascending (mixed chains, '-' chains) they are sorted with a
+//      bitonic network;
+//   3. rows are taken in sorted order; a running scan of the lengths gives every row its byte
+//      offset, a running count of inverted rows its cumulative strand byte (bed.d:173).
+// BLOCK: all threads of the CTA call it (scan_scr: TX_NW+1 words for the block scan).
+template <bool BLOCK>
+__device__ __noinline__ void expand_line_coop(const TextArgs &A, const int2 *ey, const Reader &R, uint64_t p0, int lo,
+                                              int ncand, char *dst, unsigned long long *scr, uint32_t *aux,
+                                              unsigned long long *scan_scr, int first, int stride) {
+    const TableView &T = A.T;
+    LineInfo L;
+    scan_line(A, R, p0, L);
+    Thick th{0, 0, 0};
+    if (L.numf >= 8) th = lift_thick(T, ey, L.tcid, L.ts, L.te);
+    int P = 32;
+    while (P < ncand) P <<= 1;
+    for (int c = first; c < P; c += stride) {
+        unsigned long long key = ~0ull;  // padding and non-hits sort last
+        if (c < ncand) {
+            const Block b = load_block(T, lo + c);
+            const RowCore r = make_row(b, L.start, L.end);
+            if (T.disjoint || block_hits(b, L.start)) {
+                key = ((unsigned long long)((uint32_t)r.key ^ 0x80000000u) << 32) | (uint32_t)c;
+                aux[c] = (row_len(A, L, th, r) << 1) | (r.inv < 0 ? 1u : 0u);
+            }
+        }
+        scr[c] = key;
+    }
+    if (BLOCK) __syncthreads();
+    else __syncwarp();
+    bool mine = true;
+    for (int c = first; c < P; c += stride)
+        if (c > 0 && scr[c - 1] > scr[c]) mine = false;
+    const bool sorted = BLOCK ? (__syncthreads_and(mine) != 0) : (__all_sync(FULL, mine) != 0);
+    if (!sorted) {
+        for (int k = 2; k <= P; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = first; i < P; i += stride) {
+                    const int x = i ^ j;
+                    if (x > i) {
+                        const unsigned long long va = scr[i], vb = scr[x];
+                        if ((va > vb) == ((i & k) == 0)) {
+                            scr[i] = vb;
+                            scr[x] = va;
+                        }
+                    }
+                }
+                if (BLOCK) __syncthreads();
+                else __syncwarp();
+            }
+        }
+    }
+    // rows in output order
+    unsigned long long carry = 0;  // (bytes << 32) | inverted rows, of all earlier positions
+    const int inv_first = (aux[(uint32_t)scr[0]] & 1u) ? -1 : 1;  // position 0 is a hit: the line has >= 2 hits
+    for (int base = 0; base < P; base += stride) {
+        const int j = base + first;
+        const unsigned long long e = j < P ? scr[j] : ~0ull;
+        const bool hit = e != ~0ull;
+        const uint32_t c = (uint32_t)e;
+        const uint32_t av = hit ? aux[c] : 0u;
+        const unsigned long long v = ((unsigned long long)(av >> 1) << 32) | (av & 1u);
+        unsigned long long ex, tot;
+        if (BLOCK) {
+            ex = block_exclusive_scan<unsigned long long, TX_NW>(v, scan_scr, &tot);
+        } else {
+            const unsigned long long inc = warp_inclusive_scan(v);
+            ex = inc - v;
+            tot = __shfl_sync(FULL, inc, 31);
+        }
+        if (hit) {
+            const unsigned long long at = carry + ex;
+            const int negs_le = (int)(uint32_t)at + (int)(av & 1u);
+            const RowCore rj = make_row(load_block(T, lo + (int)c), L.start, L.end);
+            const unsigned char sb = L.numf >= 6 ? strand_at_rank(L.strand, inv_first, j, negs_le) : 0;
+            emit_row(dst + (uint32_t)(at >> 32), A, R, L, th, rj, sb);
+        }
+        carry += tot;
+    }
+    if (BLOCK) __syncthreads();  // scratch is reused by the next heavy line
+}
+
 // =====================================================================================
 // Fast path: canonical line, parsed once, kept in registers between count and emit
 // =====================================================================================
@@ -719,7 +825,6 @@ __device__ __forceinline__ uint32_t nl_mask4(uint32_t x) {
     return ((t >> 7) * 0x00204081u) >> 21 & 0xFu;
 }
 
-constexpr int TX_NB = 3;  // batches of 256 lines whose parse results stay in registers
 
 struct TextSmem {
     uint32_t in_words[(TX_WIN + TX_PAD) / 4];
@@ -727,7 +832,10 @@ struct TextSmem {
     uint32_t unm_words[TX_UNM_STAGE / 4 + 8];
     unsigned long long nlm[TX_NSEG + 1];
     int2 ey[TX_EY_CAP];
-    uint16_t lstart[TX_LCAP];
+    union {  // the line table is dead once the emit phase is over, when the expansions run
+        uint16_t lstart[TX_LCAP];
+        uint32_t xaux[TX_XSCR];
+    };
     unsigned long long scan64[TX_NB * TX_NW];
     uint32_t scan32[TX_NW + 1];
     uint64_t base_l, base_u;
@@ -739,11 +847,18 @@ struct TextSmem {
     int br_cnt;  // -1: none
     int br_tcid, br_lo_q, br_hi_q, br_blo;
     uint32_t br_name_off, br_name_len;
-    int4 br_blk[TX_BR_CAP];
+    int4 br_blk[TX_USE_BRACKET ? TX_BR_CAP : 1];
     int4 cmeta[TX_CM_CAP];  // per-contig {first block, end block, Eytzinger offset, samples}
     // destination contig names
     uint32_t qoff[TX_QN_MAX + 1];
     char qchars[TX_QCHARS];
+    unsigned long long xscr[TX_XSCR];  // expand_line_coop scratch: TX_NW warp regions / one block region
+    // lines whose fan-out is too large to be summed by one thread (count phase)
+    int cw_n;
+    uint32_t cw_p[TX_CW_CAP];
+    int cw_lo[TX_CW_CAP], cw_cnt[TX_CW_CAP], cw_tcid[TX_CW_CAP];
+    uint32_t cw_len[TX_CW_CAP];
+    uint32_t red32[TX_NW];
     uint32_t wl_p0[TX_WL_CAP];   // line start, window offset
     int wl_lo[TX_WL_CAP];
     int wl_cnt[TX_WL_CAP];
@@ -769,7 +884,7 @@ __device__ __forceinline__ int st_hits(const LineState &st) { return (int)((st.m
 struct TileCtx {
     const unsigned char *win;
     const int2 *ey;
-    const TextSmem *S;
+    TextSmem *S;
     Reader R;
     uint64_t g0;     // absolute offset of window offset s0
     uint32_t s0;
@@ -778,8 +893,10 @@ struct TileCtx {
 
 // Count side of one line: parse, look up, search, exact output lengths.  Returns the
 // number of overlapping blocks, -1 for a line that is not a record, -2 for a malformed one.
+// allow_cw: a heavy-fan-out line may be handed to the block (count work list); such a line is marked
+// with both order bits (15 and 16) set and keeps its work-list slot in st.e2a5.
 __device__ __forceinline__ int line_count(const TextArgs &A, const TileCtx &X, uint32_t p, LineState &st,
-                                          uint32_t &len_l, uint32_t &len_u) {
+                                          uint32_t &len_l, uint32_t &len_u, const bool allow_cw) {
     const TableView &T = A.T;
     len_l = len_u = 0;
     st.pq = p;
@@ -791,7 +908,7 @@ __device__ __forceinline__ int line_count(const TextArgs &A, const TileCtx &X, u
     const int kind = fast_parse(A, X.win, p, X.limit, F, nw);
     if (kind == FL_NONE) return -1;
     if (kind == FL_FAST) {
-        const TextSmem &S = *X.S;
+        TextSmem &S = *X.S;
         // sorted tiles: the query usually falls inside the tile's bracket, whose blocks are
         // in shared memory -> contig lookup and block search without a global load
         bool inb = S.br_cnt >= 0 && F.len0 == S.br_name_len && F.start >= S.br_lo_q && F.end <= S.br_hi_q &&
@@ -829,8 +946,23 @@ __device__ __forceinline__ int line_count(const TextArgs &A, const TileCtx &X, u
         st.a6b7 = F.a6 | (F.b7 << 16);
         uint32_t meta = FL_FAST | ((uint32_t)(nh < 2 ? nh : 2) << 2) | ((uint32_t)(F.numf - 3) << 4) |
                         ((uint32_t)F.strand << 7);
+        int slot = TX_CW_CAP;
+        if (allow_cw && nh > 0 && cd.hi - cd.lo > TX_CW_MIN) slot = atomicAdd(&S.cw_n, 1);
         if (nh == 0) {
             len_u = F.q - p + 1;
+        } else if (slot < TX_CW_CAP) {
+            // heavy fan-out: the block sums this line's output length after the per-thread phase
+            S.cw_p[slot] = p;
+            S.cw_lo[slot] = cd.lo;
+            S.cw_cnt[slot] = cd.hi - cd.lo;
+            S.cw_tcid[slot] = F.tcid;
+            st.e2a5 = (uint32_t)slot;
+            meta |= 3u << 15;
+            st.a = F.start;
+            st.b = F.end;
+            st.x = cd.lo;
+            st.y = cd.hi - cd.lo;
+            meta |= (uint32_t)(F.tcid < 0x7FFF ? F.tcid : 0x7FFF) << 17;
         } else {
             const uint32_t fixed = fast_fixed_len(F);
             Thick th{0, 0, 0};
@@ -1022,6 +1154,38 @@ __device__ __forceinline__ void line_emit(const TextArgs &A, const TileCtx &X, T
     }
 }
 
+// Block-cooperative sum of the output lengths of the tile's heavy-fan-out lines (count work
+// list): results in S.cw_len.  Every thread of the CTA calls it.
+__device__ __noinline__ void coop_count_lines(const TextArgs &A, const TileCtx &X, TextSmem &S) {
+    const TableView &T = A.T;
+    const int tid = threadIdx.x;
+    const int ncw = min(S.cw_n, TX_CW_CAP);
+    for (int e = 0; e < ncw; e++) {
+        FastLine F;
+        uint32_t nw[4];
+        fast_parse(A, X.win, S.cw_p[e], X.limit, F, nw);
+        const uint32_t fixed = fast_fixed_len(F);
+        Thick th{0, 0, 0};
+        if (F.numf >= 8) th = lift_thick(T, X.ey, S.cw_tcid[e], F.v6, F.v7);
+        uint32_t part = 0;
+        const int lo = S.cw_lo[e], cnt = S.cw_cnt[e];
+        for (int c = tid; c < cnt; c += TX_TPB) {
+            const Block b = load_block(T, lo + c);
+            if (!T.disjoint && !block_hits(b, F.start)) continue;
+            part += fast_row_len(A, F, fixed, th, make_row(b, F.start, F.end));
+        }
+        part = warp_sum(part);
+        if (lane_id() == 0) S.red32[warp_id()] = part;
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t sum = 0;
+            for (int w = 0; w < TX_NW; w++) sum += S.red32[w];
+            S.cw_len[e] = sum;
+        }
+        __syncthreads();
+    }
+}
+
 // NB independent exclusive block scans with one pair of barriers.
 template <int NB>
 __device__ __forceinline__ void block_scan_multi(const unsigned long long (&v)[NB], unsigned long long (&ex)[NB],
@@ -1206,6 +1370,7 @@ __global__ void __launch_bounds__(TX_TPB, TX_MIN_CTAS) lift_bed_text_kernel(cons
         if (tid == 0) {
             S.tile = (int)atomicAdd(A.ticket, 1u);
             S.wl_n = 0;
+            S.cw_n = 0;
         }
         __syncthreads();
         const int tile = S.tile;
@@ -1242,7 +1407,7 @@ __global__ void __launch_bounds__(TX_TPB, TX_MIN_CTAS) lift_bed_text_kernel(cons
 
         // ---- newline masks of the window, 64 bytes per word -----------------------------
         for (int sg = tid; sg < TX_NSEG; sg += TX_TPB) {
-            const uint4 *w = reinterpret_cast<const uint4 *>(win + sg * TX_SEG);
+            const uint4 *w = reinterpret_cast<const uint4 *>(win + sg * TX_MSEG);
             unsigned long long m = 0;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
@@ -1254,14 +1419,19 @@ __global__ void __launch_bounds__(TX_TPB, TX_MIN_CTAS) lift_bed_text_kernel(cons
         }
         __syncthreads();
         // line starts inside this thread's 64 bytes of the tile: the byte before is '\n'
-        unsigned long long starts = (S.nlm[tid + 1] << 1) | (S.nlm[tid] >> 63);
+        unsigned long long starts;
+        {
+            const int w = (tid * TX_SEG) / TX_MSEG;  // mask word of this thread's bytes (window word w + 1)
+            starts = (S.nlm[w + 1] << 1) | (S.nlm[w] >> 63);
+            if (TX_SEG < TX_MSEG) starts = (starts >> ((tid * TX_SEG) % TX_MSEG)) & ((1ull << (TX_SEG % 64)) - 1ull);
+        }
         if (tile == 0 && tid == 0)  // the text starts (with a line) at offset `skip`
             starts = (starts & ~((1ull << A.skip) - 1ull)) | (1ull << A.skip);
         unsigned long long valid = starts;
         {
             const long long rem = (long long)A.in_len - (long long)(t0 + (uint64_t)tid * TX_SEG);
             if (rem <= 0) valid = 0;
-            else if (rem < 64) valid &= (1ull << rem) - 1ull;
+            else if (rem < TX_SEG) valid &= (1ull << rem) - 1ull;
         }
         // line index = prefix over ALL starts (the valid ones are a prefix of them)
         uint32_t packed_tot;
@@ -1331,7 +1501,7 @@ __global__ void __launch_bounds__(TX_TPB, TX_MIN_CTAS) lift_bed_text_kernel(cons
             v[b] = 0;
             if (li < nlines) {
                 uint32_t ll, lu;
-                const int nh = line_count(A, X, S.lstart[li], st[b], ll, lu);
+                const int nh = line_count(A, X, S.lstart[li], st[b], ll, lu, true);
                 v[b] = ((unsigned long long)ll << 32) | lu;
                 if (nh == -2)  // max(~p0) == first bad line
                     atomicMax((unsigned long long *)(A.sizes + 5),
@@ -1344,6 +1514,17 @@ __global__ void __launch_bounds__(TX_TPB, TX_MIN_CTAS) lift_bed_text_kernel(cons
             }
         }
         block_scan_multi<TX_NB>(v, ex, bt, S.scan64);
+        // lines with heavy fan-out: the block sums their output lengths (a single thread would
+        // hold the whole tile, and every successor's look-back, for hundreds of microseconds),
+        // then the tile is scanned again.  S.cw_n is stable here: the scan above had barriers.
+        if (S.cw_n > 0) {
+            coop_count_lines(A, X, S);
+#pragma unroll
+            for (int b = 0; b < TX_NB; b++)
+                if ((st[b].meta & ((3u << 15) | 15u)) == ((3u << 15) | (2u << 2) | FL_FAST))
+                    v[b] += (unsigned long long)S.cw_len[st[b].e2a5] << 32;
+            block_scan_multi<TX_NB>(v, ex, bt, S.scan64);
+        }
         uint32_t run_l = 0, run_u = 0;
 #pragma unroll
         for (int b = 0; b < TX_NB; b++) {
@@ -1363,7 +1544,7 @@ __global__ void __launch_bounds__(TX_TPB, TX_MIN_CTAS) lift_bed_text_kernel(cons
                 uint32_t ll = 0, lu = 0;
                 if (li < nlines) {
                     LineState t;
-                    const int nh = line_count(A, X, S.lstart[li - wbase], t, ll, lu);
+                    const int nh = line_count(A, X, S.lstart[li - wbase], t, ll, lu, false);
                     if (nh == -2)
                         atomicMax((unsigned long long *)(A.sizes + 5),
                                   ~(unsigned long long)(X.g0 + ((t.pq & 0xFFFFu) - X.s0)));
@@ -1431,7 +1612,7 @@ __global__ void __launch_bounds__(TX_TPB, TX_MIN_CTAS) lift_bed_text_kernel(cons
                 uint32_t ll = 0, lu = 0;
                 LineState t;
                 t.meta = FL_NONE;
-                if (li < nlines) line_count(A, X, S.lstart[li - wbase], t, ll, lu);
+                if (li < nlines) line_count(A, X, S.lstart[li - wbase], t, ll, lu, false);
                 unsigned long long t1;
                 const unsigned long long e1 =
                     block_exclusive_scan<unsigned long long, TX_NW>(((unsigned long long)ll << 32) | lu, S.scan64, &t1);
@@ -1445,13 +1626,26 @@ __global__ void __launch_bounds__(TX_TPB, TX_MIN_CTAS) lift_bed_text_kernel(cons
         if (base_l) {  // cooperative expansion of the queued multi-hit lines
             const int nwl = min(S.wl_n, TX_WL_CAP);
             for (int e = warp_id(); e < nwl; e += TX_NW)
-                if (S.wl_cnt[e] < TX_HEAVY_MIN)
-                    expand_line(A, X.ey, X.R, X.g0 + (S.wl_p0[e] - X.s0), S.wl_lo[e], S.wl_cnt[e], base_l + S.wl_off[e],
-                                lane_id(), 32);
-            for (int e = 0; e < nwl; e++)
-                if (S.wl_cnt[e] >= TX_HEAVY_MIN)
-                    expand_line(A, X.ey, X.R, X.g0 + (S.wl_p0[e] - X.s0), S.wl_lo[e], S.wl_cnt[e], base_l + S.wl_off[e], tid,
-                                TX_TPB);
+                if (S.wl_cnt[e] <= TX_HEAVY_MIN)
+                    expand_line_coop<false>(A, X.ey, X.R, X.g0 + (S.wl_p0[e] - X.s0), S.wl_lo[e], S.wl_cnt[e],
+                                            base_l + S.wl_off[e], S.xscr + warp_id() * TX_HEAVY_MIN,
+                                            S.xaux + warp_id() * TX_HEAVY_MIN, nullptr, lane_id(), 32);
+            __syncthreads();
+            for (int e = 0; e < nwl; e++) {
+                const int cnt = S.wl_cnt[e];
+                if (cnt <= TX_HEAVY_MIN) continue;
+                const uint64_t p0 = X.g0 + (S.wl_p0[e] - X.s0);
+                if (cnt <= TX_XSCR) {
+                    expand_line_coop<true>(A, X.ey, X.R, p0, S.wl_lo[e], cnt, base_l + S.wl_off[e], S.xscr, S.xaux,
+                                           S.scan64, tid, TX_TPB);
+                } else if (cnt <= TX_GSCR && A.gscr) {
+                    unsigned long long *g = A.gscr + (size_t)blockIdx.x * (TX_GSCR + TX_GSCR / 2);
+                    expand_line_coop<true>(A, X.ey, X.R, p0, S.wl_lo[e], cnt, base_l + S.wl_off[e], g,
+                                           reinterpret_cast<uint32_t *>(g + TX_GSCR), S.scan64, tid, TX_TPB);
+                } else {
+                    expand_line(A, X.ey, X.R, p0, S.wl_lo[e], cnt, base_l + S.wl_off[e], tid, TX_TPB);
+                }
+            }
         }
         // resolve + copy-out of this tile are deferred until the next tile has been counted
         pend = true;

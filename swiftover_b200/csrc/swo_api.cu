@@ -91,7 +91,7 @@ struct Device {
     DevBuf g_packed, g_off, g_len;
     int g_n = 0;
     // scratch for the look-back chains
-    DevBuf scratch;
+    DevBuf scratch, gscr;
     // binary path buffers
     DevBuf b_in, b_off, b_rows, b_thick, b_tot;
     // text path: per-slot chunk buffers
@@ -305,6 +305,8 @@ int launch_lift_text(swo_ctx *c, Device &d, const char *d_in, size_t in_len, cha
         d.text_grid = std::max(1, per) * d.sms;
     }
     const int grid = std::min(ntiles, d.text_grid);
+    CK(c, d.gscr.reserve((size_t)d.text_grid * (TX_GSCR + TX_GSCR / 2) * sizeof(unsigned long long)));
+    A.gscr = d.gscr.as<unsigned long long>();
     lift_bed_text_kernel<<<grid, TX_TPB, smem, st>>>(A);
     c->launches++;
     CK(c, cudaGetLastError());
@@ -528,7 +530,7 @@ void swo_destroy(swo_ctx *c) {
         cudaSetDevice(d.ordinal);
         cudaDeviceSynchronize();
         for (DevBuf *b : {&d.blk, &d.tkey, &d.pkey, &d.toff, &d.cmeta, &d.ey, &d.thash, &d.tchars, &d.tnoff, &d.qoff, &d.qchars, &d.g_packed,
-                          &d.g_off, &d.g_len, &d.scratch, &d.b_in, &d.b_off, &d.b_rows, &d.b_thick, &d.b_tot})
+                          &d.g_off, &d.g_len, &d.scratch, &d.gscr, &d.b_in, &d.b_off, &d.b_rows, &d.b_thick, &d.b_tot})
             b->release();
         for (int s = 0; s < N_SLOTS; s++) {
             d.t_in[s].release();
