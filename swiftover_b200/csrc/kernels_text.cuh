@@ -65,6 +65,7 @@ constexpr int TX_WIN = TX_PRE + TX_TILE + TX_LOOK;
 constexpr int TX_PAD = 32;                   // always '\n' after the window
 constexpr int TX_NSEG = TX_WIN / TX_MSEG;    // 273
 constexpr int TX_OUT_STAGE = 20480;          // lifted bytes staged per tile
+constexpr int TX_ROUND_SLACK = 4096;         // multi-round emit: a line's rows may run this far past its round's window
 constexpr int TX_UNM_STAGE = TX_TILE + TX_LOOK;  // unmatched bytes staged per tile: a tile's unmatched text never exceeds its input
 constexpr int TX_LCAP = 2048;                // line-start table entries
 constexpr int TX_BR_CAP = 64;                // blocks of the tile's bracket staged in shared memory
@@ -793,16 +794,17 @@ __device__ __forceinline__ char *fast_emit_row(char *d, const TextArgs &A, const
     return d + 1;
 }
 
-// copy n bytes from shared memory (4-byte aligned base) to global dst with
-// 16-byte aligned vector stores in the middle
-__device__ __forceinline__ void copy_out(char *dst, const uint32_t *s_words, uint32_t n) {
-    const unsigned char *s = reinterpret_cast<const unsigned char *>(s_words);
+// copy n bytes, starting at byte offset so of the shared-memory word array s_words, to global
+// dst with 16-byte aligned vector stores in the middle
+__device__ __forceinline__ void copy_out(char *dst, const uint32_t *s_words, uint32_t n, uint32_t so = 0) {
+    const unsigned char *s = reinterpret_cast<const unsigned char *>(s_words) + so;
     uint32_t head = (uint32_t)((16u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u);
     if (head > n) head = n;
     for (uint32_t i = threadIdx.x; i < head; i += blockDim.x) dst[i] = (char)s[i];
     const uint32_t nvec = (n - head) >> 4;
-    const uint32_t sh = (head & 3u) * 8u;
-    const uint32_t w0 = head >> 2;
+    const uint32_t q = so + head;  // byte offset of the first vector's source
+    const uint32_t sh = (q & 3u) * 8u;
+    const uint32_t w0 = q >> 2;
     for (uint32_t v = threadIdx.x; v < nvec; v += blockDim.x) {
         const uint32_t w = w0 + v * 4u;
         const uint32_t a0 = s_words[w], a1 = s_words[w + 1], a2 = s_words[w + 2], a3 = s_words[w + 3], a4 = s_words[w + 4];
@@ -843,6 +845,7 @@ struct TextSmem {
     int lb_found[TX_NW][2];
     int tile;
     int wl_n;
+    uint32_t rlo, rhi;  // byte range staged in the current round (multi-round emit of a large tile)
     // bracket of a sorted tile: the blocks overlapping [first line start, last line end)
     int br_cnt;  // -1: none
     int br_tcid, br_lo_q, br_hi_q, br_blo;
@@ -1580,23 +1583,49 @@ __global__ void __launch_bounds__(TX_TPB, TX_MIN_CTAS) lift_bed_text_kernel(cons
         uint64_t gb_l = 0, gb_u = 0;
         bool have_base = false;
         flush();  // previous tile: resolve + copy out, frees the stages
-        if (direct_l || direct_u) {
+        auto resolve_now = [&]() {  // block-uniform
             lookback_resolve2_block(S, A.desc_l, A.desc_u, tile, (uint64_t)tot_l, (uint64_t)tot_u);
             gb_l = S.base_l;
             gb_u = S.base_u;
             have_base = true;
-        }
-        char *const base_l = direct_l ? (gb_l + tot_l <= A.lifted_cap ? A.lifted + gb_l : nullptr) : stage_l;
+        };
+        // an oversized unmatched stream (lines longer than the look-ahead only) needs its offset now; an
+        // oversized lifted stream resolves after its first round has been formatted (see below)
+        if (direct_u) resolve_now();
         char *const base_u = direct_u ? (gb_u + tot_u <= A.unm_cap ? A.unm + gb_u : nullptr) : stage_u;
 
-        // ---- phase E: format from the cached state; no barrier inside -------------------
-#pragma unroll
-        for (int b = 0; b < TX_NB; b++) {
-            const uint32_t o_l = (uint32_t)(ex[b] >> 32), o_u = (uint32_t)ex[b];
-            line_emit(A, X, S, st[b], base_l ? base_l + o_l : nullptr, base_u ? base_u + o_u : nullptr, o_l);
-        }
-        if (nlines > TX_NB * TX_TPB) {
+        auto run_expansions = [&](char *base) {  // cooperative expansion of the queued multi-hit lines (block-uniform)
+            __syncthreads();
+            const int nwl = min(S.wl_n, TX_WL_CAP);
+            if (nwl == 0) return;
+            for (int e = warp_id(); e < nwl; e += TX_NW)
+                if (S.wl_cnt[e] <= TX_HEAVY_MIN)
+                    expand_line_coop<false>(A, X.ey, X.R, X.g0 + (S.wl_p0[e] - X.s0), S.wl_lo[e], S.wl_cnt[e],
+                                            base + S.wl_off[e], S.xscr + warp_id() * TX_HEAVY_MIN,
+                                            S.xaux + warp_id() * TX_HEAVY_MIN, nullptr, lane_id(), 32);
+            __syncthreads();
+            for (int e = 0; e < nwl; e++) {
+                const int cnt = S.wl_cnt[e];
+                if (cnt <= TX_HEAVY_MIN) continue;
+                const uint64_t p0 = X.g0 + (S.wl_p0[e] - X.s0);
+                if (cnt <= TX_XSCR) {
+                    expand_line_coop<true>(A, X.ey, X.R, p0, S.wl_lo[e], cnt, base + S.wl_off[e], S.xscr, S.xaux, S.scan64,
+                                           tid, TX_TPB);
+                } else if (cnt <= TX_GSCR && A.gscr) {
+                    unsigned long long *g = A.gscr + (size_t)blockIdx.x * (TX_GSCR + TX_GSCR / 2);
+                    expand_line_coop<true>(A, X.ey, X.R, p0, S.wl_lo[e], cnt, base + S.wl_off[e], g,
+                                           reinterpret_cast<uint32_t *>(g + TX_GSCR), S.scan64, tid, TX_TPB);
+                } else {
+                    expand_line(A, X.ey, X.R, p0, S.wl_lo[e], cnt, base + S.wl_off[e], tid, TX_TPB);
+                }
+            }
+            __syncthreads();
+        };
+        // lines beyond the cached batches (very dense tiles): re-counted and formatted batch by batch
+        auto emit_uncached = [&](char *base_l) {
+            if (nlines <= TX_NB * TX_TPB) return;
             int wbase = 0;
+            build_table(0);  // the expansions of a multi-round emit reuse the table's memory
             uint32_t r_l = 0, r_u = 0;
 #pragma unroll
             for (int b = 0; b < TX_NB; b++) {
@@ -1621,30 +1650,73 @@ __global__ void __launch_bounds__(TX_TPB, TX_MIN_CTAS) lift_bed_text_kernel(cons
                 r_u += (uint32_t)t1;
                 line_emit(A, X, S, t, base_l ? base_l + o_l : nullptr, base_u ? base_u + o_u : nullptr, o_l);
             }
-        }
-        __syncthreads();
-        if (base_l) {  // cooperative expansion of the queued multi-hit lines
-            const int nwl = min(S.wl_n, TX_WL_CAP);
-            for (int e = warp_id(); e < nwl; e += TX_NW)
-                if (S.wl_cnt[e] <= TX_HEAVY_MIN)
-                    expand_line_coop<false>(A, X.ey, X.R, X.g0 + (S.wl_p0[e] - X.s0), S.wl_lo[e], S.wl_cnt[e],
-                                            base_l + S.wl_off[e], S.xscr + warp_id() * TX_HEAVY_MIN,
-                                            S.xaux + warp_id() * TX_HEAVY_MIN, nullptr, lane_id(), 32);
-            __syncthreads();
-            for (int e = 0; e < nwl; e++) {
-                const int cnt = S.wl_cnt[e];
-                if (cnt <= TX_HEAVY_MIN) continue;
-                const uint64_t p0 = X.g0 + (S.wl_p0[e] - X.s0);
-                if (cnt <= TX_XSCR) {
-                    expand_line_coop<true>(A, X.ey, X.R, p0, S.wl_lo[e], cnt, base_l + S.wl_off[e], S.xscr, S.xaux,
-                                           S.scan64, tid, TX_TPB);
-                } else if (cnt <= TX_GSCR && A.gscr) {
-                    unsigned long long *g = A.gscr + (size_t)blockIdx.x * (TX_GSCR + TX_GSCR / 2);
-                    expand_line_coop<true>(A, X.ey, X.R, p0, S.wl_lo[e], cnt, base_l + S.wl_off[e], g,
-                                           reinterpret_cast<uint32_t *>(g + TX_GSCR), S.scan64, tid, TX_TPB);
-                } else {
-                    expand_line(A, X.ey, X.R, p0, S.wl_lo[e], cnt, base_l + S.wl_off[e], tid, TX_TPB);
+        };
+
+        if (!direct_l) {
+            // ---- phase E: format from the cached state into the stages; no barrier inside ---
+#pragma unroll
+            for (int b = 0; b < TX_NB; b++) {
+                const uint32_t o_l = (uint32_t)(ex[b] >> 32), o_u = (uint32_t)ex[b];
+                line_emit(A, X, S, st[b], stage_l + o_l, base_u ? base_u + o_u : nullptr, o_l);
+            }
+            emit_uncached(stage_l);
+            run_expansions(stage_l);
+        } else {
+            // ---- large tile (fan-out): the lifted text goes out in rounds of TX_OUT_STAGE -
+            // TX_ROUND_SLACK bytes through the stage.  A line belongs to the round its first row
+            // starts in; lines longer than the slack, and the uncached ones, are written to
+            // global memory directly AFTER the rounds (a round's copy-out may cover their bytes).
+#pragma unroll
+            for (int b = 0; b < TX_NB; b++)  // unmatched stream first
+                line_emit(A, X, S, st[b], nullptr, base_u ? base_u + (uint32_t)ex[b] : nullptr, 0);
+            {
+                constexpr uint32_t W = TX_OUT_STAGE - TX_ROUND_SLACK;
+                uint32_t cached_end = 0;
+#pragma unroll
+                for (int b = 0; b < TX_NB; b++) cached_end += (uint32_t)(bt[b] >> 32);
+                for (uint32_t r0 = 0; r0 < cached_end; r0 += W) {
+                    bool any = false;
+#pragma unroll
+                    for (int b = 0; b < TX_NB; b++) {
+                        const uint32_t o_l = (uint32_t)(ex[b] >> 32), len = (uint32_t)(v[b] >> 32);
+                        any = any || (len > 0 && len <= TX_ROUND_SLACK && o_l >= r0 && o_l - r0 < W);
+                    }
+                    if (tid == 0) {
+                        S.rlo = 0xFFFFFFFFu;
+                        S.rhi = 0;
+                        S.wl_n = 0;
+                    }
+                    if (!__syncthreads_or(any)) continue;
+#pragma unroll
+                    for (int b = 0; b < TX_NB; b++) {
+                        const uint32_t o_l = (uint32_t)(ex[b] >> 32), len = (uint32_t)(v[b] >> 32);
+                        if (len > 0 && len <= TX_ROUND_SLACK && o_l >= r0 && o_l - r0 < W) {
+                            line_emit(A, X, S, st[b], stage_l + (o_l - r0), nullptr, o_l - r0);
+                            atomicMin(&S.rlo, o_l);
+                            atomicMax(&S.rhi, o_l + len);
+                        }
+                    }
+                    run_expansions(stage_l);
+                    // the chained offset is needed only now: the formatting of the first round gave the
+                    // predecessors time to publish their aggregates
+                    if (!have_base) resolve_now();
+                    if (gb_l + tot_l <= A.lifted_cap)
+                        copy_out(A.lifted + gb_l + S.rlo, S.out_words, S.rhi - S.rlo, S.rlo - r0);
+                    __syncthreads();
                 }
+                if (!have_base) resolve_now();
+                char *const glob_l = gb_l + tot_l <= A.lifted_cap ? A.lifted + gb_l : nullptr;
+                if (tid == 0) S.wl_n = 0;
+                __syncthreads();
+                if (glob_l) {
+#pragma unroll
+                    for (int b = 0; b < TX_NB; b++) {
+                        const uint32_t o_l = (uint32_t)(ex[b] >> 32), len = (uint32_t)(v[b] >> 32);
+                        if (len > TX_ROUND_SLACK) line_emit(A, X, S, st[b], glob_l + o_l, nullptr, o_l);
+                    }
+                }
+                emit_uncached(glob_l);
+                if (glob_l) run_expansions(glob_l);
             }
         }
         // resolve + copy-out of this tile are deferred until the next tile has been counted
