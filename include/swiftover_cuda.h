@@ -174,6 +174,15 @@ int swo_lift_bed_text_dev(swo_ctx *ctx, const char *d_in, size_t in_len, char *d
 int swo_load_genome_2bit(swo_ctx *ctx, const uint8_t *packed, size_t packed_bytes,
                          const int64_t *contig_off, const int64_t *contig_len, int n_contigs);
 
+/* Destination genome from an uncompressed FASTA file (IndexedFastaFile(genomefile), vcf.d:38):
+ * packed to 2 bit/base with side channels for lower-case (soft-masked) bases and for every
+ * non-ACGT symbol, so that the REF check stays byte exact (vcf.d:144).  Sequences are keyed by
+ * the chain's destination contigs: call after swo_load_chain. */
+int swo_load_genome_fasta(swo_ctx *ctx, const char *path);
+/* fa.hasSeq(name) / fa.seqLen(name) (vcf.d:79-83); -1 if absent */
+int swo_genome_has_seq(const swo_ctx *ctx, const char *name);
+int64_t swo_genome_seq_len(const swo_ctx *ctx, const char *name);
+
 /* flags bit0 = matched (vcf.d:134), bit1 = refchg (vcf.d:144-161).  out_ref has
  * the layout of ref_bytes/ref_off and receives the destination REF
  * (fetchSequence, vcf.d:143, clipped at the contig end), out_reflen its length. */
@@ -181,6 +190,17 @@ int swo_lift_vcf_points(swo_ctx *ctx, size_t n, const int32_t *tcid, const int32
                         const int32_t *reflen, const uint64_t *ref_off, const char *ref_bytes,
                         size_t ref_bytes_len, int32_t *out_qcid, int32_t *out_pos, uint8_t *flags,
                         int32_t *out_reflen, char *out_ref);
+
+/* liftVCF, text -> text (vcf.d:29-176) for an uncompressed text VCF held in memory.  The
+ * header rewrite (vcf.d:59-108) and the column split / join run on the host; the per-record
+ * work of vcf.d:115-169 (liftDirectly, REF fetch and compare, refchg) runs in
+ * lift_vcf_points_kernel.  Columns the reference does not touch are passed through byte for
+ * byte.  chainfile / genomefile: the strings written to the ##liftoverChainfile / ##contig
+ * source= / ##liftoverGenome lines; filedate: "YYYYMMDD" for ##fileDate (NULL = today).
+ * out->lifted = what the reference writes to -o, out->unmatched = to -u (input header + the
+ * records without a block).  Needs swo_load_genome_fasta or swo_load_genome_2bit. */
+int swo_lift_vcf_text(swo_ctx *ctx, const char *in, size_t in_len, const char *chainfile,
+                      const char *genomefile, const char *filedate, swo_text_out *out);
 
 /* ---- helpers ------------------------------------------------------------ */
 

@@ -1040,6 +1040,252 @@ int orc_lift_vcf_points(const orc_chainfile *cf, const uint8_t *packed, const in
     return ORC_OK;
 }
 
+/* ------------------------------------------------------------ liftVCF on text */
+static int is_space(unsigned char c) { return c == ' ' || (c >= 9 && c <= 13); }
+static int buf_puts(orc_buf *b, const char *s) { return buf_put(b, s, strlen(s)); }
+typedef struct {
+    const char *name;
+    size_t name_len;
+    char *seq;
+    int64_t len;
+} fa_seq;
+
+static int fa_parse(const char *fa, size_t n, fa_seq **out, int *nout) {
+    int cap = 16, cnt = 0;
+    fa_seq *v = (fa_seq *)malloc(sizeof(fa_seq) * (size_t)cap);
+    size_t i = 0;
+    while (i < n) {
+        size_t e = i;
+        while (e < n && fa[e] != '\n') e++;
+        if (fa[i] == '>') {
+            if (cnt == cap) {
+                cap *= 2;
+                v = (fa_seq *)realloc(v, sizeof(fa_seq) * (size_t)cap);
+            }
+            size_t a = i + 1, b = a;
+            while (b < e && !is_space((unsigned char)fa[b])) b++;
+            v[cnt].name = fa + a;
+            v[cnt].name_len = b - a;
+            v[cnt].seq = (char *)malloc(n - e + 1);
+            v[cnt].len = 0;
+            cnt++;
+        } else if (cnt > 0) {
+            for (size_t k = i; k < e; k++)
+                if (!is_space((unsigned char)fa[k])) v[cnt - 1].seq[v[cnt - 1].len++] = fa[k];
+        }
+        i = e + 1;
+    }
+    *out = v;
+    *nout = cnt;
+    return ORC_OK;
+}
+static const fa_seq *fa_find(const fa_seq *v, int n, const char *name, size_t len) {
+    for (int i = 0; i < n; i++)
+        if (v[i].name_len == len && memcmp(v[i].name, name, len) == 0) return &v[i];
+    return NULL;
+}
+
+/* vcf.d:200-215 */
+static int contig_numeric(const char *z, size_t n) {
+    if (n >= 3 && memcmp(z, "chr", 3) == 0) {
+        z += 3;
+        n -= 3;
+    }
+    if (n == 0) return 200; /* the reference would index out of bounds */
+    if (z[0] == 'X') return 100;
+    if (z[0] == 'Y') return 101;
+    if (z[0] == 'M') return 102;
+    size_t k = 0;
+    long v = 0;
+    while (k < n && z[k] >= '0' && z[k] <= '9') v = v * 10 + (z[k++] - '0');
+    if (k == 0) return 200;
+    return (int)v;
+}
+/* vcf.d:181-196: true if x sorts before y */
+static int contig_before(const char *x, const char *y) {
+    const size_t nx = strlen(x), ny = strlen(y);
+    const int ux = memchr(x, '_', nx) != NULL, uy = memchr(y, '_', ny) != NULL;
+    if (ux && !uy) return 0;
+    if (!ux && uy) return 1;
+    const int a = contig_numeric(x, nx), b = contig_numeric(y, ny);
+    if (a != b) return a < b;
+    return strcmp(x, y) < 0;
+}
+
+int orc_lift_vcf_text(const orc_chainfile *cf, const char *fasta, size_t fasta_len, const char *in,
+                      size_t in_len, const char *chainfile, const char *genomefile,
+                      const char *filedate, orc_buf *lifted, orc_buf *unmatched,
+                      orc_vcf_stats *st, char *err, size_t errcap) {
+    fa_seq *fa = NULL;
+    int nfa = 0;
+    fa_parse(fasta, fasta_len, &fa, &nfa);
+    orc_vcf_stats s = {0, 0, 0, 0};
+    int rc = ORC_OK;
+    int header_done = 0;
+    size_t i = 0;
+    /* IDs of the contig lines of the input header */
+    while (i < in_len && rc == ORC_OK) {
+        size_t e = i;
+        while (e < in_len && in[e] != '\n') e++;
+        const char *ln = in + i;
+        size_t n = e - i;
+        if (n > 0 && ln[n - 1] == '\r') n--;
+        i = e + 1;
+        if (n == 0) continue;
+        if (ln[0] == '#') {
+            if (n >= 2 && ln[1] == '#') { /* meta line: both files */
+                buf_put(lifted, ln, n);
+                buf_putc(lifted, '\n');
+                buf_put(unmatched, ln, n);
+                buf_putc(unmatched, '\n');
+                continue;
+            }
+            /* "#CHROM" line: the additions go in front of it (vcf.d:62-103) */
+            if (!header_done) {
+                static const char *refchg =
+                    "##INFO=<ID=refchg,Number=0,Type=Flag,Description=\"REF allele changed in new genome\">\n";
+                buf_put(lifted, refchg, strlen(refchg));
+                const int nq = orc_num_qsizes(cf);
+                int *ord = (int *)malloc(sizeof(int) * (size_t)(nq > 0 ? nq : 1));
+                for (int k = 0; k < nq; k++) ord[k] = k;
+                for (int a = 1; a < nq; a++) { /* insertion sort by contigSort */
+                    int v = ord[a], b = a - 1;
+                    while (b >= 0 && contig_before(orc_qsize_name(cf, v), orc_qsize_name(cf, ord[b]))) {
+                        ord[b + 1] = ord[b];
+                        b--;
+                    }
+                    ord[b + 1] = v;
+                }
+                for (int a = 0; a < nq; a++) {
+                    const char *k = orc_qsize_name(cf, ord[a]);
+                    const fa_seq *q = fa_find(fa, nfa, k, strlen(k));
+                    if (!q || q->len != orc_qsize_value(cf, ord[a])) continue; /* vcf.d:79-87 */
+                    /* an ID the header already has is not added again */
+                    char pat[512];
+                    snprintf(pat, sizeof pat, "##contig=<ID=%s", k);
+                    const size_t pl = strlen(pat);
+                    int dup = 0;
+                    for (size_t h = 0; h + pl < lifted->len && !dup; h++)
+                        if ((h == 0 || lifted->data[h - 1] == '\n') && memcmp(lifted->data + h, pat, pl) == 0 &&
+                            (lifted->data[h + pl] == ',' || lifted->data[h + pl] == '>'))
+                            dup = 1;
+                    if (dup) continue;
+                    buf_put(lifted, pat, pl);
+                    buf_puts(lifted, ",length=");
+                    buf_put_i64(lifted, orc_qsize_value(cf, ord[a]));
+                    buf_puts(lifted, ",source=");
+                    buf_puts(lifted, chainfile);
+                    buf_puts(lifted, ">\n");
+                }
+                free(ord);
+                buf_puts(lifted, "##fileDate=");
+                buf_puts(lifted, filedate);
+                buf_puts(lifted, "\n##liftoverProgram=swiftover\n");
+                buf_puts(lifted, "##liftoverProgramURL=https://github.com/blachlylab/swiftover\n");
+                buf_puts(lifted, "##liftoverChainfile=");
+                buf_puts(lifted, chainfile);
+                buf_puts(lifted, "\n##liftoverGenome=");
+                buf_puts(lifted, genomefile);
+                buf_putc(lifted, '\n');
+                header_done = 1;
+            }
+            buf_put(lifted, ln, n);
+            buf_putc(lifted, '\n');
+            buf_put(unmatched, ln, n);
+            buf_putc(unmatched, '\n');
+            continue;
+        }
+        /* record: columns are tab separated */
+        size_t c0[9], c1[9];
+        int nc = 0;
+        size_t a = 0;
+        for (size_t k = 0; k <= n && nc < 9; k++) {
+            if (k == n || ln[k] == '\t') {
+                c0[nc] = a;
+                c1[nc] = (nc == 8) ? n : k;
+                nc++;
+                a = k + 1;
+                if (nc == 8 && k < n) { /* everything after INFO passes through */
+                    c0[8] = a;
+                    c1[8] = n;
+                    nc = 9;
+                }
+            }
+        }
+        if (nc < 8) {
+            snprintf(err, errcap, "VCF record with fewer than 8 columns at byte %zu", (size_t)(ln - in));
+            rc = ORC_E_PARSE;
+            break;
+        }
+        int64_t pos1 = 0;
+        int ok = c1[1] > c0[1];
+        for (size_t k = c0[1]; k < c1[1]; k++) {
+            if (ln[k] < '0' || ln[k] > '9') ok = 0;
+            else pos1 = pos1 * 10 + (ln[k] - '0');
+            if (pos1 > 2147483647LL) ok = 0;
+        }
+        if (!ok) {
+            snprintf(err, errcap, "bad POS at byte %zu", (size_t)(ln - in));
+            rc = ORC_E_PARSE;
+            break;
+        }
+        s.n_records++;
+        const int tcid = orc_tcontig_id(cf, ln + c0[0], c1[0] - c0[0]);
+        int32_t q = -1;
+        int64_t c = pos1 - 1; /* rec.pos is 0-based */
+        const int hit = orc_lift_directly(cf, tcid, &q, &c); /* vcf.d:125 */
+        if (!hit) {                                        /* vcf.d:134-137 */
+            s.n_unmatched++;
+            buf_put(unmatched, ln, n);
+            buf_putc(unmatched, '\n');
+            continue;
+        }
+        s.n_matched++;
+        const char *qn = orc_qcontig_name(cf, q);
+        const size_t reflen = c1[3] - c0[3];
+        const fa_seq *fs = fa_find(fa, nfa, qn, strlen(qn));
+        int64_t m = 0;
+        if (fs && c >= 0 && c < fs->len) { /* fetchSequence, clipped (vcf.d:143) */
+            m = (int64_t)reflen;
+            if (c + m > fs->len) m = fs->len - c;
+        }
+        const int diff = ((size_t)m != reflen) || (m > 0 && memcmp(fs->seq + c, ln + c0[3], (size_t)m) != 0);
+        buf_put(lifted, qn, strlen(qn));
+        buf_putc(lifted, '\t');
+        buf_put_i64(lifted, c + 1);
+        buf_putc(lifted, '\t');
+        buf_put(lifted, ln + c0[2], c1[2] - c0[2]);
+        buf_putc(lifted, '\t');
+        if (diff) {
+            s.n_refchg++;
+            if (m > 0) buf_put(lifted, fs->seq + c, (size_t)m); /* vcf.d:156-157 */
+        } else {
+            buf_put(lifted, ln + c0[3], reflen);
+        }
+        buf_putc(lifted, '\t');
+        buf_put(lifted, ln + c0[4], c1[6] - c0[4]); /* ALT QUAL FILTER */
+        buf_putc(lifted, '\t');
+        if (diff) { /* vcf.d:161 */
+            if (c1[7] - c0[7] == 1 && ln[c0[7]] == '.') buf_put(lifted, "refchg", 6);
+            else {
+                buf_put(lifted, ln + c0[7], c1[7] - c0[7]);
+                buf_put(lifted, ";refchg", 7);
+            }
+        } else {
+            buf_put(lifted, ln + c0[7], c1[7] - c0[7]);
+        }
+        if (nc == 9) {
+            buf_putc(lifted, '\t');
+            buf_put(lifted, ln + c0[8], c1[8] - c0[8]);
+        }
+        buf_putc(lifted, '\n');
+    }
+    for (int k = 0; k < nfa; k++) free(fa[k].seq);
+    free(fa);
+    if (st) *st = s;
+    return rc;
+}
+
 /* ---------------------------------------------------- bench workload helper */
 size_t orc_format_bed3(const orc_chainfile *cf, size_t n, const int32_t *tcid, const int32_t *start,
                        const int32_t *end, char *out, size_t cap) {

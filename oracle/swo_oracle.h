@@ -164,6 +164,31 @@ int orc_lift_vcf_points(const orc_chainfile *cf, const uint8_t *packed,
                         int32_t *out_qcid, int32_t *out_pos, uint8_t *flags,
                         int32_t *out_reflen, char *out_ref);
 
+/* liftVCF on text (vcf.d:29-176), restated for an UNCOMPRESSED text VCF and an in-memory FASTA.
+ * The reference goes through htslib/dhtslib (absent here, parity unpinned): this restatement
+ * keeps every column it does not touch byte for byte, which is what htslib does for records
+ * whose numeric fields are already in canonical form.
+ *   header (vcf.d:59-108): input "##" lines in order; then, before "#CHROM",
+ *     ##INFO=<ID=refchg,Number=0,Type=Flag,Description="REF allele changed in new genome">
+ *     ##contig=<ID=k,length=n,source=<chainfile>>  for every destination contig k of the chain
+ *        (contigSort order, vcf.d:181-215) that the FASTA has with the same length, unless a
+ *        contig line with that ID already exists (htslib does not add a duplicate ID)
+ *     ##fileDate=<filedate>, ##liftoverProgram=swiftover, ##liftoverProgramURL=...,
+ *     ##liftoverChainfile=<chainfile>, ##liftoverGenome=<genomefile>
+ *     the unmatched file gets the input header unchanged (vcf.d:107-108)
+ *   record (vcf.d:115-169): liftDirectly(CHROM, POS-1); no hit -> unmatched file, unchanged;
+ *     hit -> CHROM, POS rewritten; newRef = FASTA[chrom][pos, pos+len(REF)) clipped at the end
+ *     of the sequence; if REF != newRef (byte exact): REF = newRef and INFO gets the flag
+ *     "refchg" ("." -> "refchg", else appended with ';').  ALT untouched, no strand handling.
+ * fasta: plain FASTA text ('>' name up to the first white space; sequence lines joined). */
+typedef struct orc_vcf_stats {
+    uint64_t n_records, n_matched, n_unmatched, n_refchg;
+} orc_vcf_stats;
+int orc_lift_vcf_text(const orc_chainfile *cf, const char *fasta, size_t fasta_len, const char *in,
+                      size_t in_len, const char *chainfile, const char *genomefile,
+                      const char *filedate, orc_buf *lifted, orc_buf *unmatched,
+                      orc_vcf_stats *st, char *err, size_t errcap);
+
 /* Workload helper for bench.py --impl reference (not part of the restatement):
  * writes "name\tstart\tend\n" rows for n records, names taken from the chain's
  * source contigs.  Returns bytes written (<= cap) or 0 if cap is too small. */

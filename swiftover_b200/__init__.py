@@ -7,5 +7,6 @@ mirroring the reference CLI) and this thin ctypes mirror of the reference's
 """
 from .chain import ChainFile, LiftedInterval, SwiftoverError  # noqa: F401
 from .bed import liftBED  # noqa: F401
+from .vcf import liftVCF  # noqa: F401
 
-__all__ = ["ChainFile", "LiftedInterval", "SwiftoverError", "liftBED"]
+__all__ = ["ChainFile", "LiftedInterval", "SwiftoverError", "liftBED", "liftVCF"]

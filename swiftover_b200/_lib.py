@@ -73,6 +73,10 @@ def lib():
         "swo_lift_bed_text": (i32, [vp, vp, sz, C.POINTER(SwoTextOut)]),
         "swo_lift_bed_text_dev": (i32, [vp, vp, sz, vp, sz, vp, sz, vp, vp]),
         "swo_load_genome_2bit": (i32, [vp, vp, sz, vp, vp, i32]),
+        "swo_load_genome_fasta": (i32, [vp, C.c_char_p]),
+        "swo_genome_has_seq": (i32, [vp, C.c_char_p]),
+        "swo_genome_seq_len": (i64, [vp, C.c_char_p]),
+        "swo_lift_vcf_text": (i32, [vp, C.c_char_p, sz, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(SwoTextOut)]),
         "swo_lift_vcf_points": (i32, [vp, sz, vp, vp, vp, vp, vp, sz, vp, vp, vp, vp, vp]),
         "swo_host_alloc": (vp, [sz]),
         "swo_host_free": (None, [vp]),

@@ -171,6 +171,26 @@ class ChainFile:
         self._ck(self._lib.swo_load_genome_2bit(self._h, _addr(packed), packed.nbytes, _addr(contig_off),
                                                 _addr(contig_len), len(contig_off)))
 
+    def load_genome_fasta(self, path):
+        """IndexedFastaFile(genomefile) (vcf.d:38): destination genome from an uncompressed FASTA."""
+        self._ck(self._lib.swo_load_genome_fasta(self._h, path.encode()))
+
+    def genome_seq_len(self, name):
+        """fa.seqLen(name), -1 if the FASTA has no such sequence (fa.hasSeq, vcf.d:79-83)."""
+        b = name.encode() if isinstance(name, str) else bytes(name)
+        return self._lib.swo_genome_seq_len(self._h, b)
+
+    def lift_vcf_text(self, data, chainfile="", genomefile="", filedate=None):
+        """liftVCF on an in-memory text VCF (vcf.d:29-176): returns (lifted, unmatched, stats)."""
+        buf = bytes(data)
+        out = L.SwoTextOut()
+        fd = None if filedate is None else filedate.encode()
+        self._ck(self._lib.swo_lift_vcf_text(self._h, buf, len(buf), chainfile.encode(), genomefile.encode(), fd,
+                                             C.byref(out)))
+        lifted = C.string_at(out.lifted, out.lifted_len) if out.lifted_len else b""
+        unm = C.string_at(out.unmatched, out.unmatched_len) if out.unmatched_len else b""
+        return lifted, unm, dict(n_records=out.n_records, n_matched=out.n_rows, n_unmatched=out.n_unmatched)
+
     def lift_vcf_points(self, tcid, pos, reflen, ref_off, ref_bytes):
         """Batched liftVCF record body (vcf.d:115-169)."""
         tcid = np.ascontiguousarray(tcid, np.int32)

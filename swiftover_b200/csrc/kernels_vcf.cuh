@@ -17,6 +17,12 @@ namespace swo {
 struct VcfArgs {
     TableView T;
     const uint8_t *packed;  // 2 bit/base, A=0 C=1 G=2 T=3
+    const uint8_t *lower;      // 1 bit/base: soft-masked (lower case); null if the genome has none
+    const uint8_t *exc_chunk;  // 1 bit per 4096 bases: chunk holds a non-ACGT symbol; null if none
+    const int64_t *exc_start;  // runs of non-ACGT symbols, sorted by start
+    const int32_t *exc_len;
+    const uint8_t *exc_byte;
+    int exc_n;
     const int64_t *g_off;   // [g_n] first base of each destination contig
     const int64_t *g_len;   // [g_n]
     int g_n;
@@ -29,6 +35,22 @@ struct VcfArgs {
     int32_t *out_reflen;
     char *out_ref;
 };
+
+// base g of the packed destination genome, exactly as the FASTA spells it (genome.hpp)
+__device__ __forceinline__ char genome_base(const VcfArgs &A, int64_t g) {
+    char base = "ACGT"[(__ldg(A.packed + (g >> 2)) >> ((g & 3) * 2)) & 3];
+    if (A.lower && ((__ldg(A.lower + (g >> 3)) >> (g & 7)) & 1)) base |= 0x20;
+    if (A.exc_n && ((__ldg(A.exc_chunk + (g >> 15)) >> ((g >> 12) & 7)) & 1)) {
+        int lo = 0, hi = A.exc_n;  // last run starting at or before g
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(A.exc_start + mid) <= g) lo = mid + 1;
+            else hi = mid;
+        }
+        if (lo > 0 && g < __ldg(A.exc_start + lo - 1) + __ldg(A.exc_len + lo - 1)) base = (char)__ldg(A.exc_byte + lo - 1);
+    }
+    return base;
+}
 
 __global__ void __launch_bounds__(256) lift_vcf_points_kernel(const VcfArgs A) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < A.n; i += gridDim.x * blockDim.x) {
@@ -54,7 +76,7 @@ __global__ void __launch_bounds__(256) lift_vcf_points_kernel(const VcfArgs A) {
         const int64_t g0 = q < A.g_n ? A.g_off[q] + c : 0;
         for (int k = 0; k < m; k++) {
             const int64_t g = g0 + k;
-            const char base = "ACGT"[(__ldg(A.packed + (g >> 2)) >> ((g & 3) * 2)) & 3];
+            const char base = genome_base(A, g);
             A.out_ref[ro + k] = base;
             diff |= base != A.ref[ro + k];  // vcf.d:144 byte-exact compare
         }

@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <fstream>
 #include <memory>
 #include <string>
@@ -19,6 +20,7 @@
 #include <vector>
 
 #include "chain_table.hpp"
+#include "genome.hpp"
 #include "kernels_binary.cuh"
 #include "kernels_text.cuh"
 #include "kernels_vcf.cuh"
@@ -88,7 +90,9 @@ struct Device {
     uint32_t thash_mask = 0;
     int nq = 0;  // destination contigs
     // genome replica
-    DevBuf g_packed, g_off, g_len;
+    DevBuf g_packed, g_off, g_len, g_lower, g_chunk, g_estart, g_elen, g_ebyte;
+    int g_exc_n = 0;
+    bool g_has_lower = false;
     int g_n = 0;
     // scratch for the look-back chains
     DevBuf scratch, gscr;
@@ -111,6 +115,9 @@ struct swo_ctx {
     bool have_chain = false;
     std::string err;
     uint64_t launches = 0;
+    GenomeStore genome;        // FASTA-loaded destination genome (host copy of the tables, vcf header needs lengths)
+    bool have_fasta = false;
+    std::string vcf_l, vcf_u;  // outputs of swo_lift_vcf_text
     // pinned result arenas handed to the caller
     PinBuf r_lifted, r_unm, r_off, r_rows, r_thick;
     size_t chunk_bytes = 64u << 20;
@@ -530,7 +537,7 @@ void swo_destroy(swo_ctx *c) {
         cudaSetDevice(d.ordinal);
         cudaDeviceSynchronize();
         for (DevBuf *b : {&d.blk, &d.tkey, &d.pkey, &d.toff, &d.cmeta, &d.ey, &d.thash, &d.tchars, &d.tnoff, &d.qoff, &d.qchars, &d.g_packed,
-                          &d.g_off, &d.g_len, &d.scratch, &d.gscr, &d.b_in, &d.b_off, &d.b_rows, &d.b_thick, &d.b_tot})
+                          &d.g_off, &d.g_len, &d.g_lower, &d.g_chunk, &d.g_estart, &d.g_elen, &d.g_ebyte, &d.scratch, &d.gscr, &d.b_in, &d.b_off, &d.b_rows, &d.b_thick, &d.b_tot})
             b->release();
         for (int s = 0; s < N_SLOTS; s++) {
             d.t_in[s].release();
@@ -850,8 +857,46 @@ int swo_load_genome_2bit(swo_ctx *c, const uint8_t *packed, size_t packed_bytes,
         if ((rc = upload(c, d.g_len, contig_len, (size_t)n_contigs, d.s_comp))) return rc;
         CK(c, cudaStreamSynchronize(d.s_comp));
         d.g_n = n_contigs;
+        d.g_exc_n = 0;
+        d.g_has_lower = false;
     }
+    c->have_fasta = false;
     return SWO_OK;
+}
+
+int swo_load_genome_fasta(swo_ctx *c, const char *path) {
+    if (!c || !path) return SWO_E_ARG;
+    if (!c->tab.nblocks()) return fail(c, SWO_E_STATE, "load the chain before the genome (sequences are keyed by its destination contigs)");
+    std::vector<int64_t> qs(c->tab.qnames.size(), 0);
+    for (size_t i = 0; i < qs.size(); i++)
+        for (const auto &kv : c->tab.qsizes)
+            if (kv.first == c->tab.qnames[i]) qs[i] = kv.second;
+    std::string err;
+    if (!genome_from_fasta(path, c->tab.qnames, qs, c->genome, err)) return fail(c, SWO_E_IO, "%s", err.c_str());
+    const GenomeStore &g = c->genome;
+    for (Device &d : c->dev) {
+        CK(c, cudaSetDevice(d.ordinal));
+        int rc;
+        if ((rc = upload(c, d.g_packed, g.packed.data(), g.packed.size(), d.s_comp))) return rc;
+        if ((rc = upload(c, d.g_off, g.off.data(), g.off.size(), d.s_comp))) return rc;
+        if ((rc = upload(c, d.g_len, g.len.data(), g.len.size(), d.s_comp))) return rc;
+        d.g_has_lower = g.any_lower;
+        if (g.any_lower && (rc = upload(c, d.g_lower, g.lower.data(), g.lower.size(), d.s_comp))) return rc;
+        d.g_exc_n = (int)g.exc_start.size();
+        if ((rc = upload(c, d.g_chunk, g.exc_chunk.data(), g.exc_chunk.size(), d.s_comp))) return rc;
+        if ((rc = upload(c, d.g_estart, g.exc_start.data(), g.exc_start.size(), d.s_comp))) return rc;
+        if ((rc = upload(c, d.g_elen, g.exc_len.data(), g.exc_len.size(), d.s_comp))) return rc;
+        if ((rc = upload(c, d.g_ebyte, g.exc_byte.data(), g.exc_byte.size(), d.s_comp))) return rc;
+        CK(c, cudaStreamSynchronize(d.s_comp));
+        d.g_n = (int)g.off.size();
+    }
+    c->have_fasta = true;
+    return SWO_OK;
+}
+
+int swo_genome_has_seq(const swo_ctx *c, const char *name) { return c && c->have_fasta && name && c->genome.has_seq(name); }
+int64_t swo_genome_seq_len(const swo_ctx *c, const char *name) {
+    return (c && c->have_fasta && name) ? c->genome.seq_len(name) : -1;
 }
 
 int swo_lift_vcf_points(swo_ctx *c, size_t n, const int32_t *tcid, const int32_t *pos, const int32_t *reflen,
@@ -887,6 +932,12 @@ int swo_lift_vcf_points(swo_ctx *c, size_t n, const int32_t *tcid, const int32_t
     A.g_off = d.g_off.as<int64_t>();
     A.g_len = d.g_len.as<int64_t>();
     A.g_n = d.g_n;
+    A.lower = d.g_has_lower ? d.g_lower.as<uint8_t>() : nullptr;
+    A.exc_n = d.g_exc_n;
+    A.exc_chunk = d.g_exc_n ? d.g_chunk.as<uint8_t>() : nullptr;
+    A.exc_start = d.g_estart.as<int64_t>();
+    A.exc_len = d.g_elen.as<int32_t>();
+    A.exc_byte = d.g_ebyte.as<uint8_t>();
     A.n = (uint32_t)n;
     A.tcid = d_tcid;
     A.pos = d_pos;
@@ -908,6 +959,191 @@ int swo_lift_vcf_points(swo_ctx *c, size_t n, const int32_t *tcid, const int32_t
     CK(c, cudaMemcpyAsync(flags, d_fl, n, cudaMemcpyDeviceToHost, st));
     if (out_ref && ref_bytes_len) CK(c, cudaMemcpyAsync(out_ref, d_oref, ref_bytes_len, cudaMemcpyDeviceToHost, st));
     CK(c, cudaStreamSynchronize(st));
+    return SWO_OK;
+}
+
+// ---- liftVCF on text ---------------------------------------------------------------------
+namespace {
+// vcf.d:200-215
+int contig_numeric(std::string_view z) {
+    if (z.size() >= 3 && z.substr(0, 3) == "chr") z.remove_prefix(3);
+    if (z.empty()) return 200;
+    if (z[0] == 'X') return 100;
+    if (z[0] == 'Y') return 101;
+    if (z[0] == 'M') return 102;
+    size_t k = 0;
+    long v = 0;
+    while (k < z.size() && z[k] >= '0' && z[k] <= '9') v = v * 10 + (z[k++] - '0');
+    return k == 0 ? 200 : (int)v;
+}
+// vcf.d:181-196
+bool contig_sort(const std::string &x, const std::string &y) {
+    const bool ux = x.find('_') != std::string::npos, uy = y.find('_') != std::string::npos;
+    if (ux != uy) return !ux;
+    const int a = contig_numeric(x), b = contig_numeric(y);
+    return a != b ? a < b : x < y;
+}
+void put_num(std::string &o, long long v) {
+    char b[24];
+    o.append(b, (size_t)snprintf(b, sizeof b, "%lld", v));
+}
+}  // namespace
+
+int swo_lift_vcf_text(swo_ctx *c, const char *in, size_t in_len, const char *chainfile, const char *genomefile,
+                      const char *filedate, swo_text_out *out) {
+    if (!c || !out || (in_len && !in) || !chainfile || !genomefile) return SWO_E_ARG;
+    memset(out, 0, sizeof *out);
+    if (c->dev.empty()) return fail(c, SWO_E_CUDA, "inspection-only context: no CUDA device, and there is no CPU fallback");
+    if (!c->have_chain) return fail(c, SWO_E_STATE, "no chain loaded");
+    if (!c->dev[0].g_n) return fail(c, SWO_E_STATE, "no genome loaded");
+    char today[16];
+    if (!filedate) {  // addFiledate (vcf.d:99)
+        time_t t = time(nullptr);
+        struct tm tmv;
+        localtime_r(&t, &tmv);
+        strftime(today, sizeof today, "%Y%m%d", &tmv);
+        filedate = today;
+    }
+    std::string &L = c->vcf_l, &U = c->vcf_u;
+    L.clear();
+    U.clear();
+    // pass 1: header, and the columns of every record
+    struct Rec {
+        size_t a, n;       // line
+        uint32_t c[9];     // column starts, relative to a; c[8] = start of the pass-through tail or n+1
+    };
+    std::vector<Rec> recs;
+    std::vector<int32_t> tcid, pos, rl;
+    std::vector<uint64_t> ro;
+    std::string refb;
+    std::vector<std::string> hdr_contigs;
+    bool header_done = false;
+    for (size_t i = 0; i < in_len;) {
+        const char *nlp = (const char *)memchr(in + i, '\n', in_len - i);
+        const size_t e = nlp ? (size_t)(nlp - in) : in_len;
+        size_t n = e - i;
+        const char *ln = in + i;
+        const size_t a = i;
+        i = e + 1;
+        if (n && ln[n - 1] == '\r') n--;
+        if (!n) continue;
+        if (ln[0] == '#') {
+            if (n >= 2 && ln[1] == '#') {
+                L.append(ln, n).push_back('\n');
+                U.append(ln, n).push_back('\n');
+                if (n > 13 && !memcmp(ln, "##contig=<ID=", 13)) {
+                    size_t k = 13;
+                    while (k < n && ln[k] != ',' && ln[k] != '>') k++;
+                    hdr_contigs.emplace_back(ln + 13, k - 13);
+                }
+                continue;
+            }
+            if (!header_done) {  // vcf.d:62-103: additions go in front of the #CHROM line
+                L += "##INFO=<ID=refchg,Number=0,Type=Flag,Description=\"REF allele changed in new genome\">\n";
+                std::vector<std::string> keys;
+                for (const auto &kv : c->tab.qsizes) keys.push_back(kv.first);
+                std::stable_sort(keys.begin(), keys.end(), contig_sort);
+                for (const std::string &k : keys) {
+                    int64_t qsz = -1, glen = -1;
+                    for (const auto &kv : c->tab.qsizes)
+                        if (kv.first == k) qsz = kv.second;
+                    if (c->have_fasta) {
+                        glen = c->genome.seq_len(k);
+                    } else {  // 2-bit genome given directly: lengths are per destination contig id
+                        for (size_t q = 0; q < c->tab.qnames.size(); q++)
+                            if (c->tab.qnames[q] == k && (int)q < c->dev[0].g_n) glen = qsz;
+                    }
+                    if (glen < 0 || glen != qsz) continue;  // vcf.d:79-87
+                    if (std::find(hdr_contigs.begin(), hdr_contigs.end(), k) != hdr_contigs.end()) continue;
+                    L += "##contig=<ID=" + k + ",length=";
+                    put_num(L, qsz);
+                    L += std::string(",source=") + chainfile + ">\n";
+                }
+                L += std::string("##fileDate=") + filedate + "\n##liftoverProgram=swiftover\n";
+                L += "##liftoverProgramURL=https://github.com/blachlylab/swiftover\n";
+                L += std::string("##liftoverChainfile=") + chainfile + "\n##liftoverGenome=" + genomefile + "\n";
+                header_done = true;
+            }
+            L.append(ln, n).push_back('\n');
+            U.append(ln, n).push_back('\n');
+            continue;
+        }
+        Rec r;
+        r.a = a;
+        r.n = n;
+        int nc = 0;
+        size_t st0 = 0;
+        for (size_t k = 0; k <= n && nc < 8; k++)
+            if (k == n || ln[k] == '\t') {
+                r.c[nc++] = (uint32_t)st0;
+                st0 = k + 1;
+            }
+        if (nc < 8) return fail(c, SWO_E_PARSE, "VCF record with fewer than 8 columns at byte %zu", a);
+        r.c[8] = (uint32_t)st0;  // one past the tab that ends INFO (n + 1 if INFO is the last column)
+        long long p1 = 0;
+        bool ok = r.c[2] - 1 > r.c[1];
+        for (size_t k = r.c[1]; k + 1 < r.c[2]; k++) {
+            if (ln[k] < '0' || ln[k] > '9') ok = false;
+            else p1 = p1 * 10 + (ln[k] - '0');
+            if (p1 > 2147483647ll) ok = false;
+        }
+        if (!ok) return fail(c, SWO_E_PARSE, "bad POS at byte %zu", a);
+        recs.push_back(r);
+        tcid.push_back(c->tab.tcontig_id(std::string_view(ln, r.c[1] - 1)));
+        pos.push_back((int32_t)(p1 - 1));  // rec.pos is 0-based
+        const size_t rlen = r.c[4] - 1 - r.c[3];
+        rl.push_back((int32_t)rlen);
+        ro.push_back(refb.size());
+        refb.append(ln + r.c[3], rlen);
+    }
+    // the record body on the GPU (vcf.d:115-169)
+    const size_t n = recs.size();
+    std::vector<int32_t> oq(n), op(n), orl(n);
+    std::vector<uint8_t> fl(n);
+    std::string oref(refb.size(), '\0');
+    if (n) {
+        int rc = swo_lift_vcf_points(c, n, tcid.data(), pos.data(), rl.data(), ro.data(), refb.data(), refb.size(),
+                                     oq.data(), op.data(), fl.data(), orl.data(), oref.data());
+        if (rc) return rc;
+    }
+    // pass 2: join
+    uint64_t nm = 0, nu = 0;
+    for (size_t k = 0; k < n; k++) {
+        const Rec &r = recs[k];
+        const char *ln = in + r.a;
+        if (!(fl[k] & 1)) {  // vcf.d:134-137
+            U.append(ln, r.n).push_back('\n');
+            nu++;
+            continue;
+        }
+        nm++;
+        L += c->tab.qnames[oq[k]];
+        L.push_back('\t');
+        put_num(L, (long long)op[k] + 1);
+        L.push_back('\t');
+        L.append(ln + r.c[2], r.c[3] - r.c[2]);  // ID + tab
+        const bool chg = (fl[k] & 2) != 0;
+        if (chg) L.append(oref.data() + ro[k], (size_t)orl[k]);  // vcf.d:156-157
+        else L.append(ln + r.c[3], r.c[4] - 1 - r.c[3]);
+        L.push_back('\t');
+        L.append(ln + r.c[4], r.c[7] - r.c[4]);  // ALT QUAL FILTER + tab
+        const size_t info_end = r.c[8] - 1;         // INFO = [c[7], info_end)
+        if (chg) {                                   // vcf.d:161
+            if (info_end - r.c[7] == 1 && ln[r.c[7]] == '.') L += "refchg";
+            else L.append(ln + r.c[7], info_end - r.c[7]).append(";refchg");
+        } else {
+            L.append(ln + r.c[7], info_end - r.c[7]);
+        }
+        if (info_end < r.n) L.append(ln + info_end, r.n - info_end);  // FORMAT and samples, with their tab
+        L.push_back('\n');
+    }
+    out->lifted = L.data();
+    out->lifted_len = L.size();
+    out->unmatched = U.data();
+    out->unmatched_len = U.size();
+    out->n_records = n;
+    out->n_rows = nm;
+    out->n_unmatched = nu;
     return SWO_OK;
 }
 

@@ -67,6 +67,11 @@ int swo_load_genome_2bit(swo_ctx* ctx, const(ubyte)* packed, size_t packed_bytes
 int swo_lift_vcf_points(swo_ctx* ctx, size_t n, const(int)* tcid, const(int)* pos, const(int)* reflen,
                         const(ulong)* ref_off, const(char)* ref_bytes, size_t ref_bytes_len, int* out_qcid,
                         int* out_pos, ubyte* flags, int* out_reflen, char* out_ref);
+int swo_load_genome_fasta(swo_ctx* ctx, const(char)* path);
+int swo_genome_has_seq(const(swo_ctx)* ctx, const(char)* name);
+long swo_genome_seq_len(const(swo_ctx)* ctx, const(char)* name);
+int swo_lift_vcf_text(swo_ctx* ctx, const(char)* inbuf, size_t in_len, const(char)* chainfile,
+                      const(char)* genomefile, const(char)* filedate, swo_text_out* o);
 void* swo_host_alloc(size_t bytes);
 void swo_host_free(void* p);
 int swo_set_option(swo_ctx* ctx, const(char)* key, long value);

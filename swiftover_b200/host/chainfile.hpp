@@ -95,4 +95,8 @@ class ChainFile {
 void liftBED(const std::string &chainfile, const std::string &infile, const std::string &outfile,
              const std::string &unmatched);
 
+// vcf.d:29-32 (uncompressed text VCF, uncompressed FASTA)
+void liftVCF(const std::string &chainfile, const std::string &genomefile, const std::string &infile,
+             const std::string &outfile, const std::string &unmatched);
+
 }  // namespace swiftover

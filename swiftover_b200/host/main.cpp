@@ -88,8 +88,10 @@ int main(int argc, char **argv) {
             liftBED(chain, in, out, unm);  // main.d:121
         } else if (type == "vcf") {
             if (genome.empty()) throw Error(SWO_E_ARG, "Genome FASTA (for the destination build) required.");
-            throw Error(SWO_E_ARG, "vcf text I/O is not built yet in this host (the point-lift + REF-check kernels are "
-                                   "reachable through swo_lift_vcf_points)");
+            if (!exists(genome)) throw Error(SWO_E_IO, "Genome FASTA does not exist");
+            if (in.empty() || in == "-" || out.empty() || out == "-")  // vcf.d:42 "need dhtslib to support stdin/stdout"
+                throw Error(SWO_E_ARG, "VCF liftover needs -i and -o file names");
+            liftVCF(chain, genome, in, out, unm);  // main.d:130-134
         } else if (type == "maf") {
             throw Error(SWO_E_ARG, "maf is out of scope of this engine (experimental upstream)");
         } else {

@@ -255,6 +255,28 @@ class OracleChain:
         self.L.orc_rows_free(C.byref(r))
         return out
 
+    def lift_vcf_text(self, fasta: bytes, text: bytes, chainfile="", genomefile="", filedate="20240101"):
+        """liftVCF on text (vcf.d:29-176): (lifted, unmatched, stats)."""
+        class St(C.Structure):
+            _fields_ = [("n_records", C.c_uint64), ("n_matched", C.c_uint64), ("n_unmatched", C.c_uint64),
+                        ("n_refchg", C.c_uint64)]
+        fn = self.L.orc_lift_vcf_text
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_char_p, C.c_char_p, C.c_char_p,
+                       C.POINTER(OrcBuf), C.POINTER(OrcBuf), C.POINTER(St), C.c_char_p, C.c_size_t]
+        lifted, unm, st = OrcBuf(), OrcBuf(), St()
+        err = C.create_string_buffer(256)
+        rc = fn(self.h, fasta, len(fasta), text, len(text), chainfile.encode(), genomefile.encode(), filedate.encode(),
+                C.byref(lifted), C.byref(unm), C.byref(st), err, 256)
+        out = (C.string_at(lifted.data, lifted.len) if lifted.len else b"",
+               C.string_at(unm.data, unm.len) if unm.len else b"",
+               dict(n_records=st.n_records, n_matched=st.n_matched, n_unmatched=st.n_unmatched, n_refchg=st.n_refchg))
+        self.L.orc_buf_free(C.byref(lifted))
+        self.L.orc_buf_free(C.byref(unm))
+        if rc:
+            raise OracleError(rc, err.value.decode())
+        return out
+
     def lift_vcf_points(self, packed, contig_off, contig_len, tcid, pos, reflen, ref_off, ref_bytes):
         packed = np.ascontiguousarray(packed, np.uint8)
         contig_off = np.ascontiguousarray(contig_off, np.int64)
