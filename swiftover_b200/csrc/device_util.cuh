@@ -113,6 +113,47 @@ __device__ __forceinline__ uint64_t lookback_resolve(uint64_t *desc, int tile, u
     if (lane == 0) st_relaxed_u64(desc + tile, LB_INC | (excl + aggregate));
     return excl;
 }
+// Block-wide resolve: every thread of an NW-warp block calls it; NW*32 predecessors are
+// inspected per round (the walk is latency bound, so fewer rounds = shorter critical path).
+// part/found: NW words of shared memory each.  Returns the exclusive prefix (all threads).
+template <int NW>
+__device__ __forceinline__ uint64_t lookback_resolve_block(uint64_t *desc, int tile, uint64_t aggregate,
+                                                           unsigned long long *part, int *found) {
+    uint64_t excl = 0;
+    bool done = tile == 0;
+    int look = tile - 1;
+    while (!done) {
+        const int idx = look - (int)threadIdx.x;
+        uint64_t v = LB_INC;  // virtual tile before tile 0: inclusive prefix 0
+        if (idx >= 0) {
+            v = ld_relaxed_u64(desc + idx);
+            while ((v & LB_STATE) == LB_EMPTY) {
+                __nanosleep(20);
+                v = ld_relaxed_u64(desc + idx);
+            }
+        }
+        const unsigned m = __ballot_sync(FULL, (v & LB_STATE) == LB_INC);
+        const int f = m ? (__ffs(m) - 1) : 32;
+        const uint64_t s = warp_sum((lane_id() <= f) ? (v & LB_VALUE) : 0ull);
+        __syncthreads();  // previous round's readers are done
+        if (lane_id() == 0) {
+            part[warp_id()] = s;
+            found[warp_id()] = m != 0;
+        }
+        __syncthreads();
+        for (int w = 0; w < NW; w++) {  // warps are ordered by distance from the tile
+            excl += part[w];
+            if (found[w]) {
+                done = true;
+                break;
+            }
+        }
+        look -= NW * 32;
+    }
+    if (threadIdx.x == 0 && tile > 0) st_relaxed_u64(desc + tile, LB_INC | (excl + aggregate));
+    return excl;
+}
+
 __device__ __forceinline__ uint64_t lookback_exclusive(uint64_t *desc, int tile, uint64_t aggregate) {
     lookback_publish(desc, tile, aggregate);
     return lookback_resolve(desc, tile, aggregate);

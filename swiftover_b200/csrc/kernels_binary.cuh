@@ -93,10 +93,11 @@ __device__ __forceinline__ void expand_query(const LiftArgs &A, const int2 *ey, 
     }
 }
 
-__global__ void __launch_bounds__(LI_TPB) lift_intervals_kernel(const LiftArgs A) {
+__global__ void __launch_bounds__(LI_TPB, 4) lift_intervals_kernel(const LiftArgs A) {
     __shared__ int s_tile;
     __shared__ uint32_t s_scan[LI_NW + 1];
-    __shared__ uint64_t s_base;
+    __shared__ unsigned long long s_lb_part[LI_NW];
+    __shared__ int s_lb_found[LI_NW];
     __shared__ int s_wl_n;
     __shared__ uint32_t s_wl_q[LI_WL_CAP];
     __shared__ int s_wl_lo[LI_WL_CAP];
@@ -137,24 +138,39 @@ __global__ void __launch_bounds__(LI_TPB) lift_intervals_kernel(const LiftArgs A
         }
         Cand cd[LI_IPT];
         int nh[LI_IPT];
+        // row of a single-hit query, computed before the look-back is resolved
+        int r_meta[LI_IPT], r_s[LI_IPT], r_e[LI_IPT];
         uint32_t tsum = 0, unm = 0;
 #pragma unroll
         for (int k = 0; k < LI_IPT; k++) {
-            cd[k] = find_candidates(T, ey, tc[k], st[k], en[k]);
+            Block b0;
+            // sorted batches: same contig and a start that did not move back -> the lower bound only moves
+            // forward from the previous query's (a short gallop instead of a full search)
+            if (k > 0 && tc[k] == tc[k - 1] && st[k] >= st[k - 1] && tc[k] >= 0 && tc[k] < T.ntc)
+                cd[k] = find_candidates_from(T, load_cmeta(T, tc[k]).y, cd[k - 1].lo, st[k], en[k], b0);
+            else
+                cd[k] = find_candidates_b0(T, ey, tc[k], st[k], en[k], b0);
             nh[k] = count_hits(T, cd[k], st[k]);
             tsum += (uint32_t)nh[k];
             unm += (q0 + k < A.n && nh[k] == 0) ? 1u : 0u;
+            r_meta[k] = r_s[k] = r_e[k] = 0;
+            if (nh[k] == 1) {
+                int j = cd[k].lo;
+                if (!T.disjoint)
+                    while (!block_hits(b0, st[k])) b0 = load_block(T, ++j);
+                const RowCore r = make_row(b0, st[k], en[k]);
+                const unsigned char sb = A.strand ? strand_flip(__ldg(A.strand + q0 + k), r.inv) : 0;
+                r_meta[k] = r.qcid | ((int)sb << 16);
+                r_s[k] = r.s;
+                r_e[k] = r.e;
+            }
         }
         uint32_t tile_total;
         const uint32_t excl = block_exclusive_scan<uint32_t, LI_NW>(tsum, s_scan, &tile_total);
-        if (warp_id() == 0) {
-            const uint64_t b = lookback_exclusive(A.desc, tile, (uint64_t)tile_total);
-            if (tid == 0) s_base = b;
-        }
+        if (warp_id() == 0) lookback_publish(A.desc, tile, (uint64_t)tile_total);
         unm = warp_sum(unm);
         if (lane_id() == 0 && unm) atomicAdd((unsigned long long *)(A.totals + 1), (unsigned long long)unm);
-        __syncthreads();
-        const uint64_t gbase = s_base;
+        const uint64_t gbase = lookback_resolve_block<LI_NW>(A.desc, tile, (uint64_t)tile_total, s_lb_part, s_lb_found);
 
         // row_offset: four consecutive values per thread
         uint32_t off[LI_IPT];
@@ -185,18 +201,12 @@ __global__ void __launch_bounds__(LI_TPB) lift_intervals_kernel(const LiftArgs A
         for (int k = 0; k < LI_IPT; k++) {
             const uint32_t q = q0 + k;
             if (nh[k] == 1) {
-                int j = cd[k].lo;
-                Block b = load_block(T, j);
-                if (!T.disjoint)
-                    while (!block_hits(b, st[k])) b = load_block(T, ++j);
-                const RowCore r = make_row(b, st[k], en[k]);
                 if (run64 < A.rows_cap) {
-                    const unsigned char sb = A.strand ? strand_flip(__ldg(A.strand + q), r.inv) : 0;
-                    st_stream_v4(A.rows + run64, make_int4(r.qcid | ((int)sb << 16), r.s, r.e, (int)q));
+                    st_stream_v4(A.rows + run64, make_int4(r_meta[k], r_s[k], r_e[k], (int)q));
                     if (A.thick_s) {
                         const Thick th = lift_thick(T, ey, tc[k], __ldg(A.thick_s + q), __ldg(A.thick_e + q));
                         swo_thick t;
-                        thick_clamp(th, r.s, r.e, t.thick_start, t.thick_end);
+                        thick_clamp(th, r_s[k], r_e[k], t.thick_start, t.thick_end);
                         A.thick[run64] = t;
                     }
                 }

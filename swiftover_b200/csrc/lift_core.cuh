@@ -166,6 +166,41 @@ SWO_HD Cand find_candidates_b0(const TableView &T, const int2 *__restrict__ ey, 
     return c;
 }
 
+// first j in [lo,b) with key[j] > x, else b — exponential probe from lo, then bisection
+SWO_HD int gallop_gt(const int32_t *__restrict__ key, int lo, int b, int x) {
+    int a = lo, step = 1;
+    while (a < b) {
+        int p = a + step - 1;
+        if (p >= b) p = b - 1;
+        if (SWO_LDG(key + p) > x) {
+            int l = a, r = p;
+            while (l < r) {
+                const int m = (l + r) >> 1;
+                if (SWO_LDG(key + m) > x) r = m;
+                else l = m + 1;
+            }
+            return l;
+        }
+        a = p + 1;
+        step <<= 1;
+    }
+    return b;
+}
+// Candidates of a query known to start at or after an earlier query of the same contig whose
+// lower bound was lo_hint (sorted batches): the lower bound only moves forward, usually by 0-2.
+SWO_HD Cand find_candidates_from(const TableView &T, int contig_end, int lo_hint, int start, int end, Block &b0) {
+    Cand c;
+    const int lo = gallop_gt(T.pmaxKey, lo_hint, contig_end, start);
+    c.lo = c.hi = lo;
+    b0 = Block{0, 0, 0, 0};
+    if (lo >= contig_end) return c;
+    b0 = load_block(T, lo);
+    const int s1 = lo + 1 < contig_end ? SWO_LDG(T.tStartKey + lo + 1) : 0x7fffffff;
+    if (b0.tStart >= end) return c;
+    c.hi = s1 >= end ? lo + 1 : gallop_ge(T.tStartKey, lo + 2, contig_end, end);
+    return c;
+}
+
 SWO_HD bool block_hits(const Block &b, int start) { return b.tEnd > start; }
 
 // number of overlapping blocks in the candidate range
