@@ -210,7 +210,9 @@ void swo_host_free(void *p);
 
 /* tuning knobs: "chunk_bytes" = bytes of text per H2D/kernel/D2H pipeline stage
  * (default 64 MiB, up to 8 in flight; the tests shrink it to exercise chunk boundaries);
- * "zero_copy_input" = 1: pinned input is read by the kernel over PCIe instead of being staged (default 0) */
+ * "zero_copy_input" = 1: pinned input is read by the kernel over PCIe instead of being staged (default 0);
+ * "tile_bytes" = 0 (default: 16 KiB, lowered per chunk when the output is much larger than the input),
+ * 4096, 8192 or 16384: text tile size of lift_bed_text_kernel */
 int swo_set_option(swo_ctx *ctx, const char *key, int64_t value);
 
 /* number of kernel launches issued by this ctx since creation (bench.py's

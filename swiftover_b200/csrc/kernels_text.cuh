@@ -55,10 +55,9 @@ namespace swo {
 #endif
 constexpr int TX_TPB = TX_THREADS;
 constexpr int TX_NW = TX_TPB / 32;
-constexpr int TX_TILE = 16384;               // bytes of text per tile
+constexpr int TX_TILE = 16384;               // largest tile (bytes of text); TextArgs.tile_bytes picks 16, 8 or 4 KiB
 constexpr int TX_MSEG = 64;                  // bytes per newline-mask word
-constexpr int TX_SEG = TX_TILE / TX_TPB;     // bytes whose line starts a thread enumerates (64 or 32)
-static_assert(TX_SEG == 64 || TX_SEG == 32, "TX_THREADS must be 256 or 512");
+static_assert(TX_TILE / TX_TPB == 64 || TX_TILE / TX_TPB == 32, "TX_THREADS must be 256 or 512");
 constexpr int TX_PRE = 64;                   // bytes staged before the tile
 constexpr int TX_LOOK = 1024;                // bytes staged after the tile
 constexpr int TX_WIN = TX_PRE + TX_TILE + TX_LOOK;
@@ -107,6 +106,8 @@ struct TextArgs {
     const char *in;   // 16-byte aligned
     uint64_t in_len;  // includes `skip`
     uint32_t skip;    // leading bytes (< 16) that belong to the previous chunk; the text starts at in + skip
+    uint32_t tile_bytes;  // TX_TILE, or a smaller power of two (>= 16 * TX_THREADS) for inputs whose output is
+                          // much larger than the input, so that a tile's lifted text still fits the stage
     int ntiles;
     char *lifted;
     uint64_t lifted_cap;
@@ -1378,7 +1379,8 @@ __global__ void __launch_bounds__(TX_TPB, TX_MIN_CTAS) lift_bed_text_kernel(cons
         __syncthreads();
         const int tile = S.tile;
         if (tile >= A.ntiles) break;
-        const uint64_t t0 = (uint64_t)tile * TX_TILE;
+        const uint32_t tile_b = A.tile_bytes, seg = tile_b / TX_TPB;  // bytes a thread enumerates line starts of
+        const uint64_t t0 = (uint64_t)tile * tile_b;
 
         // ---- stage the window [t0-PRE, t0+TILE+LOOK); everything else reads as '\n' ----
         TileCtx X;
@@ -1387,7 +1389,7 @@ __global__ void __launch_bounds__(TX_TPB, TX_MIN_CTAS) lift_bed_text_kernel(cons
         X.S = &S;
         X.g0 = tile == 0 ? 0 : t0 - TX_PRE;  // absolute offset of the first staged byte
         X.s0 = tile == 0 ? TX_PRE : 0;       // its window offset
-        const uint64_t gend = min(A.in_len, t0 + TX_TILE + TX_LOOK);
+        const uint64_t gend = min(A.in_len, t0 + tile_b + TX_LOOK);
         const uint32_t nst = (uint32_t)(gend - X.g0);
         const uint32_t wv = X.s0 + nst;  // window offsets < wv hold input bytes
         {
@@ -1409,7 +1411,7 @@ __global__ void __launch_bounds__(TX_TPB, TX_MIN_CTAS) lift_bed_text_kernel(cons
         __syncthreads();
 
         // ---- newline masks of the window, 64 bytes per word -----------------------------
-        for (int sg = tid; sg < TX_NSEG; sg += TX_TPB) {
+        for (int sg = tid; sg < (int)((TX_PRE + tile_b + TX_LOOK) / TX_MSEG); sg += TX_TPB) {
             const uint4 *w = reinterpret_cast<const uint4 *>(win + sg * TX_MSEG);
             unsigned long long m = 0;
 #pragma unroll
@@ -1424,17 +1426,17 @@ __global__ void __launch_bounds__(TX_TPB, TX_MIN_CTAS) lift_bed_text_kernel(cons
         // line starts inside this thread's 64 bytes of the tile: the byte before is '\n'
         unsigned long long starts;
         {
-            const int w = (tid * TX_SEG) / TX_MSEG;  // mask word of this thread's bytes (window word w + 1)
+            const int w = (int)((tid * seg) / TX_MSEG);  // mask word of this thread's bytes (window word w + 1)
             starts = (S.nlm[w + 1] << 1) | (S.nlm[w] >> 63);
-            if (TX_SEG < TX_MSEG) starts = (starts >> ((tid * TX_SEG) % TX_MSEG)) & ((1ull << (TX_SEG % 64)) - 1ull);
+            if (seg < TX_MSEG) starts = (starts >> ((tid * seg) % TX_MSEG)) & ((1ull << seg) - 1ull);
         }
         if (tile == 0 && tid == 0)  // the text starts (with a line) at offset `skip`
             starts = (starts & ~((1ull << A.skip) - 1ull)) | (1ull << A.skip);
         unsigned long long valid = starts;
         {
-            const long long rem = (long long)A.in_len - (long long)(t0 + (uint64_t)tid * TX_SEG);
+            const long long rem = (long long)A.in_len - (long long)(t0 + (uint64_t)tid * seg);
             if (rem <= 0) valid = 0;
-            else if (rem < TX_SEG) valid &= (1ull << rem) - 1ull;
+            else if (rem < (long long)seg) valid &= (1ull << rem) - 1ull;
         }
         // line index = prefix over ALL starts (the valid ones are a prefix of them)
         uint32_t packed_tot;
@@ -1448,7 +1450,7 @@ __global__ void __launch_bounds__(TX_TPB, TX_MIN_CTAS) lift_bed_text_kernel(cons
             for (unsigned long long m = starts; m; m &= m - 1, j++) {
                 const int slot = j - wbase;
                 if (slot >= 0 && slot < TX_LCAP)
-                    S.lstart[slot] = (uint16_t)(TX_PRE + tid * TX_SEG + __ffsll((long long)m) - 1);
+                    S.lstart[slot] = (uint16_t)(TX_PRE + tid * seg + __ffsll((long long)m) - 1);
             }
             __syncthreads();
         };

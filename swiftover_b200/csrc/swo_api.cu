@@ -124,6 +124,10 @@ struct swo_ctx {
     // read pinned input from the kernel over PCIe instead of staging it with H2D copies: as fast as the
     // copy when nothing else uses the link, but slower than staging once D2H copies of the output overlap
     bool zero_copy_input = false;
+    // text tile size: TX_TILE, or 8192 / 4096 for inputs with large fan-out (a tile's lifted text should fit
+    // its 20 KiB stage); 0 = choose per chunk from the previous chunk's output/input ratio
+    uint32_t tile_bytes = TX_TILE;
+    bool tile_auto = true;
 };
 
 namespace {
@@ -278,8 +282,10 @@ int launch_lift_intervals(swo_ctx *c, Device &d, size_t n, const int32_t *tcid, 
 // ---- text path -------------------------------------------------------------------
 // d_in: 16-byte aligned; the text is d_in[skip, in_len) and starts with a line
 int launch_lift_text(swo_ctx *c, Device &d, const char *d_in, size_t in_len, char *d_lifted, size_t lifted_cap,
-                     char *d_unm, size_t unm_cap, uint64_t *d_sizes, cudaStream_t st, uint32_t skip = 0) {
-    const int ntiles = (int)((in_len + TX_TILE - 1) / TX_TILE);
+                     char *d_unm, size_t unm_cap, uint64_t *d_sizes, cudaStream_t st, uint32_t skip = 0,
+                     uint32_t tile_bytes = 0) {
+    if (!tile_bytes) tile_bytes = c->tile_bytes;
+    const int ntiles = (int)((in_len + tile_bytes - 1) / tile_bytes);
     const size_t scratch_bytes = 16 + (size_t)ntiles * 16;
     CK(c, d.scratch.reserve((scratch_bytes + 3) & ~(size_t)3));
     if (int rc = zero_async(c, d.scratch.p, scratch_bytes, d_sizes, 48, st)) return rc;
@@ -294,6 +300,7 @@ int launch_lift_text(swo_ctx *c, Device &d, const char *d_in, size_t in_len, cha
     A.nq = d.nq;
     A.in = d_in;
     A.skip = skip;
+    A.tile_bytes = tile_bytes;
     A.in_len = in_len;
     A.ntiles = ntiles;
     A.lifted = d_lifted;
@@ -369,6 +376,8 @@ int run_shard(swo_ctx *c, Device &d, const char *in, size_t a, size_t b, PinBuf 
             cudaGetLastError();
     }
     std::vector<uint32_t> skips(nch, 0);
+    // tile size of the next launches: follows the output/input ratio of the chunks seen so far
+    uint32_t tile_now = c->tile_bytes;
     // SWO_TRACE=1: per-chunk timeline (CUDA events on the three streams) printed to stderr
     static const bool trace = getenv("SWO_TRACE") != nullptr;
     struct Tr { cudaEvent_t h0, h1, k0, k1, o0, o1; };
@@ -385,10 +394,11 @@ int run_shard(swo_ctx *c, Device &d, const char *in, size_t a, size_t b, PinBuf 
             const uint32_t skip = (uint32_t)(reinterpret_cast<uintptr_t>(zc_in + off) & 15u);
             skips[k] = skip;
             return launch_lift_text(c, d, zc_in + off - skip, len + skip, d.t_out[s].as<char>(), d.t_out[s].cap,
-                                    d.t_unm[s].as<char>(), d.t_unm[s].cap, d.t_sizes[s].as<uint64_t>(), d.s_comp, skip);
+                                    d.t_unm[s].as<char>(), d.t_unm[s].cap, d.t_sizes[s].as<uint64_t>(), d.s_comp, skip,
+                                    tile_now);
         }
         return launch_lift_text(c, d, d.t_in[s].as<char>(), len, d.t_out[s].as<char>(), d.t_out[s].cap,
-                                d.t_unm[s].as<char>(), d.t_unm[s].cap, d.t_sizes[s].as<uint64_t>(), d.s_comp);
+                                d.t_unm[s].as<char>(), d.t_unm[s].cap, d.t_sizes[s].as<uint64_t>(), d.s_comp, 0, tile_now);
     };
     auto sizes_to_host = [&](int s) -> int {
         copy_sizes_kernel<<<1, 32, 0, d.s_comp>>>(d.t_sizes[s].as<uint64_t>(), hs + 6 * s);
@@ -439,6 +449,12 @@ int run_shard(swo_ctx *c, Device &d, const char *in, size_t a, size_t b, PinBuf 
             if ((rc = sizes_to_host(s))) return rc;
             CK(c, cudaEventSynchronize(d.ev_comp[s]));
             memcpy(sz, hs + 6 * s, 48);
+        }
+        if (c->tile_auto && len > 65536) {  // lifted bytes per input byte of this chunk -> tile size of later launches
+            const double ratio = (double)sz[0] / (double)len;
+            // measured on the reference's fixtures: 4 KiB tiles win for moderate fan-out (2.3 bytes out per byte
+            // in: 570 vs 380 M lines/s); for very large fan-out every tile overflows anyway and big tiles win
+            tile_now = (ratio >= 1.15 && ratio < 4.0) ? 4096u : (uint32_t)TX_TILE;
         }
         if (sz[5] && !res.has_err) {
             res.has_err = true;
@@ -576,6 +592,17 @@ int swo_set_option(swo_ctx *c, const char *key, int64_t value) {
     if (!strcmp(key, "chunk_bytes")) {
         if (value < 64) return fail(c, SWO_E_ARG, "chunk_bytes must be >= 64");
         c->chunk_bytes = (size_t)value;
+        return SWO_OK;
+    }
+    if (!strcmp(key, "tile_bytes")) {
+        if (value == 0) {
+            c->tile_auto = true;
+            c->tile_bytes = TX_TILE;
+            return SWO_OK;
+        }
+        if (value != 4096 && value != 8192 && value != 16384) return fail(c, SWO_E_ARG, "tile_bytes must be 0 (auto), 4096, 8192 or 16384");
+        c->tile_bytes = (uint32_t)value;
+        c->tile_auto = false;
         return SWO_OK;
     }
     if (!strcmp(key, "zero_copy_input")) {
@@ -806,6 +833,8 @@ int swo_lift_bed_text(swo_ctx *c, const char *in, size_t in_len, swo_text_out *o
                 swo_ctx local;  // private error sink; run_shard only touches err/launches/chunk_bytes
                 local.chunk_bytes = c->chunk_bytes;
                 local.zero_copy_input = c->zero_copy_input;
+                local.tile_bytes = c->tile_bytes;
+                local.tile_auto = c->tile_auto;
                 Device &d = c->dev[k];
                 res[k].rc = run_shard(&local, d, in, cut[k], cut[k + 1], &d.a_lifted, 0, &d.a_unm, 0, res[k]);
                 emsg[k] = local.err;

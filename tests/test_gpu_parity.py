@@ -215,6 +215,19 @@ def test_text_chunk_boundaries(oracle, chunk):
     cf.close()
 
 
+@pytest.mark.parametrize("tile", [4096, 8192])
+def test_text_small_tiles(oracle, tile):
+    """Smaller text tiles (chosen automatically for inputs with large fan-out) give the same bytes."""
+    cf, oc = pair(oracle, resource_bytes("hg19ToHg38.over.chain"))
+    cf.set_option("tile_bytes", tile)
+    for name in ("hg19_col123.bed", "chr1_hg19.bed", "test.bed"):
+        data = resource_bytes(name)
+        lifted, unm, _ = cf.lift_bed_text(data)
+        o_l, o_u, _ = oc.lift_bed(data)
+        assert lifted == o_l and unm == o_u, name
+    cf.close()
+
+
 @pytest.mark.parametrize("nshards", [2, 3, 4, 8])
 def test_text_logical_shards(oracle, nshards):
     """Byte-range sharder with N logical shards on one device: output must

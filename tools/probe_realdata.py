@@ -9,6 +9,8 @@ from swiftover_b200 import ChainFile, synth as S
 dev = torch.device("cuda", 0)
 rd = lambda n: gzip.open(os.path.join(ROOT, "tests/golden/resources", n + ".gz"), "rb").read()
 cf = ChainFile(text=rd("hg19ToHg38.over.chain"))
+if os.environ.get("TILE"):
+    cf.set_option("tile_bytes", int(os.environ["TILE"]))
 out = {}
 SETS = (("hg19_col123.bed", 200), ("chr1_hg19.bed", 300))
 if os.environ.get("ONLY"):
