@@ -897,10 +897,19 @@ struct TileCtx {
 
 // Count side of one line: parse, look up, search, exact output lengths.  Returns the
 // number of overlapping blocks, -1 for a line that is not a record, -2 for a malformed one.
+// What a thread remembers from its previous line (256 lines earlier in the tile).  In sorted input
+// the next line names the same contig and starts no earlier, so the contig lookup is a register
+// compare and the block search a short gallop from the previous lower bound.
+struct LineHint {
+    uint32_t nw[4];  // first 16 name bytes
+    uint32_t len0;   // name length; 0 = no hint
+    int tcid, lo, start, contig_end;
+};
+
 // allow_cw: a heavy-fan-out line may be handed to the block (count work list); such a line is marked
 // with both order bits (15 and 16) set and keeps its work-list slot in st.e2a5.
 __device__ __forceinline__ int line_count(const TextArgs &A, const TileCtx &X, uint32_t p, LineState &st,
-                                          uint32_t &len_l, uint32_t &len_u, const bool allow_cw) {
+                                          uint32_t &len_l, uint32_t &len_u, const bool allow_cw, LineHint &H) {
     const TableView &T = A.T;
     len_l = len_u = 0;
     st.pq = p;
@@ -941,8 +950,20 @@ __device__ __forceinline__ int line_count(const TextArgs &A, const TileCtx &X, u
                 b0 = Block{v.x, v.y, v.z, v.w};
             }
         } else {
-            F.tcid = lookup_tcontig_win(A, X.win, p, F.len0, nw);
-            cd = find_candidates_b0(T, X.ey, F.tcid, F.start, F.end, b0);
+            const bool same = H.len0 == F.len0 && F.len0 <= 16u && H.nw[0] == nw[0] && H.nw[1] == nw[1] &&
+                              H.nw[2] == nw[2] && H.nw[3] == nw[3];
+            F.tcid = same ? H.tcid : lookup_tcontig_win(A, X.win, p, F.len0, nw);
+            if (same && F.tcid >= 0 && F.start >= H.start) {
+                cd = find_candidates_from(T, H.contig_end, H.lo, F.start, F.end, b0);
+            } else {
+                cd = find_candidates_b0(T, X.ey, F.tcid, F.start, F.end, b0);
+                H.contig_end = F.tcid >= 0 && F.tcid < T.ntc ? load_cmeta(T, F.tcid).y : 0;
+            }
+            H.nw[0] = nw[0], H.nw[1] = nw[1], H.nw[2] = nw[2], H.nw[3] = nw[3];
+            H.len0 = F.len0;
+            H.tcid = F.tcid;
+            H.lo = cd.lo;
+            H.start = F.start;
         }
         const int nh = count_hits(T, cd, F.start);
         st.pq = p | (F.q << 16);
@@ -1497,6 +1518,8 @@ __global__ void __launch_bounds__(TX_TPB, TX_MIN_CTAS) lift_bed_text_kernel(cons
 
         // ---- phase C: parse + search + exact output lengths; no barrier inside ---------
         uint32_t c_rec = 0, c_rows = 0, c_unm = 0;
+        LineHint H;
+        H.len0 = 0;
         LineState st[TX_NB];
         unsigned long long v[TX_NB], ex[TX_NB], bt[TX_NB];
 #pragma unroll
@@ -1506,7 +1529,7 @@ __global__ void __launch_bounds__(TX_TPB, TX_MIN_CTAS) lift_bed_text_kernel(cons
             v[b] = 0;
             if (li < nlines) {
                 uint32_t ll, lu;
-                const int nh = line_count(A, X, S.lstart[li], st[b], ll, lu, true);
+                const int nh = line_count(A, X, S.lstart[li], st[b], ll, lu, true, H);
                 v[b] = ((unsigned long long)ll << 32) | lu;
                 if (nh == -2)  // max(~p0) == first bad line
                     atomicMax((unsigned long long *)(A.sizes + 5),
@@ -1549,7 +1572,7 @@ __global__ void __launch_bounds__(TX_TPB, TX_MIN_CTAS) lift_bed_text_kernel(cons
                 uint32_t ll = 0, lu = 0;
                 if (li < nlines) {
                     LineState t;
-                    const int nh = line_count(A, X, S.lstart[li - wbase], t, ll, lu, false);
+                    const int nh = line_count(A, X, S.lstart[li - wbase], t, ll, lu, false, H);
                     if (nh == -2)
                         atomicMax((unsigned long long *)(A.sizes + 5),
                                   ~(unsigned long long)(X.g0 + ((t.pq & 0xFFFFu) - X.s0)));
@@ -1643,7 +1666,9 @@ __global__ void __launch_bounds__(TX_TPB, TX_MIN_CTAS) lift_bed_text_kernel(cons
                 uint32_t ll = 0, lu = 0;
                 LineState t;
                 t.meta = FL_NONE;
-                if (li < nlines) line_count(A, X, S.lstart[li - wbase], t, ll, lu, false);
+                LineHint H2;
+                H2.len0 = 0;
+                if (li < nlines) line_count(A, X, S.lstart[li - wbase], t, ll, lu, false, H2);
                 unsigned long long t1;
                 const unsigned long long e1 =
                     block_exclusive_scan<unsigned long long, TX_NW>(((unsigned long long)ll << 32) | lu, S.scan64, &t1);
