@@ -93,7 +93,6 @@ struct NameEnt {
     uint32_t off, len;
     uint32_t w[4];  // name bytes 0..15, little endian, zero padded
 };
-constexpr int TX_CM_CAP = 256;  // per-contig table entries kept in shared memory
 
 struct TextArgs {
     TableView T;
@@ -315,9 +314,14 @@ __device__ __forceinline__ char *put_i32(char *d, int v) {
     return e;
 }
 
-// (plain loads: inside the text kernel the destination-name table usually lives in shared memory)
-__device__ __forceinline__ uint32_t qname_len(const TextArgs &A, int qcid) {
-    return A.qname_off[qcid + 1] - A.qname_off[qcid];
+// Destination-name table: usually the CTA's shared-memory copy, else the global one; the two
+// pointers live in shared memory (TextSmem::qoff_p / qchars_p, set once per CTA).  The kernel's
+// argument struct itself is never copied or modified: it stays in the constant bank.
+__device__ __forceinline__ const uint32_t *tx_qoff();
+__device__ __forceinline__ const char *tx_qchars();
+__device__ __forceinline__ uint32_t qname_len(const TextArgs &, int qcid) {
+    const uint32_t *o = tx_qoff();
+    return o[qcid + 1] - o[qcid];
 }
 
 // bytes of one lifted row (bed.d:161-199)
@@ -344,9 +348,11 @@ __device__ __forceinline__ char *copy_field(char *d, const Reader &R, uint64_t a
     return d;
 }
 
-__device__ __forceinline__ char *emit_qname(char *d, const TextArgs &A, int qcid) {
-    const uint32_t o = A.qname_off[qcid], e = A.qname_off[qcid + 1];
-    for (uint32_t i = o; i < e; i++) *d++ = A.qname_chars[i];  // bed.d:163
+__device__ __forceinline__ char *emit_qname(char *d, const TextArgs &, int qcid) {
+    const uint32_t *off = tx_qoff();
+    const char *ch = tx_qchars();
+    const uint32_t o = off[qcid], e = off[qcid + 1];
+    for (uint32_t i = o; i < e; i++) *d++ = ch[i];  // bed.d:163
     return d;
 }
 
@@ -852,8 +858,9 @@ struct TextSmem {
     int br_tcid, br_lo_q, br_hi_q, br_blo;
     uint32_t br_name_off, br_name_len;
     int4 br_blk[TX_USE_BRACKET ? TX_BR_CAP : 1];
-    int4 cmeta[TX_CM_CAP];  // per-contig {first block, end block, Eytzinger offset, samples}
-    // destination contig names
+    // destination contig names (copy, when they fit) and the pointers every formatter uses
+    const uint32_t *qoff_p;
+    const char *qchars_p;
     uint32_t qoff[TX_QN_MAX + 1];
     char qchars[TX_QCHARS];
     unsigned long long xscr[TX_XSCR];  // expand_line_coop scratch: TX_NW warp regions / one block region
@@ -868,6 +875,10 @@ struct TextSmem {
     int wl_cnt[TX_WL_CAP];
     uint32_t wl_off[TX_WL_CAP];  // byte offset inside the tile's lifted output
 };
+
+extern __shared__ __align__(16) unsigned char tx_smem_raw[];
+__device__ __forceinline__ const uint32_t *tx_qoff() { return reinterpret_cast<const TextSmem *>(tx_smem_raw)->qoff_p; }
+__device__ __forceinline__ const char *tx_qchars() { return reinterpret_cast<const TextSmem *>(tx_smem_raw)->qchars_p; }
 
 // What a thread keeps about one line between the count and the emit phase (8 words).
 //   meta: bits 0-1 kind, 2-3 hit class (0, 1, 2 = two or more), 4-6 numf-3, 7-14 strand byte,
@@ -1338,24 +1349,21 @@ __device__ __forceinline__ void lookback_resolve2_block(TextSmem &S, uint64_t *d
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(TX_TPB, TX_MIN_CTAS) lift_bed_text_kernel(const TextArgs A0) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    TextSmem &S = *reinterpret_cast<TextSmem *>(smem_raw);
+__global__ void __launch_bounds__(TX_TPB, TX_MIN_CTAS) lift_bed_text_kernel(const __grid_constant__ TextArgs A) {
+    TextSmem &S = *reinterpret_cast<TextSmem *>(tx_smem_raw);
     const int tid = threadIdx.x;
-    TextArgs A = A0;
     {  // destination contig names -> shared memory when they fit (once per persistent CTA)
-        const int nq = A0.nq;
-        if (nq <= TX_QN_MAX && A0.qname_off[nq] <= (uint32_t)TX_QCHARS) {
-            for (int i = tid; i <= nq; i += TX_TPB) S.qoff[i] = A0.qname_off[i];
-            const uint32_t nc = A0.qname_off[nq];
-            for (uint32_t i = tid; i < nc; i += TX_TPB) S.qchars[i] = A0.qname_chars[i];
-            A.qname_off = S.qoff;
-            A.qname_chars = S.qchars;
+        const int nq = A.nq;
+        const bool fits = nq <= TX_QN_MAX && A.qname_off[nq] <= (uint32_t)TX_QCHARS;
+        if (fits) {
+            for (int i = tid; i <= nq; i += TX_TPB) S.qoff[i] = A.qname_off[i];
+            const uint32_t nc = A.qname_off[nq];
+            for (uint32_t i = tid; i < nc; i += TX_TPB) S.qchars[i] = A.qname_chars[i];
         }
-    }
-    if (A0.T.ntc <= TX_CM_CAP) {  // per-contig table -> shared memory
-        for (int i = tid; i < A0.T.ntc; i += TX_TPB) S.cmeta[i] = A0.T.cmeta[i];
-        A.T.cmeta = S.cmeta;
+        if (tid == 0) {
+            S.qoff_p = fits ? S.qoff : A.qname_off;
+            S.qchars_p = fits ? S.qchars : A.qname_chars;
+        }
     }
     const TableView &T = A.T;
     unsigned char *const win = reinterpret_cast<unsigned char *>(S.in_words);
