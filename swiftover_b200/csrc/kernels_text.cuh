@@ -835,6 +835,22 @@ __device__ __forceinline__ uint32_t nl_mask4(uint32_t x) {
 }
 
 
+// per-tile constants shared by the helpers; one copy per CTA in shared memory (TextSmem::X),
+// written by thread 0 while the tile is staged
+struct TileCtx {
+    Reader R;
+    uint64_t g0;     // absolute offset of window offset s0
+    uint32_t s0;
+    uint32_t limit;  // see fast_parse
+};
+
+// pending tile (formatted, not yet copied out): block-uniform, kept in shared memory
+struct PendTile {
+    int pend, have_base, direct_l, direct_u, tile;
+    uint32_t tot_l, tot_u;
+    uint64_t gb_l, gb_u;
+};
+
 struct TextSmem {
     uint32_t in_words[(TX_WIN + TX_PAD) / 4];
     uint32_t out_words[TX_OUT_STAGE / 4 + 8];
@@ -848,6 +864,8 @@ struct TextSmem {
     unsigned long long scan64[TX_NB * TX_NW];
     uint32_t scan32[TX_NW + 1];
     uint64_t base_l, base_u;
+    TileCtx X;
+    PendTile P;
     unsigned long long lb_part[TX_NW][2];
     int lb_found[TX_NW][2];
     int tile;
@@ -879,6 +897,10 @@ struct TextSmem {
 extern __shared__ __align__(16) unsigned char tx_smem_raw[];
 __device__ __forceinline__ const uint32_t *tx_qoff() { return reinterpret_cast<const TextSmem *>(tx_smem_raw)->qoff_p; }
 __device__ __forceinline__ const char *tx_qchars() { return reinterpret_cast<const TextSmem *>(tx_smem_raw)->qchars_p; }
+// fixed shared-memory addresses: no register or load is spent on them
+__device__ __forceinline__ TextSmem &tx_smem() { return *reinterpret_cast<TextSmem *>(tx_smem_raw); }
+__device__ __forceinline__ const unsigned char *tx_win() { return reinterpret_cast<const unsigned char *>(tx_smem().in_words); }
+__device__ __forceinline__ const int2 *tx_ey() { return tx_smem().ey; }
 
 // What a thread keeps about one line between the count and the emit phase (8 words).
 //   meta: bits 0-1 kind, 2-3 hit class (0, 1, 2 = two or more), 4-6 numf-3, 7-14 strand byte,
@@ -895,16 +917,6 @@ struct LineState {
 __device__ __forceinline__ int st_kind(const LineState &st) { return (int)(st.meta & 3u); }
 __device__ __forceinline__ int st_hits(const LineState &st) { return (int)((st.meta >> 2) & 3u); }
 
-// per-tile constants shared by the helpers
-struct TileCtx {
-    const unsigned char *win;
-    const int2 *ey;
-    TextSmem *S;
-    Reader R;
-    uint64_t g0;     // absolute offset of window offset s0
-    uint32_t s0;
-    uint32_t limit;  // see fast_parse
-};
 
 // Count side of one line: parse, look up, search, exact output lengths.  Returns the
 // number of overlapping blocks, -1 for a line that is not a record, -2 for a malformed one.
@@ -929,17 +941,17 @@ __device__ __forceinline__ int line_count(const TextArgs &A, const TileCtx &X, u
     st.meta = FL_NONE;
     FastLine F;
     uint32_t nw[4];
-    const int kind = fast_parse(A, X.win, p, X.limit, F, nw);
+    const int kind = fast_parse(A, tx_win(), p, X.limit, F, nw);
     if (kind == FL_NONE) return -1;
     if (kind == FL_FAST) {
-        TextSmem &S = *X.S;
+        TextSmem &S = tx_smem();
         // sorted tiles: the query usually falls inside the tile's bracket, whose blocks are
         // in shared memory -> contig lookup and block search without a global load
         bool inb = S.br_cnt >= 0 && F.len0 == S.br_name_len && F.start >= S.br_lo_q && F.end <= S.br_hi_q &&
                    F.end > F.start;
         if (inb) {
             uint32_t i = 0;
-            while (i < F.len0 && X.win[p + i] == X.win[S.br_name_off + i]) i++;
+            while (i < F.len0 && tx_win()[p + i] == tx_win()[S.br_name_off + i]) i++;
             inb = i == F.len0;
         }
         Cand cd;
@@ -963,11 +975,11 @@ __device__ __forceinline__ int line_count(const TextArgs &A, const TileCtx &X, u
         } else {
             const bool same = H.len0 == F.len0 && F.len0 <= 16u && H.nw[0] == nw[0] && H.nw[1] == nw[1] &&
                               H.nw[2] == nw[2] && H.nw[3] == nw[3];
-            F.tcid = same ? H.tcid : lookup_tcontig_win(A, X.win, p, F.len0, nw);
+            F.tcid = same ? H.tcid : lookup_tcontig_win(A, tx_win(), p, F.len0, nw);
             if (same && F.tcid >= 0 && F.start >= H.start) {
                 cd = find_candidates_from(T, H.contig_end, H.lo, F.start, F.end, b0);
             } else {
-                cd = find_candidates_b0(T, X.ey, F.tcid, F.start, F.end, b0);
+                cd = find_candidates_b0(T, tx_ey(), F.tcid, F.start, F.end, b0);
                 H.contig_end = F.tcid >= 0 && F.tcid < T.ntc ? load_cmeta(T, F.tcid).y : 0;
             }
             H.nw[0] = nw[0], H.nw[1] = nw[1], H.nw[2] = nw[2], H.nw[3] = nw[3];
@@ -1002,7 +1014,7 @@ __device__ __forceinline__ int line_count(const TextArgs &A, const TileCtx &X, u
         } else {
             const uint32_t fixed = fast_fixed_len(F);
             Thick th{0, 0, 0};
-            if (F.numf >= 8) th = lift_thick(T, X.ey, F.tcid, F.v6, F.v7);
+            if (F.numf >= 8) th = lift_thick(T, tx_ey(), F.tcid, F.v6, F.v7);
             RowCore r;
             r.key = r.s = r.e = r.qcid = 0;
             r.inv = 1;
@@ -1048,7 +1060,7 @@ __device__ __forceinline__ int line_count(const TextArgs &A, const TileCtx &X, u
         return nh;
     }
     SlowCount C;
-    slow_count(A, X.ey, X.R, X.g0 + (p - X.s0), C);
+    slow_count(A, tx_ey(), X.R, X.g0 + (p - X.s0), C);
     if (C.status == LN_ERROR) return -2;
     if (C.status == LN_SKIP) return -1;
     len_l = C.len_l;
@@ -1118,11 +1130,11 @@ __device__ __forceinline__ void fast_expand_sorted(const TextArgs &A, const Tile
     const TableView &T = A.T;
     Thick th{0, 0, 0};
     if (F.numf >= 8) {  // thickStart / thickEnd are re-read from the line (not kept between the phases)
-        const uint32_t *W = reinterpret_cast<const uint32_t *>(X.win);
+        const uint32_t *W = reinterpret_cast<const uint32_t *>(tx_win());
         uint32_t v6 = 0, v7 = 0, n6 = 0, n7 = 0, term;
         parse_uint_swar(W, F.a6, v6, n6, term);
         parse_uint_swar(W, F.a6 + n6 + 1, v7, n7, term);
-        th = lift_thick(T, X.ey, tcid, (int)v6, (int)v7);
+        th = lift_thick(T, tx_ey(), tcid, (int)v6, (int)v7);
     }
     unsigned char sb = F.strand;
     char *d = dst;
@@ -1131,7 +1143,7 @@ __device__ __forceinline__ void fast_expand_sorted(const TextArgs &A, const Tile
         if (!T.disjoint && !block_hits(b, F.start)) continue;
         const RowCore r = make_row(b, F.start, F.end);
         if (F.numf >= 6) sb = strand_flip(sb, r.inv);
-        d = fast_emit_row(d, A, X.win, F, th, r, sb);
+        d = fast_emit_row(d, A, tx_win(), F, th, r, sb);
     }
 }
 
@@ -1148,8 +1160,8 @@ __device__ __forceinline__ void line_emit(const TextArgs &A, const TileCtx &X, T
     const uint32_t p = st.pq & 0xFFFFu;
     if (nhc == 0) {
         if (!dst_u) return;
-        if (kind == FL_FAST) copy_span(dst_u, X.win, p, (st.pq >> 16) + 1);
-        else slow_emit(A, X.ey, X.R, X.g0 + (p - X.s0), st.x, 0, dst_u);
+        if (kind == FL_FAST) copy_span(dst_u, tx_win(), p, (st.pq >> 16) + 1);
+        else slow_emit(A, tx_ey(), X.R, X.g0 + (p - X.s0), st.x, 0, dst_u);
         return;
     }
     if (!dst_l) return;
@@ -1166,7 +1178,7 @@ __device__ __forceinline__ void line_emit(const TextArgs &A, const TileCtx &X, T
         r.qcid = (int)(st.meta >> 17);
         r.inv = (st.meta >> 15) & 1u ? -1 : 1;
         r.key = 0;
-        fast_emit_row(dst_l, A, X.win, F, th, r, strand_flip(F.strand, r.inv));
+        fast_emit_row(dst_l, A, tx_win(), F, th, r, strand_flip(F.strand, r.inv));
     } else if (kind == FL_FAST && (st.meta & (3u << 15)) && st.y <= TX_SEQ_FANOUT && (st.meta >> 17) != 0x7FFFu) {
         FastLine F;
         state_to_fast(st, F);
@@ -1174,9 +1186,9 @@ __device__ __forceinline__ void line_emit(const TextArgs &A, const TileCtx &X, T
     } else if (kind == FL_FAST && st.y <= TX_SMALL_FANOUT && ((st.meta >> 4) & 7u) < 5u) {
         FastLine F;
         state_to_fast(st, F);
-        fast_expand_small(A, X.win, F, st.x, st.y, dst_l);
+        fast_expand_small(A, tx_win(), F, st.x, st.y, dst_l);
     } else if (nhc == 1) {
-        slow_emit(A, X.ey, X.R, X.g0 + (p - X.s0), st.x, 1, dst_l);
+        slow_emit(A, tx_ey(), X.R, X.g0 + (p - X.s0), st.x, 1, dst_l);
     } else {
         const int slot = atomicAdd(&S.wl_n, 1);
         if (slot < TX_WL_CAP) {
@@ -1185,7 +1197,7 @@ __device__ __forceinline__ void line_emit(const TextArgs &A, const TileCtx &X, T
             S.wl_cnt[slot] = st.y;
             S.wl_off[slot] = o_l;
         } else {
-            expand_line(A, X.ey, X.R, X.g0 + (p - X.s0), st.x, st.y, dst_l, 0, 1);
+            expand_line(A, tx_ey(), X.R, X.g0 + (p - X.s0), st.x, st.y, dst_l, 0, 1);
         }
     }
 }
@@ -1199,10 +1211,10 @@ __device__ __noinline__ void coop_count_lines(const TextArgs &A, const TileCtx &
     for (int e = 0; e < ncw; e++) {
         FastLine F;
         uint32_t nw[4];
-        fast_parse(A, X.win, S.cw_p[e], X.limit, F, nw);
+        fast_parse(A, tx_win(), S.cw_p[e], X.limit, F, nw);
         const uint32_t fixed = fast_fixed_len(F);
         Thick th{0, 0, 0};
-        if (F.numf >= 8) th = lift_thick(T, X.ey, S.cw_tcid[e], F.v6, F.v7);
+        if (F.numf >= 8) th = lift_thick(T, tx_ey(), S.cw_tcid[e], F.v6, F.v7);
         uint32_t part = 0;
         const int lo = S.cw_lo[e], cnt = S.cw_cnt[e];
         for (int c = tid; c < cnt; c += TX_TPB) {
@@ -1377,25 +1389,24 @@ __global__ void __launch_bounds__(TX_TPB, TX_MIN_CTAS) lift_bed_text_kernel(cons
     // counted (none of which touches the stages); only then is its chained offset resolved
     // and the stage copied out.  Predecessor tiles therefore have a whole extra count phase
     // to publish their aggregates and the look-back practically never waits.
-    bool pend = false, p_have_base = false, p_direct_l = false, p_direct_u = false;
-    int p_tile = 0;
-    uint32_t p_tot_l = 0, p_tot_u = 0;
-    uint64_t p_gb_l = 0, p_gb_u = 0;
+    if (tid == 0) S.P.pend = 0;
     auto flush = [&]() {  // block-uniform
-        if (!pend) return;
-        if (!p_have_base) {
-            lookback_resolve2_block(S, A.desc_l, A.desc_u, p_tile, (uint64_t)p_tot_l, (uint64_t)p_tot_u);
-            p_gb_l = S.base_l;
-            p_gb_u = S.base_u;
+        PendTile &P = S.P;
+        if (!P.pend) return;
+        uint64_t gb_l = P.gb_l, gb_u = P.gb_u;
+        if (!P.have_base) {
+            lookback_resolve2_block(S, A.desc_l, A.desc_u, P.tile, (uint64_t)P.tot_l, (uint64_t)P.tot_u);
+            gb_l = S.base_l;
+            gb_u = S.base_u;
         }
-        if (p_tile == A.ntiles - 1 && tid == 0) {
-            A.sizes[0] = p_gb_l + p_tot_l;
-            A.sizes[1] = p_gb_u + p_tot_u;
+        if (P.tile == A.ntiles - 1 && tid == 0) {
+            A.sizes[0] = gb_l + P.tot_l;
+            A.sizes[1] = gb_u + P.tot_u;
         }
-        if (!p_direct_l && p_tot_l && p_gb_l + p_tot_l <= A.lifted_cap) copy_out(A.lifted + p_gb_l, S.out_words, p_tot_l);
-        if (!p_direct_u && p_tot_u && p_gb_u + p_tot_u <= A.unm_cap) copy_out(A.unm + p_gb_u, S.unm_words, p_tot_u);
-        pend = false;
+        if (!P.direct_l && P.tot_l && gb_l + P.tot_l <= A.lifted_cap) copy_out(A.lifted + gb_l, S.out_words, P.tot_l);
+        if (!P.direct_u && P.tot_u && gb_u + P.tot_u <= A.unm_cap) copy_out(A.unm + gb_u, S.unm_words, P.tot_u);
         __syncthreads();  // the stages may be overwritten now
+        if (tid == 0) P.pend = 0;
     };
 
     for (;;) {
@@ -1412,31 +1423,32 @@ __global__ void __launch_bounds__(TX_TPB, TX_MIN_CTAS) lift_bed_text_kernel(cons
         const uint64_t t0 = (uint64_t)tile * tile_b;
 
         // ---- stage the window [t0-PRE, t0+TILE+LOOK); everything else reads as '\n' ----
-        TileCtx X;
-        X.win = win;
-        X.ey = S.ey;
-        X.S = &S;
-        X.g0 = tile == 0 ? 0 : t0 - TX_PRE;  // absolute offset of the first staged byte
-        X.s0 = tile == 0 ? TX_PRE : 0;       // its window offset
+        TileCtx &X = S.X;
+        const uint64_t g0 = tile == 0 ? 0 : t0 - TX_PRE;  // absolute offset of the first staged byte
+        const uint32_t s0 = tile == 0 ? TX_PRE : 0;       // its window offset
         const uint64_t gend = min(A.in_len, t0 + tile_b + TX_LOOK);
-        const uint32_t nst = (uint32_t)(gend - X.g0);
-        const uint32_t wv = X.s0 + nst;  // window offsets < wv hold input bytes
+        const uint32_t nst = (uint32_t)(gend - g0);
+        const uint32_t wv = s0 + nst;  // window offsets < wv hold input bytes
         {
             const uint32_t nvec = nst >> 4;
-            const int4 *src = reinterpret_cast<const int4 *>(A.in + X.g0);
-            int4 *dstv = reinterpret_cast<int4 *>(win + X.s0);
+            const int4 *src = reinterpret_cast<const int4 *>(A.in + g0);
+            int4 *dstv = reinterpret_cast<int4 *>(win + s0);
             for (uint32_t v = tid; v < nvec; v += TX_TPB) dstv[v] = ld_stream_v4(src + v);
-            for (uint32_t i = (nvec << 4) + tid; i < nst; i += TX_TPB) win[X.s0 + i] = (unsigned char)A.in[X.g0 + i];
-            for (uint32_t i = tid; i < X.s0; i += TX_TPB) win[i] = '\n';
+            for (uint32_t i = (nvec << 4) + tid; i < nst; i += TX_TPB) win[s0 + i] = (unsigned char)A.in[g0 + i];
+            for (uint32_t i = tid; i < s0; i += TX_TPB) win[i] = '\n';
             for (uint32_t i = wv + tid; i < TX_WIN + TX_PAD; i += TX_TPB) win[i] = '\n';
         }
-        X.R.win = win + X.s0;
-        X.R.ws = X.g0;
-        X.R.wlen = nst;
-        X.R.g = reinterpret_cast<const unsigned char *>(A.in);
-        X.R.in_len = A.in_len;
-        // a terminator found at or beyond this window offset is not the line's real end
-        X.limit = gend == A.in_len ? wv + 1 : wv;
+        if (tid == 0) {
+            X.g0 = g0;
+            X.s0 = s0;
+            X.R.win = win + s0;
+            X.R.ws = g0;
+            X.R.wlen = nst;
+            X.R.g = reinterpret_cast<const unsigned char *>(A.in);
+            X.R.in_len = A.in_len;
+            // a terminator found at or beyond this window offset is not the line's real end
+            X.limit = gend == A.in_len ? wv + 1 : wv;
+        }
         __syncthreads();
 
         // ---- newline masks of the window, 64 bytes per word -----------------------------
@@ -1633,7 +1645,7 @@ __global__ void __launch_bounds__(TX_TPB, TX_MIN_CTAS) lift_bed_text_kernel(cons
             if (nwl == 0) return;
             for (int e = warp_id(); e < nwl; e += TX_NW)
                 if (S.wl_cnt[e] <= TX_HEAVY_MIN)
-                    expand_line_coop<false>(A, X.ey, X.R, X.g0 + (S.wl_p0[e] - X.s0), S.wl_lo[e], S.wl_cnt[e],
+                    expand_line_coop<false>(A, tx_ey(), X.R, X.g0 + (S.wl_p0[e] - X.s0), S.wl_lo[e], S.wl_cnt[e],
                                             base + S.wl_off[e], S.xscr + warp_id() * TX_HEAVY_MIN,
                                             S.xaux + warp_id() * TX_HEAVY_MIN, nullptr, lane_id(), 32);
             __syncthreads();
@@ -1642,14 +1654,14 @@ __global__ void __launch_bounds__(TX_TPB, TX_MIN_CTAS) lift_bed_text_kernel(cons
                 if (cnt <= TX_HEAVY_MIN) continue;
                 const uint64_t p0 = X.g0 + (S.wl_p0[e] - X.s0);
                 if (cnt <= TX_XSCR) {
-                    expand_line_coop<true>(A, X.ey, X.R, p0, S.wl_lo[e], cnt, base + S.wl_off[e], S.xscr, S.xaux, S.scan64,
+                    expand_line_coop<true>(A, tx_ey(), X.R, p0, S.wl_lo[e], cnt, base + S.wl_off[e], S.xscr, S.xaux, S.scan64,
                                            tid, TX_TPB);
                 } else if (cnt <= TX_GSCR && A.gscr) {
                     unsigned long long *g = A.gscr + (size_t)blockIdx.x * (TX_GSCR + TX_GSCR / 2);
-                    expand_line_coop<true>(A, X.ey, X.R, p0, S.wl_lo[e], cnt, base + S.wl_off[e], g,
+                    expand_line_coop<true>(A, tx_ey(), X.R, p0, S.wl_lo[e], cnt, base + S.wl_off[e], g,
                                            reinterpret_cast<uint32_t *>(g + TX_GSCR), S.scan64, tid, TX_TPB);
                 } else {
-                    expand_line(A, X.ey, X.R, p0, S.wl_lo[e], cnt, base + S.wl_off[e], tid, TX_TPB);
+                    expand_line(A, tx_ey(), X.R, p0, S.wl_lo[e], cnt, base + S.wl_off[e], tid, TX_TPB);
                 }
             }
             __syncthreads();
@@ -1755,16 +1767,21 @@ __global__ void __launch_bounds__(TX_TPB, TX_MIN_CTAS) lift_bed_text_kernel(cons
             }
         }
         // resolve + copy-out of this tile are deferred until the next tile has been counted
-        pend = true;
-        p_have_base = have_base;
-        p_direct_l = direct_l;
-        p_direct_u = direct_u;
-        p_tile = tile;
-        p_tot_l = tot_l;
-        p_tot_u = tot_u;
-        p_gb_l = gb_l;
-        p_gb_u = gb_u;
+        __syncthreads();  // (also orders this tile's last reads of S.P before the update)
+        if (tid == 0) {
+            PendTile &P = S.P;
+            P.pend = 1;
+            P.have_base = have_base;
+            P.direct_l = direct_l;
+            P.direct_u = direct_u;
+            P.tile = tile;
+            P.tot_l = tot_l;
+            P.tot_u = tot_u;
+            P.gb_l = gb_l;
+            P.gb_u = gb_u;
+        }
     }
+    __syncthreads();
     flush();
 }
 
