@@ -1088,7 +1088,7 @@ __device__ __forceinline__ void state_to_fast(const LineState &st, FastLine &F) 
 // A fast line (fewer than 8 columns) with a handful of hits, expanded by its own thread:
 // every row's sorted position (qStart, then block order: bed.d:156-157), byte offset and
 // cumulative strand byte (bed.d:173) are computed directly.
-__device__ __forceinline__ void fast_expand_small(const TextArgs &A, const unsigned char *win, const FastLine &F, int lo,
+__device__ __noinline__ void fast_expand_small(const TextArgs &A, const unsigned char *win, const FastLine &F, int lo,
                                                   int ncand, char *dst) {
     const TableView &T = A.T;
     const uint32_t fixed = fast_fixed_len(F);
@@ -1125,7 +1125,7 @@ __device__ __forceinline__ void fast_expand_small(const TextArgs &A, const unsig
 // A fast line whose hits are already in output order (or exactly reversed, '-' chains):
 // one sequential pass, the strand byte flipping cumulatively as the reference's in-place
 // update does (bed.d:173).
-__device__ __forceinline__ void fast_expand_sorted(const TextArgs &A, const TileCtx &X, const FastLine &F, int tcid,
+__device__ __noinline__ void fast_expand_sorted(const TextArgs &A, const TileCtx &X, const FastLine &F, int tcid,
                                                    int lo, int ncand, bool reversed, char *dst) {
     const TableView &T = A.T;
     Thick th{0, 0, 0};
@@ -1200,6 +1200,20 @@ __device__ __forceinline__ void line_emit(const TextArgs &A, const TileCtx &X, T
             expand_line(A, tx_ey(), X.R, X.g0 + (p - X.s0), st.x, st.y, dst_l, 0, 1);
         }
     }
+}
+
+// Out-of-line copies for the rare call sites (dense tiles beyond the cached batches, multi-round
+// and direct emits): the hot loop keeps one inlined copy per cached batch and the kernel stays
+// small enough for the instruction cache.
+__device__ __noinline__ void line_emit_cold(const TextArgs &A, const TileCtx &X, TextSmem &S, const LineState st,
+                                            char *dst_l, char *dst_u, uint32_t o_l) {
+    line_emit(A, X, S, st, dst_l, dst_u, o_l);
+}
+__device__ __noinline__ int line_count_cold(const TextArgs &A, const TileCtx &X, uint32_t p, LineState &st,
+                                            uint32_t &len_l, uint32_t &len_u) {
+    LineHint H;
+    H.len0 = 0;
+    return line_count(A, X, p, st, len_l, len_u, false, H);
 }
 
 // Block-cooperative sum of the output lengths of the tile's heavy-fan-out lines (count work
@@ -1574,12 +1588,15 @@ __global__ void __launch_bounds__(TX_TPB, TX_MIN_CTAS) lift_bed_text_kernel(cons
             block_scan_multi<TX_NB>(v, ex, bt, S.scan64);
         }
         uint32_t run_l = 0, run_u = 0;
+        uint32_t len_l[TX_NB];  // lifted bytes of each cached line (the multi-round emit places lines by it)
 #pragma unroll
         for (int b = 0; b < TX_NB; b++) {
             ex[b] += ((unsigned long long)run_l << 32) | run_u;
             run_l += (uint32_t)(bt[b] >> 32);
             run_u += (uint32_t)bt[b];
+            len_l[b] = (uint32_t)(v[b] >> 32);
         }
+        const uint32_t cached_l = run_l, cached_u = run_u;  // output bytes of the cached batches
         // tiles with more than TX_NB*256 lines (very short lines): count the rest now, redo them when emitting
         if (nlines > TX_NB * TX_TPB) {
             int wbase = 0;
@@ -1592,7 +1609,7 @@ __global__ void __launch_bounds__(TX_TPB, TX_MIN_CTAS) lift_bed_text_kernel(cons
                 uint32_t ll = 0, lu = 0;
                 if (li < nlines) {
                     LineState t;
-                    const int nh = line_count(A, X, S.lstart[li - wbase], t, ll, lu, false, H);
+                    const int nh = line_count_cold(A, X, S.lstart[li - wbase], t, ll, lu);
                     if (nh == -2)
                         atomicMax((unsigned long long *)(A.sizes + 5),
                                   ~(unsigned long long)(X.g0 + ((t.pq & 0xFFFFu) - X.s0)));
@@ -1671,12 +1688,7 @@ __global__ void __launch_bounds__(TX_TPB, TX_MIN_CTAS) lift_bed_text_kernel(cons
             if (nlines <= TX_NB * TX_TPB) return;
             int wbase = 0;
             build_table(0);  // the expansions of a multi-round emit reuse the table's memory
-            uint32_t r_l = 0, r_u = 0;
-#pragma unroll
-            for (int b = 0; b < TX_NB; b++) {
-                r_l += (uint32_t)(bt[b] >> 32);
-                r_u += (uint32_t)bt[b];
-            }
+            uint32_t r_l = cached_l, r_u = cached_u;
             for (int lb = TX_NB * TX_TPB; lb < nlines; lb += TX_TPB) {
                 if (lb >= wbase + TX_LCAP) {
                     wbase += TX_LCAP;
@@ -1686,16 +1698,14 @@ __global__ void __launch_bounds__(TX_TPB, TX_MIN_CTAS) lift_bed_text_kernel(cons
                 uint32_t ll = 0, lu = 0;
                 LineState t;
                 t.meta = FL_NONE;
-                LineHint H2;
-                H2.len0 = 0;
-                if (li < nlines) line_count(A, X, S.lstart[li - wbase], t, ll, lu, false, H2);
+                if (li < nlines) line_count_cold(A, X, S.lstart[li - wbase], t, ll, lu);
                 unsigned long long t1;
                 const unsigned long long e1 =
                     block_exclusive_scan<unsigned long long, TX_NW>(((unsigned long long)ll << 32) | lu, S.scan64, &t1);
                 const uint32_t o_l = r_l + (uint32_t)(e1 >> 32), o_u = r_u + (uint32_t)e1;
                 r_l += (uint32_t)(t1 >> 32);
                 r_u += (uint32_t)t1;
-                line_emit(A, X, S, t, base_l ? base_l + o_l : nullptr, base_u ? base_u + o_u : nullptr, o_l);
+                line_emit_cold(A, X, S, t, base_l ? base_l + o_l : nullptr, base_u ? base_u + o_u : nullptr, o_l);
             }
         };
 
@@ -1715,17 +1725,15 @@ __global__ void __launch_bounds__(TX_TPB, TX_MIN_CTAS) lift_bed_text_kernel(cons
             // global memory directly AFTER the rounds (a round's copy-out may cover their bytes).
 #pragma unroll
             for (int b = 0; b < TX_NB; b++)  // unmatched stream first
-                line_emit(A, X, S, st[b], nullptr, base_u ? base_u + (uint32_t)ex[b] : nullptr, 0);
+                line_emit_cold(A, X, S, st[b], nullptr, base_u ? base_u + (uint32_t)ex[b] : nullptr, 0);
             {
                 constexpr uint32_t W = TX_OUT_STAGE - TX_ROUND_SLACK;
-                uint32_t cached_end = 0;
-#pragma unroll
-                for (int b = 0; b < TX_NB; b++) cached_end += (uint32_t)(bt[b] >> 32);
+                const uint32_t cached_end = cached_l;
                 for (uint32_t r0 = 0; r0 < cached_end; r0 += W) {
                     bool any = false;
 #pragma unroll
                     for (int b = 0; b < TX_NB; b++) {
-                        const uint32_t o_l = (uint32_t)(ex[b] >> 32), len = (uint32_t)(v[b] >> 32);
+                        const uint32_t o_l = (uint32_t)(ex[b] >> 32), len = len_l[b];
                         any = any || (len > 0 && len <= TX_ROUND_SLACK && o_l >= r0 && o_l - r0 < W);
                     }
                     if (tid == 0) {
@@ -1736,9 +1744,9 @@ __global__ void __launch_bounds__(TX_TPB, TX_MIN_CTAS) lift_bed_text_kernel(cons
                     if (!__syncthreads_or(any)) continue;
 #pragma unroll
                     for (int b = 0; b < TX_NB; b++) {
-                        const uint32_t o_l = (uint32_t)(ex[b] >> 32), len = (uint32_t)(v[b] >> 32);
+                        const uint32_t o_l = (uint32_t)(ex[b] >> 32), len = len_l[b];
                         if (len > 0 && len <= TX_ROUND_SLACK && o_l >= r0 && o_l - r0 < W) {
-                            line_emit(A, X, S, st[b], stage_l + (o_l - r0), nullptr, o_l - r0);
+                            line_emit_cold(A, X, S, st[b], stage_l + (o_l - r0), nullptr, o_l - r0);
                             atomicMin(&S.rlo, o_l);
                             atomicMax(&S.rhi, o_l + len);
                         }
@@ -1758,8 +1766,8 @@ __global__ void __launch_bounds__(TX_TPB, TX_MIN_CTAS) lift_bed_text_kernel(cons
                 if (glob_l) {
 #pragma unroll
                     for (int b = 0; b < TX_NB; b++) {
-                        const uint32_t o_l = (uint32_t)(ex[b] >> 32), len = (uint32_t)(v[b] >> 32);
-                        if (len > TX_ROUND_SLACK) line_emit(A, X, S, st[b], glob_l + o_l, nullptr, o_l);
+                        const uint32_t o_l = (uint32_t)(ex[b] >> 32), len = len_l[b];
+                        if (len > TX_ROUND_SLACK) line_emit_cold(A, X, S, st[b], glob_l + o_l, nullptr, o_l);
                     }
                 }
                 emit_uncached(glob_l);
