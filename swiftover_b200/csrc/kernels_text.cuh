@@ -305,11 +305,22 @@ __device__ __forceinline__ char *put_i32(char *d, int v) {
     unsigned u = v < 0 ? 0u - (unsigned)v : (unsigned)v;
     char *e = d + n;
     char *p = e;
-    do {
-        const unsigned q = u / 10u;
-        *--p = (char)('0' + (u - q * 10u));
+    while (u >= 100u) {  // two digits per step
+        const unsigned q = u / 100u, r = u - q * 100u;
+        const unsigned t = (r * 103u) >> 10;  // r / 10 for r < 100
+        p -= 2;
+        p[0] = (char)('0' + t);
+        p[1] = (char)('0' + (r - t * 10u));
         u = q;
-    } while (u);
+    }
+    if (u >= 10u) {
+        const unsigned t = (u * 103u) >> 10;
+        p -= 2;
+        p[0] = (char)('0' + t);
+        p[1] = (char)('0' + (u - t * 10u));
+    } else {
+        *--p = (char)('0' + u);
+    }
     if (v < 0) *--p = '-';
     return e;
 }

@@ -83,7 +83,7 @@ constexpr int N_SLOTS = 8;  // chunks in flight per device (H2D / kernel / D2H o
 struct Device {
     int ordinal = 0;
     int sms = 148;
-    cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
+    cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr, s_d2h2 = nullptr;  // two D2H streams: alternate chunks
     // chain table replica
     DevBuf blk, tkey, pkey, toff, cmeta, ey, thash, tchars, tnoff, qoff, qchars;
     TableView T{};
@@ -124,6 +124,7 @@ struct swo_ctx {
     // read pinned input from the kernel over PCIe instead of staging it with H2D copies: as fast as the
     // copy when nothing else uses the link, but slower than staging once D2H copies of the output overlap
     bool zero_copy_input = false;
+    int d2h_streams = 1;  // 2: alternate the chunks' D2H copies over two streams
     // text tile size: TX_TILE, or 8192 / 4096 for inputs with large fan-out (a tile's lifted text should fit
     // its 20 KiB stage); 0 = choose per chunk from the previous chunk's output/input ratio
     uint32_t tile_bytes = TX_TILE;
@@ -463,18 +464,21 @@ int run_shard(swo_ctx *c, Device &d, const char *in, size_t a, size_t b, PinBuf 
         // grow the host arenas if needed (keeps what is already there)
         if (out_l + sz[0] > pl->cap) {
             CK(c, cudaStreamSynchronize(d.s_d2h));
+            CK(c, cudaStreamSynchronize(d.s_d2h2));
             CK(c, pl->reserve(out_l + sz[0], true, out_l));
         }
         if (out_u + sz[1] > pu->cap) {
             CK(c, cudaStreamSynchronize(d.s_d2h));
+            CK(c, cudaStreamSynchronize(d.s_d2h2));
             CK(c, pu->reserve(out_u + sz[1], true, out_u));
         }
-        CK(c, cudaStreamWaitEvent(d.s_d2h, d.ev_comp[s], 0));
-        if (trace) mark(&tr[k].o0, d.s_d2h);
-        if (sz[0]) CK(c, cudaMemcpyAsync(pl->as<char>() + out_l, d.t_out[s].p, sz[0], cudaMemcpyDeviceToHost, d.s_d2h));
-        if (sz[1]) CK(c, cudaMemcpyAsync(pu->as<char>() + out_u, d.t_unm[s].p, sz[1], cudaMemcpyDeviceToHost, d.s_d2h));
-        if (trace) mark(&tr[k].o1, d.s_d2h);
-        CK(c, cudaEventRecord(d.ev_d2h[s], d.s_d2h));
+        cudaStream_t sd = (c->d2h_streams > 1 && (k & 1)) ? d.s_d2h2 : d.s_d2h;
+        CK(c, cudaStreamWaitEvent(sd, d.ev_comp[s], 0));
+        if (trace) mark(&tr[k].o0, sd);
+        if (sz[0]) CK(c, cudaMemcpyAsync(pl->as<char>() + out_l, d.t_out[s].p, sz[0], cudaMemcpyDeviceToHost, sd));
+        if (sz[1]) CK(c, cudaMemcpyAsync(pu->as<char>() + out_u, d.t_unm[s].p, sz[1], cudaMemcpyDeviceToHost, sd));
+        if (trace) mark(&tr[k].o1, sd);
+        CK(c, cudaEventRecord(d.ev_d2h[s], sd));
         out_l += sz[0];
         out_u += sz[1];
         res.rec += sz[2];
@@ -482,6 +486,7 @@ int run_shard(swo_ctx *c, Device &d, const char *in, size_t a, size_t b, PinBuf 
         res.nunm += sz[4];
     }
     CK(c, cudaStreamSynchronize(d.s_d2h));
+    CK(c, cudaStreamSynchronize(d.s_d2h2));
     if (trace && nch && !zc_in) {
         auto ms = [&](cudaEvent_t e) {
             float f = 0;
@@ -528,7 +533,8 @@ int swo_create(swo_ctx **out, const int *devices, int ndev) {
         d.sms = p.multiProcessorCount;
         if (cudaStreamCreateWithFlags(&d.s_h2d, cudaStreamNonBlocking) != cudaSuccess ||
             cudaStreamCreateWithFlags(&d.s_comp, cudaStreamNonBlocking) != cudaSuccess ||
-            cudaStreamCreateWithFlags(&d.s_d2h, cudaStreamNonBlocking) != cudaSuccess)
+            cudaStreamCreateWithFlags(&d.s_d2h, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&d.s_d2h2, cudaStreamNonBlocking) != cudaSuccess)
             return SWO_E_CUDA;
         for (int s = 0; s < N_SLOTS; s++) {
             cudaEventCreateWithFlags(&d.ev_h2d[s], cudaEventDisableTiming);
@@ -570,6 +576,7 @@ void swo_destroy(swo_ctx *c) {
         cudaStreamDestroy(d.s_h2d);
         cudaStreamDestroy(d.s_comp);
         cudaStreamDestroy(d.s_d2h);
+        cudaStreamDestroy(d.s_d2h2);
     }
     for (PinBuf *b : {&c->r_lifted, &c->r_unm, &c->r_off, &c->r_rows, &c->r_thick}) b->release();
     delete c;
@@ -603,6 +610,10 @@ int swo_set_option(swo_ctx *c, const char *key, int64_t value) {
         if (value != 4096 && value != 8192 && value != 16384) return fail(c, SWO_E_ARG, "tile_bytes must be 0 (auto), 4096, 8192 or 16384");
         c->tile_bytes = (uint32_t)value;
         c->tile_auto = false;
+        return SWO_OK;
+    }
+    if (!strcmp(key, "d2h_streams")) {
+        c->d2h_streams = value >= 2 ? 2 : 1;
         return SWO_OK;
     }
     if (!strcmp(key, "zero_copy_input")) {
@@ -833,6 +844,7 @@ int swo_lift_bed_text(swo_ctx *c, const char *in, size_t in_len, swo_text_out *o
                 swo_ctx local;  // private error sink; run_shard only touches err/launches/chunk_bytes
                 local.chunk_bytes = c->chunk_bytes;
                 local.zero_copy_input = c->zero_copy_input;
+                local.d2h_streams = c->d2h_streams;
                 local.tile_bytes = c->tile_bytes;
                 local.tile_auto = c->tile_auto;
                 Device &d = c->dev[k];

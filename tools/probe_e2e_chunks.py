@@ -16,6 +16,8 @@ host.copy_(text); torch.cuda.synchronize()
 del iv, text
 torch.cuda.empty_cache()
 out = {}
+if os.environ.get("D2H"):
+    cf.set_option("d2h_streams", int(os.environ["D2H"]))
 for mib in [int(x) for x in os.environ.get("CHUNKS", "4,8,16,32,64").split(",")]:
     cf.set_option("chunk_bytes", mib << 20)
     for _ in range(2): cf.lift_bed_text_ptr(host.data_ptr(), host.numel())
