@@ -26,7 +26,8 @@ constexpr int LI_IPT = 4;
 constexpr int LI_TILE = LI_TPB * LI_IPT;
 constexpr int LI_NW = LI_TPB / 32;
 constexpr int LI_WL_CAP = 256;      // multi-hit queries queued per tile
-constexpr int LI_HEAVY_MIN = 512;   // candidates >= this: whole block expands
+constexpr int LI_HEAVY_MIN = 128;   // candidates above this: the whole block expands the query
+constexpr int LI_XSCR = 1024;       // shared-memory sort scratch (= LI_NW warp regions of LI_HEAVY_MIN)
 
 struct LiftArgs {
     TableView T;
@@ -93,7 +94,94 @@ __device__ __forceinline__ void expand_query(const LiftArgs &A, const int2 *ey, 
     }
 }
 
-__global__ void __launch_bounds__(LI_TPB, 4) lift_intervals_kernel(const LiftArgs A) {
+// Cooperative, sort-based form for the queued multi-hit queries (one warp, or the block for heavy
+// fan-out): one 64-bit key (qStart, candidate, invert) per candidate in shared memory, a bitonic
+// sort only if the keys are not already ascending, then every sorted position writes its row;
+// the cumulative strand byte comes from a running count of inverted rows (bed.d:173).
+template <bool BLOCK>
+__device__ __noinline__ void expand_query_coop(const LiftArgs &A, const int2 *ey, uint32_t q, int lo, int ncand,
+                                               uint64_t rowbase, unsigned long long *scr, uint32_t *scan_scr, int first,
+                                               int stride) {
+    const TableView &T = A.T;
+    const int start = __ldg(A.start + q), end = __ldg(A.end + q);
+    const unsigned char orig = A.strand ? __ldg(A.strand + q) : 0;
+    Thick th{0, 0, 0};
+    if (A.thick_s) th = lift_thick(T, ey, __ldg(A.tcid + q), __ldg(A.thick_s + q), __ldg(A.thick_e + q));
+    int P = 32;
+    while (P < ncand) P <<= 1;
+    for (int c = first; c < P; c += stride) {
+        unsigned long long key = ~0ull;  // padding and non-hits sort last
+        if (c < ncand) {
+            const Block b = load_block(T, lo + c);
+            if (T.disjoint || block_hits(b, start)) {
+                const RowCore r = make_row(b, start, end);
+                key = ((unsigned long long)((uint32_t)r.key ^ 0x80000000u) << 32) | ((uint32_t)c << 1) | (r.inv < 0 ? 1u : 0u);
+            }
+        }
+        scr[c] = key;
+    }
+    if (BLOCK) __syncthreads();
+    else __syncwarp();
+    bool mine = true;
+    for (int c = first; c < P; c += stride)
+        if (c > 0 && scr[c - 1] > scr[c]) mine = false;
+    const bool sorted = BLOCK ? (__syncthreads_and(mine) != 0) : (__all_sync(FULL, mine) != 0);
+    if (!sorted) {
+        for (int k = 2; k <= P; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = first; i < P; i += stride) {
+                    const int x = i ^ j;
+                    if (x > i) {
+                        const unsigned long long va = scr[i], vb = scr[x];
+                        if ((va > vb) == ((i & k) == 0)) {
+                            scr[i] = vb;
+                            scr[x] = va;
+                        }
+                    }
+                }
+                if (BLOCK) __syncthreads();
+                else __syncwarp();
+            }
+        }
+    }
+    const int inv_first = (scr[0] & 1ull) ? -1 : 1;  // position 0 is a hit: the query has >= 2 hits
+    uint32_t carry = 0;                              // inverted rows at earlier positions
+    for (int base = 0; base < P; base += stride) {
+        const int j = base + first;
+        const unsigned long long e = j < P ? scr[j] : ~0ull;
+        const bool hit = e != ~0ull;
+        const uint32_t neg = hit ? (uint32_t)(e & 1ull) : 0u;
+        uint32_t ex, tot;
+        if (BLOCK) {
+            ex = block_exclusive_scan<uint32_t, LI_NW>(neg, scan_scr, &tot);
+        } else {
+            const uint32_t inc = warp_inclusive_scan(neg);
+            ex = inc - neg;
+            tot = __shfl_sync(FULL, inc, 31);
+        }
+        const uint64_t pos = rowbase + (uint64_t)j;
+        if (hit && pos < A.rows_cap) {
+            const int c = (int)(((uint32_t)e) >> 1);
+            const RowCore r = make_row(load_block(T, lo + c), start, end);
+            const unsigned char sb = A.strand ? strand_at_rank(orig, inv_first, j, (int)(carry + ex + neg)) : 0;
+            swo_row row;
+            row.qcid_strand = r.qcid | ((int)sb << 16);
+            row.start = r.s;
+            row.end = r.e;
+            row.src = q;
+            A.rows[pos] = row;
+            if (A.thick_s) {
+                swo_thick t;
+                thick_clamp(th, r.s, r.e, t.thick_start, t.thick_end);
+                A.thick[pos] = t;
+            }
+        }
+        carry += tot;
+    }
+    if (BLOCK) __syncthreads();  // scratch is reused by the next heavy query
+}
+
+__global__ void __launch_bounds__(LI_TPB, 4) lift_intervals_kernel(const __grid_constant__ LiftArgs A) {
     __shared__ int s_tile;
     __shared__ uint32_t s_scan[LI_NW + 1];
     __shared__ unsigned long long s_lb_part[LI_NW];
@@ -104,6 +192,7 @@ __global__ void __launch_bounds__(LI_TPB, 4) lift_intervals_kernel(const LiftArg
     __shared__ int s_wl_cnt[LI_WL_CAP];
     __shared__ uint32_t s_wl_off[LI_WL_CAP];
     __shared__ int2 s_ey[ChainTable::EY_CAP];  // upper search levels (Eytzinger order)
+    __shared__ unsigned long long s_xscr[LI_XSCR];
 
     const int tid = threadIdx.x;
     const TableView &T = A.T;
@@ -228,12 +317,18 @@ __global__ void __launch_bounds__(LI_TPB, 4) lift_intervals_kernel(const LiftArg
         const int nwl = min(s_wl_n, LI_WL_CAP);
         // light and medium fan-out: one warp per query
         for (int e = warp_id(); e < nwl; e += LI_NW) {
-            if (s_wl_cnt[e] < LI_HEAVY_MIN)
-                expand_query(A, ey, s_wl_q[e], s_wl_lo[e], s_wl_cnt[e], gbase + s_wl_off[e], lane_id(), 32);
+            if (s_wl_cnt[e] <= LI_HEAVY_MIN)
+                expand_query_coop<false>(A, ey, s_wl_q[e], s_wl_lo[e], s_wl_cnt[e], gbase + s_wl_off[e],
+                                         s_xscr + warp_id() * LI_HEAVY_MIN, nullptr, lane_id(), 32);
         }
+        if (nwl > 0) __syncthreads();
         // heavy fan-out: the whole block per query
         for (int e = 0; e < nwl; e++) {
-            if (s_wl_cnt[e] >= LI_HEAVY_MIN)
+            if (s_wl_cnt[e] <= LI_HEAVY_MIN) continue;
+            if (s_wl_cnt[e] <= LI_XSCR)
+                expand_query_coop<true>(A, ey, s_wl_q[e], s_wl_lo[e], s_wl_cnt[e], gbase + s_wl_off[e], s_xscr, s_scan, tid,
+                                        LI_TPB);
+            else
                 expand_query(A, ey, s_wl_q[e], s_wl_lo[e], s_wl_cnt[e], gbase + s_wl_off[e], tid, LI_TPB);
         }
     }

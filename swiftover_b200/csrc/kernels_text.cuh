@@ -1096,14 +1096,21 @@ __device__ __forceinline__ void state_to_fast(const LineState &st, FastLine &F) 
     F.v6 = F.v7 = 0;
 }
 
-// A fast line (fewer than 8 columns) with a handful of hits, expanded by its own thread:
+// A fast line with a handful of hits in no particular order, expanded by its own thread:
 // every row's sorted position (qStart, then block order: bed.d:156-157), byte offset and
 // cumulative strand byte (bed.d:173) are computed directly.
-__device__ __noinline__ void fast_expand_small(const TextArgs &A, const unsigned char *win, const FastLine &F, int lo,
-                                                  int ncand, char *dst) {
+__device__ __noinline__ void fast_expand_small(const TextArgs &A, const unsigned char *win, const FastLine &F, int tcid,
+                                                  int lo, int ncand, char *dst) {
     const TableView &T = A.T;
     const uint32_t fixed = fast_fixed_len(F);
-    const Thick th{0, 0, 0};
+    Thick th{0, 0, 0};
+    if (F.numf >= 8) {  // thickStart / thickEnd are re-read from the line (not kept between the phases)
+        const uint32_t *W = reinterpret_cast<const uint32_t *>(win);
+        uint32_t v6 = 0, v7 = 0, n6 = 0, n7 = 0, term;
+        parse_uint_swar(W, F.a6, v6, n6, term);
+        parse_uint_swar(W, F.a6 + n6 + 1, v7, n7, term);
+        th = lift_thick(T, tx_ey(), tcid, (int)v6, (int)v7);
+    }
     for (int c = 0; c < ncand; c++) {
         const Block bj = load_block(T, lo + c);
         if (!T.disjoint && !block_hits(bj, F.start)) continue;
@@ -1194,10 +1201,10 @@ __device__ __forceinline__ void line_emit(const TextArgs &A, const TileCtx &X, T
         FastLine F;
         state_to_fast(st, F);
         fast_expand_sorted(A, X, F, (int)(st.meta >> 17), st.x, st.y, (st.meta >> 16) & 1u, dst_l);
-    } else if (kind == FL_FAST && st.y <= TX_SMALL_FANOUT && ((st.meta >> 4) & 7u) < 5u) {
+    } else if (kind == FL_FAST && st.y <= TX_SMALL_FANOUT && (st.meta >> 17) != 0x7FFFu) {
         FastLine F;
         state_to_fast(st, F);
-        fast_expand_small(A, tx_win(), F, st.x, st.y, dst_l);
+        fast_expand_small(A, tx_win(), F, (int)(st.meta >> 17), st.x, st.y, dst_l);
     } else if (nhc == 1) {
         slow_emit(A, tx_ey(), X.R, X.g0 + (p - X.s0), st.x, 1, dst_l);
     } else {
