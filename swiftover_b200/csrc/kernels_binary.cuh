@@ -293,7 +293,8 @@ __global__ void __launch_bounds__(LI_TPB, 4) lift_intervals_kernel(const __grid_
                 if (run64 < A.rows_cap) {
                     st_stream_v4(A.rows + run64, make_int4(r_meta[k], r_s[k], r_e[k], (int)q));
                     if (A.thick_s) {
-                        const Thick th = lift_thick(T, ey, tc[k], __ldg(A.thick_s + q), __ldg(A.thick_e + q));
+                        const Thick th = lift_thick_from(T, ey, tc[k], __ldg(A.thick_s + q), __ldg(A.thick_e + q), st[k],
+                                                         cd[k].lo, load_cmeta(T, tc[k]).y);
                         swo_thick t;
                         thick_clamp(th, r_s[k], r_e[k], t.thick_start, t.thick_end);
                         A.thick[run64] = t;

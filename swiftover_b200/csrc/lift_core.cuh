@@ -284,6 +284,33 @@ SWO_HD Thick lift_thick(const TableView &T, const int2 *__restrict__ ey, int tci
     k.te = a < b ? b : a;
     return k;
 }
+// Point query c >= start on the contig of an interval query whose lower bound was lo_hint: the
+// lower bound of c lies at or after it (thickStart / thickEnd normally fall inside the interval),
+// so a short gallop replaces a full search.
+SWO_HD int point_hit_from(const TableView &T, int contig_end, int lo_hint, int c) {
+    int j = gallop_gt(T.pmaxKey, lo_hint, contig_end, c);
+    for (; j < contig_end; j++) {
+        if (SWO_LDG(T.tStartKey + j) > c) return -1;
+        if (T.disjoint || SWO_LDG(&T.blk[j].tEnd) > c) return j;
+    }
+    return -1;
+}
+// lift_thick for a record whose interval [start, ..) has candidates starting at block lo_hint
+SWO_HD Thick lift_thick_from(const TableView &T, const int2 *__restrict__ ey, int tcid, int ts, int te, int start,
+                             int lo_hint, int contig_end) {
+    Thick k{0, ts, te};
+    if (ts == te) return k;
+    const int j0 = ts >= start ? point_hit_from(T, contig_end, lo_hint, ts) : point_hit(T, ey, tcid, ts);
+    if (j0 < 0) return k;  // short-circuit: thickEnd is not looked up
+    const int j1 = te >= start ? point_hit_from(T, contig_end, lo_hint, te) : point_hit(T, ey, tcid, te);
+    if (j1 < 0) return k;
+    const int a = point_coord(load_block(T, j0), ts);
+    const int b = point_coord(load_block(T, j1), te);
+    k.has = 1;
+    k.ts = a < b ? a : b;  // orderStartEnd  bed.d:146
+    k.te = a < b ? b : a;
+    return k;
+}
 // columns 7 and 8 of one output row (bed.d:175-196)
 SWO_HD void thick_clamp(const Thick &k, int s, int e, int &c7, int &c8) {
     if (!k.has || k.ts >= e || k.te <= s) {
