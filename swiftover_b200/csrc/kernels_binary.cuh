@@ -286,6 +286,7 @@ __global__ void __launch_bounds__(LI_TPB, 4) lift_intervals_kernel(const __grid_
 
         // rows
         uint64_t run64 = gbase + excl;
+        uint32_t pending = 0;
 #pragma unroll
         for (int k = 0; k < LI_IPT; k++) {
             const uint32_t q = q0 + k;
@@ -301,19 +302,30 @@ __global__ void __launch_bounds__(LI_TPB, 4) lift_intervals_kernel(const __grid_
                     }
                 }
             } else if (nh[k] >= 2) {
-                const int slot = atomicAdd(&s_wl_n, 1);
-                if (slot < LI_WL_CAP) {
-                    s_wl_q[slot] = q;
-                    s_wl_lo[slot] = cd[k].lo;
-                    s_wl_cnt[slot] = cd[k].hi - cd[k].lo;
-                    s_wl_off[slot] = (uint32_t)(run64 - gbase);
-                } else {
-                    // work list full: expand serially in this thread
-                    expand_query(A, ey, q, cd[k].lo, cd[k].hi - cd[k].lo, run64, 0, 1);
-                }
+                pending |= 1u << k;  // queued below, possibly over several rounds of the work list
             }
             run64 += (uint64_t)nh[k];
         }
+        // multi-hit queries: rounds of (fill the work list, expand it cooperatively) until none is
+        // pending — batches where most queries have many hits need more than one round
+        for (;;) {
+            {
+                uint64_t rb = gbase + excl;
+#pragma unroll
+                for (int k = 0; k < LI_IPT; k++) {
+                    if ((pending >> k) & 1u) {
+                        const int slot = atomicAdd(&s_wl_n, 1);
+                        if (slot < LI_WL_CAP) {
+                            s_wl_q[slot] = q0 + k;
+                            s_wl_lo[slot] = cd[k].lo;
+                            s_wl_cnt[slot] = cd[k].hi - cd[k].lo;
+                            s_wl_off[slot] = (uint32_t)(rb - gbase);
+                            pending &= ~(1u << k);
+                        }
+                    }
+                    rb += (uint64_t)nh[k];
+                }
+            }
         __syncthreads();
         const int nwl = min(s_wl_n, LI_WL_CAP);
         // light and medium fan-out: one warp per query
@@ -331,6 +343,10 @@ __global__ void __launch_bounds__(LI_TPB, 4) lift_intervals_kernel(const __grid_
                                         LI_TPB);
             else
                 expand_query(A, ey, s_wl_q[e], s_wl_lo[e], s_wl_cnt[e], gbase + s_wl_off[e], tid, LI_TPB);
+        }
+            if (!__syncthreads_or(pending != 0)) break;
+            if (tid == 0) s_wl_n = 0;
+            __syncthreads();
         }
     }
 }
