@@ -232,6 +232,7 @@ int zero_async(swo_ctx *c, void *a, size_t abytes, void *b, size_t bbytes, cudaS
     const size_t na = (abytes + 3) / 4, nb = (bbytes + 3) / 4;
     const int grid = (int)std::min<size_t>(std::max<size_t>((std::max(na, nb) + 255) / 256, 1), 296);
     zero_words_kernel<<<grid, 256, 0, st>>>((uint32_t *)a, na, (uint32_t *)b, nb);
+    c->launches++;
     CK(c, cudaGetLastError());
     return SWO_OK;
 }
@@ -403,6 +404,7 @@ int run_shard(swo_ctx *c, Device &d, const char *in, size_t a, size_t b, PinBuf 
     };
     auto sizes_to_host = [&](int s) -> int {
         copy_sizes_kernel<<<1, 32, 0, d.s_comp>>>(d.t_sizes[s].as<uint64_t>(), hs + 6 * s);
+        c->launches++;
         CK(c, cudaGetLastError());
         CK(c, cudaEventRecord(d.ev_comp[s], d.s_comp));
         return SWO_OK;
