@@ -191,6 +191,13 @@ int swo_lift_vcf_points(swo_ctx *ctx, size_t n, const int32_t *tcid, const int32
                         size_t ref_bytes_len, int32_t *out_qcid, int32_t *out_pos, uint8_t *flags,
                         int32_t *out_reflen, char *out_ref);
 
+/* Same kernel on device-resident arrays (kernel-only measurement, or callers that already hold the
+ * records on the GPU): every pointer is a device pointer on devices[0]; asynchronous on `stream`. */
+int swo_lift_vcf_points_dev(swo_ctx *ctx, size_t n, const int32_t *d_tcid, const int32_t *d_pos,
+                            const int32_t *d_reflen, const uint64_t *d_ref_off, const char *d_ref_bytes,
+                            int32_t *d_out_qcid, int32_t *d_out_pos, uint8_t *d_flags, int32_t *d_out_reflen,
+                            char *d_out_ref, void *stream);
+
 /* liftVCF, text -> text (vcf.d:29-176) for an uncompressed text VCF held in memory.  The
  * header rewrite (vcf.d:59-108) and the column split / join run on the host; the per-record
  * work of vcf.d:115-169 (liftDirectly, REF fetch and compare, refchg) runs in

@@ -73,6 +73,7 @@ def lib():
         "swo_lift_bed_text": (i32, [vp, vp, sz, C.POINTER(SwoTextOut)]),
         "swo_lift_bed_text_dev": (i32, [vp, vp, sz, vp, sz, vp, sz, vp, vp]),
         "swo_load_genome_2bit": (i32, [vp, vp, sz, vp, vp, i32]),
+        "swo_lift_vcf_points_dev": (i32, [vp, sz, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "swo_load_genome_fasta": (i32, [vp, C.c_char_p]),
         "swo_genome_has_seq": (i32, [vp, C.c_char_p]),
         "swo_genome_seq_len": (i64, [vp, C.c_char_p]),

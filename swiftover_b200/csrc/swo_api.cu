@@ -1005,6 +1005,47 @@ int swo_lift_vcf_points(swo_ctx *c, size_t n, const int32_t *tcid, const int32_t
     return SWO_OK;
 }
 
+int swo_lift_vcf_points_dev(swo_ctx *c, size_t n, const int32_t *d_tcid, const int32_t *d_pos, const int32_t *d_rl,
+                            const uint64_t *d_ro, const char *d_ref, int32_t *d_oq, int32_t *d_op, uint8_t *d_fl,
+                            int32_t *d_orl, char *d_oref, void *stream) {
+    if (!c || (n && (!d_tcid || !d_pos || !d_rl || !d_ro || !d_oq || !d_op || !d_fl || !d_orl))) return SWO_E_ARG;
+    if (c->dev.empty()) return fail(c, SWO_E_CUDA, "inspection-only context: no CUDA device, and there is no CPU fallback");
+    if (!c->have_chain) return fail(c, SWO_E_STATE, "no chain loaded");
+    Device &d = c->dev[0];
+    if (!d.g_n) return fail(c, SWO_E_STATE, "no genome loaded");
+    if (n >= 0xFFFFFFFFull) return fail(c, SWO_E_ARG, "n must be < 2^32-1 per call");
+    if (!n) return SWO_OK;
+    CK(c, cudaSetDevice(d.ordinal));
+    VcfArgs A;
+    A.T = d.T;
+    A.packed = d.g_packed.as<uint8_t>();
+    A.g_off = d.g_off.as<int64_t>();
+    A.g_len = d.g_len.as<int64_t>();
+    A.g_n = d.g_n;
+    A.lower = d.g_has_lower ? d.g_lower.as<uint8_t>() : nullptr;
+    A.exc_n = d.g_exc_n;
+    A.exc_chunk = d.g_exc_n ? d.g_chunk.as<uint8_t>() : nullptr;
+    A.exc_start = d.g_estart.as<int64_t>();
+    A.exc_len = d.g_elen.as<int32_t>();
+    A.exc_byte = d.g_ebyte.as<uint8_t>();
+    A.n = (uint32_t)n;
+    A.tcid = d_tcid;
+    A.pos = d_pos;
+    A.reflen = d_rl;
+    A.ref_off = d_ro;
+    A.ref = d_ref;
+    A.out_qcid = d_oq;
+    A.out_pos = d_op;
+    A.flags = d_fl;
+    A.out_reflen = d_orl;
+    A.out_ref = d_oref;
+    const int grid = (int)std::min<size_t>((n + 255) / 256, (size_t)d.sms * 8);
+    lift_vcf_points_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A);
+    c->launches++;
+    CK(c, cudaGetLastError());
+    return SWO_OK;
+}
+
 // ---- liftVCF on text ---------------------------------------------------------------------
 namespace {
 // vcf.d:200-215

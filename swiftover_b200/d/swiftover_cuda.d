@@ -67,6 +67,9 @@ int swo_load_genome_2bit(swo_ctx* ctx, const(ubyte)* packed, size_t packed_bytes
 int swo_lift_vcf_points(swo_ctx* ctx, size_t n, const(int)* tcid, const(int)* pos, const(int)* reflen,
                         const(ulong)* ref_off, const(char)* ref_bytes, size_t ref_bytes_len, int* out_qcid,
                         int* out_pos, ubyte* flags, int* out_reflen, char* out_ref);
+int swo_lift_vcf_points_dev(swo_ctx* ctx, size_t n, const(int)* d_tcid, const(int)* d_pos, const(int)* d_reflen,
+                            const(ulong)* d_ref_off, const(char)* d_ref_bytes, int* d_out_qcid, int* d_out_pos,
+                            ubyte* d_flags, int* d_out_reflen, char* d_out_ref, void* stream);
 int swo_load_genome_fasta(swo_ctx* ctx, const(char)* path);
 int swo_genome_has_seq(const(swo_ctx)* ctx, const(char)* name);
 long swo_genome_seq_len(const(swo_ctx)* ctx, const(char)* name);

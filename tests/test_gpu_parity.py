@@ -344,6 +344,22 @@ def test_vcf_points(oracle):
     for i in range(n):
         a, m = int(ro[i]), int(ref["reflen"][i])
         assert bytes(got["ref"][a:a + m]) == bytes(ref["ref"][a:a + m])
+    # device-resident entry point: same kernel, same answers
+    import torch
+    from swiftover_b200 import _lib as L
+    dt = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    d_tc, d_pos, d_rl, d_ro, d_ref = dt(tc), dt(pos), dt(rl), dt(ro.astype(np.int64)), dt(refb)
+    d_oq = torch.empty(n, dtype=torch.int32, device="cuda")
+    d_op, d_orl = torch.empty_like(d_oq), torch.empty_like(d_oq)
+    d_fl = torch.empty(n, dtype=torch.uint8, device="cuda")
+    d_oref = torch.zeros_like(d_ref)
+    rc = L.lib().swo_lift_vcf_points_dev(cf.handle, n, d_tc.data_ptr(), d_pos.data_ptr(), d_rl.data_ptr(), d_ro.data_ptr(),
+                                         d_ref.data_ptr(), d_oq.data_ptr(), d_op.data_ptr(), d_fl.data_ptr(),
+                                         d_orl.data_ptr(), d_oref.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(d_oq.cpu().numpy(), ref["qcid"]) and np.array_equal(d_op.cpu().numpy(), ref["pos"])
+    assert np.array_equal(d_fl.cpu().numpy(), ref["flags"]) and np.array_equal(d_orl.cpu().numpy(), ref["reflen"])
     cf.close()
 
 

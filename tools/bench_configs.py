@@ -65,6 +65,21 @@ for _ in range(3):
 out["cfg4_vcf_points_host_arrays"] = dict(records=n, ms=min(ts) * 1e3, M_records_per_s=n / min(ts) / 1e6,
                                           matched=int((r["flags"] & 1).sum()), refchg=int((r["flags"] >> 1).sum()),
                                           note="pageable numpy arrays in/out: dominated by host copies")
+# kernel only: the same records resident on the device
+from swiftover_b200 import _lib as L
+dt = lambda a: torch.from_numpy(a).to(dev)
+d_tc, d_pos, d_rl, d_ro, d_ref = dt(tc), dt(pos), dt(rl), dt(ro.astype(np.int64)), dt(refb)
+d_oq = torch.empty(n, dtype=torch.int32, device=dev); d_op = torch.empty_like(d_oq); d_orl = torch.empty_like(d_oq)
+d_fl = torch.empty(n, dtype=torch.uint8, device=dev); d_oref = torch.empty_like(d_ref)
+def vcf_dev():
+    rc = L.lib().swo_lift_vcf_points_dev(cf.handle, n, d_tc.data_ptr(), d_pos.data_ptr(), d_rl.data_ptr(), d_ro.data_ptr(),
+                                         d_ref.data_ptr(), d_oq.data_ptr(), d_op.data_ptr(), d_fl.data_ptr(),
+                                         d_orl.data_ptr(), d_oref.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+    assert rc == 0
+ms = time_dev(vcf_dev)
+assert np.array_equal(d_fl.cpu().numpy(), r["flags"]) and np.array_equal(d_op.cpu().numpy(), r["pos"])
+out["cfg4_vcf_points_kernel_only"] = dict(records=n, ms=ms, G_records_per_s=n / ms / 1e6,
+                                          GBs=(n * (20 + 13) + 2 * len(refb) + n * 32) / ms / 1e6)
 cf.close()
 # ---- cfg5 ------------------------------------------------------------------------------
 from test_gpu_fullsize import fragmented_chain
