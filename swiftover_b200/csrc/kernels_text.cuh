@@ -41,9 +41,6 @@
 
 namespace swo {
 
-#ifndef TX_USE_BRACKET
-#define TX_USE_BRACKET 0  // per-tile block bracket in shared memory (sorted input); off: its serial set-up costs more than it saves
-#endif
 #ifndef TX_MIN_CTAS
 #define TX_MIN_CTAS 2  // resident CTAs per SM the register budget is sized for
 #endif
@@ -67,7 +64,6 @@ constexpr int TX_OUT_STAGE = 20480;          // lifted bytes staged per tile
 constexpr int TX_ROUND_SLACK = 4096;         // multi-round emit: a line's rows may run this far past its round's window
 constexpr int TX_UNM_STAGE = TX_TILE + TX_LOOK;  // unmatched bytes staged per tile: a tile's unmatched text never exceeds its input
 constexpr int TX_LCAP = 2048;                // line-start table entries
-constexpr int TX_BR_CAP = 64;                // blocks of the tile's bracket staged in shared memory
 constexpr int TX_QN_MAX = 256;               // destination contig names kept in shared memory ...
 constexpr int TX_QCHARS = 3072;              // ... if their characters fit here
 constexpr int TX_WL_CAP = 256;
@@ -882,11 +878,6 @@ struct TextSmem {
     int tile;
     int wl_n;
     uint32_t rlo, rhi;  // byte range staged in the current round (multi-round emit of a large tile)
-    // bracket of a sorted tile: the blocks overlapping [first line start, last line end)
-    int br_cnt;  // -1: none
-    int br_tcid, br_lo_q, br_hi_q, br_blo;
-    uint32_t br_name_off, br_name_len;
-    int4 br_blk[TX_USE_BRACKET ? TX_BR_CAP : 1];
     // destination contig names (copy, when they fit) and the pointers every formatter uses
     const uint32_t *qoff_p;
     const char *qchars_p;
@@ -956,34 +947,9 @@ __device__ __forceinline__ int line_count(const TextArgs &A, const TileCtx &X, u
     if (kind == FL_NONE) return -1;
     if (kind == FL_FAST) {
         TextSmem &S = tx_smem();
-        // sorted tiles: the query usually falls inside the tile's bracket, whose blocks are
-        // in shared memory -> contig lookup and block search without a global load
-        bool inb = S.br_cnt >= 0 && F.len0 == S.br_name_len && F.start >= S.br_lo_q && F.end <= S.br_hi_q &&
-                   F.end > F.start;
-        if (inb) {
-            uint32_t i = 0;
-            while (i < F.len0 && tx_win()[p + i] == tx_win()[S.br_name_off + i]) i++;
-            inb = i == F.len0;
-        }
         Cand cd;
         Block b0{0, 0, 0, 0};
-        if (inb) {
-            F.tcid = S.br_tcid;
-            int lo = 0, hi = S.br_cnt;
-            while (lo < hi) {  // first block with tEnd > start
-                const int mid = (lo + hi) >> 1;
-                if (S.br_blk[mid].y > F.start) hi = mid;
-                else lo = mid + 1;
-            }
-            int k = lo;
-            while (k < S.br_cnt && S.br_blk[k].x < F.end) k++;
-            cd.lo = S.br_blo + lo;
-            cd.hi = S.br_blo + k;
-            if (k > lo) {
-                const int4 v = S.br_blk[lo];
-                b0 = Block{v.x, v.y, v.z, v.w};
-            }
-        } else {
+        {
             const bool same = H.len0 == F.len0 && F.len0 <= 16u && H.nw[0] == nw[0] && H.nw[1] == nw[1] &&
                               H.nw[2] == nw[2] && H.nw[3] == nw[3];
             F.tcid = same ? H.tcid : lookup_tcontig_win(A, tx_win(), p, F.len0, nw);
@@ -1032,15 +998,7 @@ __device__ __forceinline__ int line_count(const TextArgs &A, const TileCtx &X, u
             bool asc = true, desc = true, first = true;
             int prev_key = 0;
             for (int j = cd.lo; j < cd.hi; j++) {
-                Block b = b0;
-                if (j > cd.lo) {
-                    if (inb) {
-                        const int4 v = S.br_blk[j - S.br_blo];
-                        b = Block{v.x, v.y, v.z, v.w};
-                    } else {
-                        b = load_block(T, j);
-                    }
-                }
+                const Block b = j > cd.lo ? load_block(T, j) : b0;
                 if (!T.disjoint && !block_hits(b, F.start)) continue;
                 r = make_row(b, F.start, F.end);
                 len_l += fast_row_len(A, F, fixed, th, r);
@@ -1293,33 +1251,6 @@ __device__ __forceinline__ void block_scan_multi(const unsigned long long (&v)[N
     }
 }
 
-// digits at win[i...]: value, returns the offset of the first non-digit
-__device__ __forceinline__ uint32_t parse_digits(const unsigned char *win, uint32_t i, uint32_t &v) {
-    uint32_t x = 0, d;
-    while ((d = (uint32_t)win[i] - '0') <= 9u) {
-        x = x * 10u + d;
-        i++;
-    }
-    v = x;
-    return i;
-}
-// first three fields of a canonical line (used for the tile bracket)
-__device__ __forceinline__ bool parse_head(const unsigned char *win, uint32_t p, uint32_t limit, uint32_t &name_len,
-                                           int &start, int &end) {
-    uint32_t i = p;
-    while (win[i] > 0x20u) i++;
-    if (win[i] != '\t' || i == p) return false;
-    name_len = i - p;
-    uint32_t v, j = parse_digits(win, i + 1, v);
-    if (win[j] != '\t' || j == i + 1 || j - (i + 1) > 9u) return false;
-    start = (int)v;
-    i = j;
-    j = parse_digits(win, i + 1, v);
-    if (j == i + 1 || j - (i + 1) > 9u || j >= limit || (win[j] != '\t' && win[j] != '\n')) return false;
-    end = (int)v;
-    return true;
-}
-
 // Block-wide resolve of both look-back chains: 256 predecessors per round instead of 32.
 // Every thread of the block calls it; returns the exclusive prefixes in S.base_l / S.base_u.
 __device__ __forceinline__ void lookback_resolve2_block(TextSmem &S, uint64_t *desc_l, uint64_t *desc_u, int tile,
@@ -1528,45 +1459,6 @@ __global__ void __launch_bounds__(TX_TPB, TX_MIN_CTAS) lift_bed_text_kernel(cons
             __syncthreads();
         };
         build_table(0);
-
-        // ---- bracket of a sorted tile: blocks overlapping [first line start, last line end) ----
-        if (tid == 0) {
-            int cnt = -1;
-            if (TX_USE_BRACKET && T.disjoint && nlines > 0) {
-                const uint32_t p0 = S.lstart[0], p1 = S.lstart[min(nlines, TX_LCAP) - 1];
-                uint32_t n0 = 0, n1 = 0;
-                int s_first = 0, e_first = 0, s_last = 0, e_last = 0;
-                if (parse_head(win, p0, X.limit, n0, s_first, e_first) &&
-                    parse_head(win, p1, X.limit, n1, s_last, e_last) && n0 == n1 && e_last > s_first) {
-                    uint32_t i = 0;
-                    while (i < n0 && win[p0 + i] == win[p1 + i]) i++;
-                    uint32_t nw0[4] = {0, 0, 0, 0};
-                    for (uint32_t k = 0; k < n0 && k < 16u; k++) nw0[k >> 2] |= (uint32_t)win[p0 + k] << (8u * (k & 3u));
-                    const int tcid = i == n0 ? lookup_tcontig_win(A, win, p0, n0, nw0) : -1;
-                    if (tcid >= 0) {
-                        const int4 cm = load_cmeta(T, tcid);
-                        const int blo = lower_gt_ey(T, S.ey, cm, s_first);
-                        const int bhi = gallop_ge(T.tStartKey, blo, cm.y, e_last);
-                        if (bhi - blo <= TX_BR_CAP) {
-                            cnt = bhi - blo;
-                            S.br_tcid = tcid;
-                            S.br_lo_q = s_first;
-                            S.br_hi_q = e_last;
-                            S.br_blo = blo;
-                            S.br_name_off = p0;
-                            S.br_name_len = n0;
-                        }
-                    }
-                }
-            }
-            S.br_cnt = cnt;
-        }
-        __syncthreads();
-        for (int i = tid; i < S.br_cnt; i += TX_TPB) {
-            const Block b = load_block(T, S.br_blo + i);
-            S.br_blk[i] = make_int4(b.tStart, b.tEnd, b.qStart, b.meta);
-        }
-        __syncthreads();
 
         // ---- phase C: parse + search + exact output lengths; no barrier inside ---------
         uint32_t c_rec = 0, c_rows = 0, c_unm = 0;

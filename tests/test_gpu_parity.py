@@ -215,6 +215,24 @@ def test_text_chunk_boundaries(oracle, chunk):
     cf.close()
 
 
+@pytest.mark.parametrize("opt", [("zero_copy_input", 1), ("d2h_streams", 2)])
+def test_text_pipeline_options(oracle, opt):
+    """Optional pipeline paths (kernel reads pinned input over PCIe; two D2H streams) give the same bytes."""
+    import ctypes as C
+    import torch
+    cf, oc = pair(oracle, resource_bytes("hg19ToHg38.over.chain"))
+    cf.set_option(*opt)
+    cf.set_option("chunk_bytes", 300_000)
+    data = resource_bytes("hg19_col123.bed") + resource_bytes("chr1_hg19.bed")
+    host = torch.empty(len(data) + 5, dtype=torch.uint8, pin_memory=True)
+    o_l, o_u, _ = oc.lift_bed(data)
+    for shift in (0, 5):  # pinned input at an aligned and at an odd address
+        host[shift: shift + len(data)] = torch.frombuffer(bytearray(data), dtype=torch.uint8)
+        out = cf.lift_bed_text_ptr(host.data_ptr() + shift, len(data))
+        assert C.string_at(out.lifted, out.lifted_len) == o_l and C.string_at(out.unmatched, out.unmatched_len) == o_u
+    cf.close()
+
+
 @pytest.mark.parametrize("tile", [4096, 8192])
 def test_text_small_tiles(oracle, tile):
     """Smaller text tiles (chosen automatically for inputs with large fan-out) give the same bytes."""
