@@ -6,14 +6,18 @@
 //   sort by qStart, orderStartEnd, strand table, thick clamp   bed.d:156-196
 //
 // One persistent kernel.  A tile is 1024 consecutive queries (256 threads x 4,
-// 128-bit loads).  Each thread searches its four queries, the per-query fan-out
-// is block-scanned, the tile aggregate is chained to its predecessors with a
-// decoupled look-back (so the variable-length output needs no separate count
-// and scan passes: every input byte is read once and every output byte is
-// written once), then rows are written in place.  Queries with one hit (the
-// common case) are written by their own thread; queries with >= 2 hits go to a
-// shared-memory work list and are expanded by a warp (or by the whole block
-// when the fan-out is large), each row computing its own sorted position.
+// 128-bit loads).  Each thread searches its four queries (Eytzinger upper levels
+// in shared memory + quaternary bottom search; in sorted batches queries 2-4
+// gallop forward from the previous lower bound), computes the rows of its
+// single-hit queries, the per-query fan-out is block-scanned and the tile
+// aggregate is chained to its predecessors with a decoupled look-back resolved
+// block-wide (so the variable-length output needs no separate count and scan
+// passes: every input byte is read once and every output byte is written
+// once); then rows are stored in place.  Queries with >= 2 hits go to a
+// shared-memory work list, filled and expanded in rounds: a warp (or the whole
+// block for heavy fan-out) writes one sort key per candidate to shared memory,
+// sorts only if the keys are not already ascending, and stores every row at its
+// sorted position with the cumulative strand byte.
 #pragma once
 #include "device_util.cuh"
 #include "lift_core.cuh"
