@@ -209,6 +209,38 @@ int swo_lift_vcf_points_dev(swo_ctx *ctx, size_t n, const int32_t *d_tcid, const
 int swo_lift_vcf_text(swo_ctx *ctx, const char *in, size_t in_len, const char *chainfile,
                       const char *genomefile, const char *filedate, swo_text_out *out);
 
+/* ---- liftMAF  (maf.d:119-319) -------------------------------------------- */
+
+/* Record body of liftMAF (maf.d:172-310) on arrays: record i is the zero-based half-open
+ * interval [start[i], end[i]) (= MAF start-1, end; maf.d:186) on source contig tcid[i].
+ *   nhits[i]  0 -> unmatched (maf.d:192), 1 -> lifted, 2 -> more than one block: dropped (maf.d:298)
+ *   on one hit: out_qcid, out_start/out_end (one-based closed, orderStartEnd then start+1,
+ *   maf.d:208-214); flags bit0 = lifted, bit2 = '-' block (the caller reverse-complements the
+ *   tumor alleles, maf.d:220-224), bit1 = Reference_Allele differs from the destination genome
+ *   (maf.d:265); out_ref + out_off[i] receives fetchSequence(contig, out_start, out_end)
+ *   (maf.d:264, clipped at the end of the sequence), out_reflen[i] its length.  reflen[i] = -1
+ *   marks a "-" Reference_Allele: nothing is fetched or compared (maf.d:263).  The caller sizes
+ *   out_ref so that record i owns at least min(end-start, longest block) bytes. */
+int swo_lift_maf_records(swo_ctx *ctx, size_t n, const int32_t *tcid, const int32_t *start,
+                         const int32_t *end, const int32_t *reflen, const uint64_t *ref_off,
+                         const char *ref_bytes, size_t ref_bytes_len, const uint64_t *out_off,
+                         size_t out_ref_cap, uint8_t *nhits, int32_t *out_qcid, int32_t *out_start,
+                         int32_t *out_end, uint8_t *flags, int32_t *out_reflen, char *out_ref);
+
+/* counters the reference logs at the end of liftMAF (maf.d:160, 309-312) */
+typedef struct swo_maf_stats {
+    uint64_t n_records, n_matched, n_unmatched, n_multiple, n_refchg, n_neither;
+} swo_maf_stats;
+
+/* liftMAF, text -> text (maf.d:119-319) for a MAF held in memory: the first two lines go to both
+ * outputs (maf.d:166-171); the column split / join and the tumor-allele reverse complement
+ * (maf.d:36-54) run on the host, lift + REF fetch/compare in lift_maf_records_kernel.
+ * genomebuild replaces NCBI_Build (maf.d:294).  A record with fewer than 13 fields, a
+ * non-integer start/end or start > end is SWO_E_PARSE (reference: range violation /
+ * ConvException / assert).  stats may be NULL.  Needs a genome (swo_load_genome_fasta). */
+int swo_lift_maf_text(swo_ctx *ctx, const char *in, size_t in_len, const char *genomebuild,
+                      swo_text_out *out, swo_maf_stats *stats);
+
 /* ---- helpers ------------------------------------------------------------ */
 
 /* pinned host memory for inputs (cudaHostAlloc); faster H2D than pageable */

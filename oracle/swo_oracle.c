@@ -1286,6 +1286,198 @@ int orc_lift_vcf_text(const orc_chainfile *cf, const char *fasta, size_t fasta_l
     return rc;
 }
 
+/* ------------------------------------------------------------ liftMAF text */
+/* maf.d:21-32 */
+static unsigned char nt_comp(unsigned char c) {
+    switch (c) {
+    case '-': return '-';
+    case 'A': return 'T';
+    case 'C': return 'G';
+    case 'G': return 'C';
+    case 'T': return 'A';
+    case 'a': return 't';
+    case 'c': return 'g';
+    case 'g': return 'c';
+    case 't': return 'a';
+    default: return 0;
+    }
+}
+/* maf.d:36-54 */
+size_t orc_reverse_complement(const char *allele, size_t n, char *out) {
+    if (n == 2 && allele[0] == 'N' && allele[1] == 'A') { /* maf.d:41-42 */
+        out[0] = 'N';
+        out[1] = 'A';
+        return 2;
+    }
+    for (size_t i = 0; i < n; i++) out[n - 1 - i] = (char)nt_comp((unsigned char)allele[i]);
+    return n;
+}
+
+/* std.conv.to!long: optional sign, then digits only */
+static int parse_int64(const char *s, size_t n, int64_t *out) {
+    size_t i = 0;
+    int neg = 0;
+    if (n && (s[0] == '-' || s[0] == '+')) {
+        neg = s[0] == '-';
+        i = 1;
+    }
+    if (i == n) return 0;
+    uint64_t v = 0;
+    for (; i < n; i++) {
+        if (s[i] < '0' || s[i] > '9') return 0;
+        const uint64_t d = (uint64_t)(s[i] - '0');
+        if (v > (UINT64_MAX - d) / 10) return 0;
+        v = v * 10 + d;
+    }
+    if (neg ? v > (uint64_t)INT64_MAX + 1 : v > (uint64_t)INT64_MAX) return 0;
+    *out = neg ? (int64_t)(0 - v) : (int64_t)v;
+    return 1;
+}
+
+int orc_lift_maf_text(const orc_chainfile *cf, const char *fasta, size_t fasta_len, const char *in,
+                      size_t in_len, const char *genomebuild, orc_buf *lifted, orc_buf *unmatched,
+                      orc_maf_stats *st, char *err, size_t errcap) {
+    enum { M_BUILD = 3, M_CONTIG = 4, M_START = 5, M_END = 6, M_VTYPE = 9, M_REF = 10, M_T1 = 11, M_T2 = 12 }; /* maf.d:57-72 */
+    fa_seq *fa = NULL;
+    int nfa = 0;
+    fa_parse(fasta, fasta_len, &fa, &nfa);
+    orc_maf_stats s = {0, 0, 0, 0, 0, 0};
+    int rc = ORC_OK;
+    size_t i = 0;
+    for (int h = 0; h < 2 && i < in_len; h++) { /* readln x2, terminator kept (maf.d:166-171) */
+        size_t e = i;
+        while (e < in_len && in[e] != '\n') e++;
+        if (e < in_len) e++;
+        buf_put(lifted, in + i, e - i);
+        buf_put(unmatched, in + i, e - i);
+        i = e;
+    }
+    size_t fcap = 64, *f0 = (size_t *)malloc(sizeof(size_t) * fcap), *f1 = (size_t *)malloc(sizeof(size_t) * fcap);
+    char *tmp = NULL;
+    size_t tmpcap = 0;
+    while (i < in_len && rc == ORC_OK) {
+        size_t e = i;
+        while (e < in_len && in[e] != '\n') e++;
+        const char *ln = in + i;
+        const size_t n = e - i;
+        const size_t at = i;
+        i = e + 1;
+        size_t nf = 0, k = 0; /* splitter(): runs of white space (maf.d:175) */
+        while (k < n) {
+            while (k < n && is_space((unsigned char)ln[k])) k++;
+            if (k == n) break;
+            if (nf == fcap) {
+                fcap *= 2;
+                f0 = (size_t *)realloc(f0, sizeof(size_t) * fcap);
+                f1 = (size_t *)realloc(f1, sizeof(size_t) * fcap);
+            }
+            f0[nf] = k;
+            while (k < n && !is_space((unsigned char)ln[k])) k++;
+            f1[nf++] = k;
+        }
+        int64_t start, end;
+        if (nf < 13) {
+            snprintf(err, errcap, "MAF record with fewer than 13 fields at byte %zu", at);
+            rc = ORC_E_PARSE;
+            break;
+        }
+        if (!parse_int64(ln + f0[M_START], f1[M_START] - f0[M_START], &start) ||
+            !parse_int64(ln + f0[M_END], f1[M_END] - f0[M_END], &end)) {
+            snprintf(err, errcap, "bad start/end at byte %zu", at);
+            rc = ORC_E_PARSE;
+            break;
+        }
+        if (start > end) { /* assert(start <= end), maf.d:183 */
+            snprintf(err, errcap, "start > end at byte %zu", at);
+            rc = ORC_E_PARSE;
+            break;
+        }
+        s.n_records++;
+        start -= 1; /* maf.d:186 */
+        const int tcid = orc_tcontig_id(cf, ln + f0[M_CONTIG], f1[M_CONTIG] - f0[M_CONTIG]);
+        orc_link *hits = NULL;
+        const int64_t nh = orc_lift(cf, tcid, start, end, &hits); /* maf.d:189 */
+        if (nh == 0) { /* maf.d:192-195 */
+            s.n_unmatched++;
+            for (size_t j = 0; j < nf; j++) {
+                if (j) buf_putc(unmatched, '\t');
+                buf_put(unmatched, ln + f0[j], f1[j] - f0[j]);
+            }
+            buf_putc(unmatched, '\n');
+        } else if (nh > 1) { /* maf.d:298-307 */
+            s.n_matched++;
+            s.n_multiple++;
+        } else {
+            s.n_matched++;
+            const orc_link l = hits[0];
+            int64_t qs = l.qStart, qe = orc_link_qend(&l);
+            orc_order_start_end(&qs, &qe); /* maf.d:211 */
+            qs++;                          /* maf.d:212 */
+            const char *qn = orc_qcontig_name(cf, l.qcid);
+            /* new REF (maf.d:263-264) */
+            const char *ref = ln + f0[M_REF];
+            const size_t reflen = f1[M_REF] - f0[M_REF];
+            const char *newref;
+            size_t newlen;
+            if (reflen == 1 && ref[0] == '-') {
+                newref = "-";
+                newlen = 1;
+            } else {
+                const fa_seq *fs = fa_find(fa, nfa, qn, strlen(qn));
+                const int64_t a = qs - 1, b = qe; /* 1-based closed -> [a,b) */
+                newref = "";
+                newlen = 0;
+                if (fs && a >= 0 && a < fs->len && b > a) {
+                    newref = fs->seq + a;
+                    newlen = (size_t)((b > fs->len ? fs->len : b) - a);
+                }
+            }
+            /* tumor alleles after the strand flip (maf.d:220-224) */
+            const size_t l1 = f1[M_T1] - f0[M_T1], l2 = f1[M_T2] - f0[M_T2];
+            if (l1 + l2 + 2 > tmpcap) {
+                tmpcap = (l1 + l2 + 2) * 2;
+                tmp = (char *)realloc(tmp, tmpcap);
+            }
+            const char *t1 = ln + f0[M_T1], *t2 = ln + f0[M_T2];
+            if (l.invert < 0) {
+                orc_reverse_complement(t1, l1, tmp);
+                orc_reverse_complement(t2, l2, tmp + l1);
+                t1 = tmp;
+                t2 = tmp + l1;
+            }
+            const int chg = reflen != newlen || memcmp(ref, newref, reflen) != 0; /* maf.d:265 */
+            if (chg) {
+                s.n_refchg++;
+                const size_t vl = f1[M_VTYPE] - f0[M_VTYPE];
+                const int is_del = vl == 3 && memcmp(ln + f0[M_VTYPE], "DEL", 3) == 0;
+                const int eq1 = newlen == l1 && memcmp(newref, t1, l1) == 0;
+                const int eq2 = newlen == l2 && memcmp(newref, t2, l2) == 0;
+                if (!is_del && !eq1 && !eq2) s.n_neither++; /* maf.d:273-277 */
+            }
+            for (size_t j = 0; j < nf; j++) { /* maf.d:296 */
+                if (j) buf_putc(lifted, '\t');
+                if (j == M_BUILD) buf_puts(lifted, genomebuild);
+                else if (j == M_CONTIG) buf_puts(lifted, qn);
+                else if (j == M_START) buf_put_i64(lifted, qs);
+                else if (j == M_END) buf_put_i64(lifted, qe);
+                else if (j == M_REF && chg) buf_put(lifted, newref, newlen);
+                else if (j == M_T1) buf_put(lifted, t1, l1);
+                else if (j == M_T2) buf_put(lifted, t2, l2);
+                else buf_put(lifted, ln + f0[j], f1[j] - f0[j]);
+            }
+            buf_putc(lifted, '\n');
+        }
+        free(hits);
+    }
+    free(f0);
+    free(f1);
+    free(tmp);
+    for (int k = 0; k < nfa; k++) free(fa[k].seq);
+    free(fa);
+    if (st) *st = s;
+    return rc;
+}
+
 /* ---------------------------------------------------- bench workload helper */
 size_t orc_format_bed3(const orc_chainfile *cf, size_t n, const int32_t *tcid, const int32_t *start,
                        const int32_t *end, char *out, size_t cap) {

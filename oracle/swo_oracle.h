@@ -15,6 +15,7 @@
  *   source/swiftover/chain.d:787-805   orderStartEnd, ContigIDorAdd
  *   source/swiftover/bed.d:34-52,113-202   STRAND_TABLE, liftBED record loop
  *   source/swiftover/vcf.d:115-169     liftVCF record loop
+ *   source/swiftover/maf.d:21-54,119-319   NT_COMP_TABLE, reverse_complement, liftMAF
  *
  * Third-party pieces that are NOT in /root/reference and are restated from
  * their published behaviour (dub.json:7-11, versions floating):
@@ -188,6 +189,31 @@ int orc_lift_vcf_text(const orc_chainfile *cf, const char *fasta, size_t fasta_l
                       size_t in_len, const char *chainfile, const char *genomefile,
                       const char *filedate, orc_buf *lifted, orc_buf *unmatched,
                       orc_vcf_stats *st, char *err, size_t errcap);
+
+/* liftMAF on text (maf.d:119-319), with an in-memory FASTA for the destination genome.
+ *   lines 1 and 2 (version header, column header; maf.d:166-171) go to both outputs verbatim;
+ *   record (maf.d:172-310): split on white-space runs; start,end = to!long of columns 6,7
+ *     (1-based closed); hits = lift(contig, start-1, end)
+ *     0 hits  -> unmatched file, fields tab-joined (maf.d:190-193)
+ *     1 hit   -> contig = destination name; start,end = orderStartEnd(qStart,qEnd), start+1;
+ *                '-' block: Tumor_Seq_Allele1/2 reverse-complemented through NT_COMP_TABLE
+ *                (maf.d:21-54: only ACGTacgt and '-' map, every other byte becomes NUL, "NA" stays);
+ *                newRef = REF == "-" ? "-" : FASTA[contig][start-1, end) (clipped at the end of the
+ *                sequence); REF != newRef -> REF = newRef (maf.d:263-291); NCBI_Build = genomebuild;
+ *                fields tab-joined to the lifted file (maf.d:294-296)
+ *     >1 hits -> record is dropped from both outputs (maf.d:298-307)
+ * DEFINED DEVIATIONS: a record with fewer than 13 fields, a non-integer start/end or
+ * start > end is ORC_E_PARSE (reference: range violation / ConvException / assert); allele bytes >= 128 map to NUL
+ * (reference indexes a 128-entry table out of bounds); a destination contig the FASTA lacks
+ * yields an empty newRef.  dhtslib/htslib faidx is absent from /root/reference: parity unpinned. */
+typedef struct orc_maf_stats {
+    uint64_t n_records, n_matched, n_unmatched, n_multiple, n_refchg, n_neither; /* maf.d:160, 309-312 */
+} orc_maf_stats;
+int orc_lift_maf_text(const orc_chainfile *cf, const char *fasta, size_t fasta_len, const char *in,
+                      size_t in_len, const char *genomebuild, orc_buf *lifted, orc_buf *unmatched,
+                      orc_maf_stats *st, char *err, size_t errcap);
+/* maf.d:36-54; out has room for n bytes; returns the output length (== n) */
+size_t orc_reverse_complement(const char *allele, size_t n, char *out);
 
 /* Workload helper for bench.py --impl reference (not part of the restatement):
  * writes "name\tstart\tend\n" rows for n records, names taken from the chain's

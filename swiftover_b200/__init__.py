@@ -8,5 +8,6 @@ mirroring the reference CLI) and this thin ctypes mirror of the reference's
 from .chain import ChainFile, LiftedInterval, SwiftoverError  # noqa: F401
 from .bed import liftBED  # noqa: F401
 from .vcf import liftVCF  # noqa: F401
+from .maf import liftMAF  # noqa: F401
 
-__all__ = ["ChainFile", "LiftedInterval", "SwiftoverError", "liftBED", "liftVCF"]
+__all__ = ["ChainFile", "LiftedInterval", "SwiftoverError", "liftBED", "liftVCF", "liftMAF"]

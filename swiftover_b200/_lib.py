@@ -32,6 +32,10 @@ class SwoTextOut(C.Structure):
                 ("n_unmatched", C.c_uint64)]
 
 
+class SwoMafStats(C.Structure):
+    _fields_ = [(k, C.c_uint64) for k in ("n_records", "n_matched", "n_unmatched", "n_multiple", "n_refchg", "n_neither")]
+
+
 _lib = None
 
 
@@ -79,6 +83,8 @@ def lib():
         "swo_genome_seq_len": (i64, [vp, C.c_char_p]),
         "swo_lift_vcf_text": (i32, [vp, C.c_char_p, sz, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(SwoTextOut)]),
         "swo_lift_vcf_points": (i32, [vp, sz, vp, vp, vp, vp, vp, sz, vp, vp, vp, vp, vp]),
+        "swo_lift_maf_records": (i32, [vp, sz, vp, vp, vp, vp, vp, vp, sz, vp, sz, vp, vp, vp, vp, vp, vp, vp]),
+        "swo_lift_maf_text": (i32, [vp, C.c_char_p, sz, C.c_char_p, C.POINTER(SwoTextOut), C.POINTER(SwoMafStats)]),
         "swo_host_alloc": (vp, [sz]),
         "swo_host_free": (None, [vp]),
         "swo_set_option": (i32, [vp, C.c_char_p, i64]),

@@ -191,6 +191,36 @@ class ChainFile:
         unm = C.string_at(out.unmatched, out.unmatched_len) if out.unmatched_len else b""
         return lifted, unm, dict(n_records=out.n_records, n_matched=out.n_rows, n_unmatched=out.n_unmatched)
 
+    def lift_maf_text(self, data, genomebuild):
+        """liftMAF on an in-memory MAF (maf.d:119-319): returns (lifted, unmatched, stats)."""
+        buf = bytes(data)
+        out, st = L.SwoTextOut(), L.SwoMafStats()
+        self._ck(self._lib.swo_lift_maf_text(self._h, buf, len(buf), genomebuild.encode(), C.byref(out), C.byref(st)))
+        lifted = C.string_at(out.lifted, out.lifted_len) if out.lifted_len else b""
+        unm = C.string_at(out.unmatched, out.unmatched_len) if out.unmatched_len else b""
+        return lifted, unm, {k: getattr(st, k) for k, _ in st._fields_}
+
+    def lift_maf_records(self, tcid, start, end, reflen, ref_off, ref_bytes, out_off, out_cap):
+        """Batched liftMAF record body (maf.d:189-291): zero-based half-open [start,end) in,
+        one-based closed out; reflen -1 = "-" allele (no REF check)."""
+        tcid = np.ascontiguousarray(tcid, np.int32)
+        start = np.ascontiguousarray(start, np.int32)
+        end = np.ascontiguousarray(end, np.int32)
+        reflen = np.ascontiguousarray(reflen, np.int32)
+        ref_off = np.ascontiguousarray(ref_off, np.uint64)
+        out_off = np.ascontiguousarray(out_off, np.uint64)
+        ref_bytes = np.ascontiguousarray(ref_bytes, np.uint8)
+        n = len(tcid)
+        nh, fl = np.empty(n, np.uint8), np.empty(n, np.uint8)
+        oq, os_, oe, orl = (np.empty(n, np.int32) for _ in range(4))
+        oref = np.zeros(max(int(out_cap), 1), np.uint8)
+        self._ck(self._lib.swo_lift_maf_records(self._h, n, _addr(tcid), _addr(start), _addr(end), _addr(reflen),
+                                                _addr(ref_off), _addr(ref_bytes) if len(ref_bytes) else None,
+                                                len(ref_bytes), _addr(out_off), int(out_cap), _addr(nh), _addr(oq),
+                                                _addr(os_), _addr(oe), _addr(fl), _addr(orl),
+                                                _addr(oref) if out_cap else None))
+        return dict(nhits=nh, qcid=oq, start=os_, end=oe, flags=fl, reflen=orl, ref=oref[:int(out_cap)])
+
     def lift_vcf_points(self, tcid, pos, reflen, ref_off, ref_bytes):
         """Batched liftVCF record body (vcf.d:115-169)."""
         tcid = np.ascontiguousarray(tcid, np.int32)

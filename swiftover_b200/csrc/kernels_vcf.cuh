@@ -14,18 +14,23 @@
 
 namespace swo {
 
-struct VcfArgs {
-    TableView T;
-    const uint8_t *packed;  // 2 bit/base, A=0 C=1 G=2 T=3
+// Destination genome in HBM (genome.hpp): what IndexedFastaFile.fetchSequence reads (vcf.d:143, maf.d:264)
+struct GenomeView {
+    const uint8_t *packed;     // 2 bit/base, A=0 C=1 G=2 T=3
     const uint8_t *lower;      // 1 bit/base: soft-masked (lower case); null if the genome has none
     const uint8_t *exc_chunk;  // 1 bit per 4096 bases: chunk holds a non-ACGT symbol; null if none
     const int64_t *exc_start;  // runs of non-ACGT symbols, sorted by start
     const int32_t *exc_len;
     const uint8_t *exc_byte;
     int exc_n;
-    const int64_t *g_off;   // [g_n] first base of each destination contig
-    const int64_t *g_len;   // [g_n]
+    const int64_t *g_off;  // [g_n] first base of each destination contig
+    const int64_t *g_len;  // [g_n]
     int g_n;
+};
+
+struct VcfArgs {
+    TableView T;
+    GenomeView G;
     uint32_t n;
     const int32_t *tcid, *pos, *reflen;
     const uint64_t *ref_off;
@@ -37,7 +42,7 @@ struct VcfArgs {
 };
 
 // base g of the packed destination genome, exactly as the FASTA spells it (genome.hpp)
-__device__ __forceinline__ char genome_base(const VcfArgs &A, int64_t g) {
+__device__ __forceinline__ char genome_base(const GenomeView &A, int64_t g) {
     char base = "ACGT"[(__ldg(A.packed + (g >> 2)) >> ((g & 3) * 2)) & 3];
     if (A.lower && ((__ldg(A.lower + (g >> 3)) >> (g & 7)) & 1)) base |= 0x20;
     if (A.exc_n && ((__ldg(A.exc_chunk + (g >> 15)) >> ((g >> 12) & 7)) & 1)) {
@@ -69,14 +74,14 @@ __global__ void __launch_bounds__(256) lift_vcf_points_kernel(const VcfArgs A) {
         const Block b = load_block(A.T, j);
         const int q = b.meta >> 1;
         const int c = point_coord(b, c0);
-        const int64_t L = q < A.g_n ? A.g_len[q] : 0;
+        const int64_t L = q < A.G.g_n ? A.G.g_len[q] : 0;
         int m = 0;  // faidx clips the fetch at the contig end
         if (c >= 0 && (int64_t)c < L) m = (int64_t)c + rl > L ? (int)(L - c) : rl;
         bool diff = m != rl;
-        const int64_t g0 = q < A.g_n ? A.g_off[q] + c : 0;
+        const int64_t g0 = q < A.G.g_n ? A.G.g_off[q] + c : 0;
         for (int k = 0; k < m; k++) {
             const int64_t g = g0 + k;
-            const char base = genome_base(A, g);
+            const char base = genome_base(A.G, g);
             A.out_ref[ro + k] = base;
             diff |= base != A.ref[ro + k];  // vcf.d:144 byte-exact compare
         }

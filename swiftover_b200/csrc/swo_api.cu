@@ -23,6 +23,7 @@
 #include "genome.hpp"
 #include "kernels_binary.cuh"
 #include "kernels_text.cuh"
+#include "kernels_maf.cuh"
 #include "kernels_vcf.cuh"
 #include "swiftover_cuda.h"
 #include "swo_internal.hpp"
@@ -152,6 +153,21 @@ int fail(swo_ctx *c, int code, const char *fmt, ...) {
             return fail(ctx, e__ == cudaErrorMemoryAllocation ? SWO_E_OOM : SWO_E_CUDA, "%s: %s (%s:%d)", #call, \
                         cudaGetErrorString(e__), __FILE__, __LINE__);                              \
     } while (0)
+
+GenomeView genome_view(Device &d) {
+    GenomeView G;
+    G.packed = d.g_packed.as<uint8_t>();
+    G.g_off = d.g_off.as<int64_t>();
+    G.g_len = d.g_len.as<int64_t>();
+    G.g_n = d.g_n;
+    G.lower = d.g_has_lower ? d.g_lower.as<uint8_t>() : nullptr;
+    G.exc_n = d.g_exc_n;
+    G.exc_chunk = d.g_exc_n ? d.g_chunk.as<uint8_t>() : nullptr;
+    G.exc_start = d.g_estart.as<int64_t>();
+    G.exc_len = d.g_elen.as<int32_t>();
+    G.exc_byte = d.g_ebyte.as<uint8_t>();
+    return G;
+}
 
 template <typename T>
 int upload(swo_ctx *c, DevBuf &b, const T *src, size_t n, cudaStream_t s) {
@@ -971,16 +987,7 @@ int swo_lift_vcf_points(swo_ctx *c, size_t n, const int32_t *tcid, const int32_t
     if (ref_bytes_len) CK(c, cudaMemcpyAsync(d_ref, ref_bytes, ref_bytes_len, cudaMemcpyHostToDevice, st));
     VcfArgs A;
     A.T = d.T;
-    A.packed = d.g_packed.as<uint8_t>();
-    A.g_off = d.g_off.as<int64_t>();
-    A.g_len = d.g_len.as<int64_t>();
-    A.g_n = d.g_n;
-    A.lower = d.g_has_lower ? d.g_lower.as<uint8_t>() : nullptr;
-    A.exc_n = d.g_exc_n;
-    A.exc_chunk = d.g_exc_n ? d.g_chunk.as<uint8_t>() : nullptr;
-    A.exc_start = d.g_estart.as<int64_t>();
-    A.exc_len = d.g_elen.as<int32_t>();
-    A.exc_byte = d.g_ebyte.as<uint8_t>();
+    A.G = genome_view(d);
     A.n = (uint32_t)n;
     A.tcid = d_tcid;
     A.pos = d_pos;
@@ -1018,16 +1025,7 @@ int swo_lift_vcf_points_dev(swo_ctx *c, size_t n, const int32_t *d_tcid, const i
     CK(c, cudaSetDevice(d.ordinal));
     VcfArgs A;
     A.T = d.T;
-    A.packed = d.g_packed.as<uint8_t>();
-    A.g_off = d.g_off.as<int64_t>();
-    A.g_len = d.g_len.as<int64_t>();
-    A.g_n = d.g_n;
-    A.lower = d.g_has_lower ? d.g_lower.as<uint8_t>() : nullptr;
-    A.exc_n = d.g_exc_n;
-    A.exc_chunk = d.g_exc_n ? d.g_chunk.as<uint8_t>() : nullptr;
-    A.exc_start = d.g_estart.as<int64_t>();
-    A.exc_len = d.g_elen.as<int32_t>();
-    A.exc_byte = d.g_ebyte.as<uint8_t>();
+    A.G = genome_view(d);
     A.n = (uint32_t)n;
     A.tcid = d_tcid;
     A.pos = d_pos;
@@ -1228,6 +1226,274 @@ int swo_lift_vcf_text(swo_ctx *c, const char *in, size_t in_len, const char *cha
     out->n_records = n;
     out->n_rows = nm;
     out->n_unmatched = nu;
+    return SWO_OK;
+}
+
+// ---- liftMAF ------------------------------------------------------------------------------
+int swo_lift_maf_records(swo_ctx *c, size_t n, const int32_t *tcid, const int32_t *start, const int32_t *end,
+                         const int32_t *reflen, const uint64_t *ref_off, const char *ref_bytes, size_t ref_bytes_len,
+                         const uint64_t *out_off, size_t out_ref_cap, uint8_t *nhits, int32_t *out_qcid,
+                         int32_t *out_start, int32_t *out_end, uint8_t *flags, int32_t *out_reflen, char *out_ref) {
+    if (!c || (n && (!tcid || !start || !end || !reflen || !ref_off || !out_off || !nhits || !out_qcid || !out_start ||
+                     !out_end || !flags || !out_reflen)) ||
+        (ref_bytes_len && !ref_bytes) || (out_ref_cap && !out_ref))
+        return SWO_E_ARG;
+    if (c->dev.empty()) return fail(c, SWO_E_CUDA, "inspection-only context: no CUDA device, and there is no CPU fallback");
+    if (!c->have_chain) return fail(c, SWO_E_STATE, "no chain loaded");
+    Device &d = c->dev[0];
+    if (!d.g_n) return fail(c, SWO_E_STATE, "no genome loaded");
+    if (n >= 0xFFFFFFFFull) return fail(c, SWO_E_ARG, "n must be < 2^32-1 per call");
+    if (!n) return SWO_OK;
+    CK(c, cudaSetDevice(d.ordinal));
+    cudaStream_t st = d.s_comp;
+    auto al = [](size_t b) { return (b + 15) & ~(size_t)15; };
+    const size_t n4 = al(n * 4), n8 = al(n * 8), n1 = al(n);
+    CK(c, d.b_in.reserve(8 * n4 + 2 * n8 + 2 * n1 + al(ref_bytes_len) + al(out_ref_cap) + 64));
+    char *p = d.b_in.as<char>();
+    auto take = [&p](size_t b) {
+        char *r = p;
+        p += b;
+        return r;
+    };
+    int32_t *d_tcid = (int32_t *)take(n4), *d_s = (int32_t *)take(n4), *d_e = (int32_t *)take(n4),
+            *d_rl = (int32_t *)take(n4), *d_oq = (int32_t *)take(n4), *d_os = (int32_t *)take(n4),
+            *d_oe = (int32_t *)take(n4), *d_orl = (int32_t *)take(n4);
+    uint64_t *d_ro = (uint64_t *)take(n8), *d_oo = (uint64_t *)take(n8);
+    uint8_t *d_nh = (uint8_t *)take(n1), *d_fl = (uint8_t *)take(n1);
+    char *d_ref = take(al(ref_bytes_len)), *d_oref = take(al(out_ref_cap));
+    CK(c, cudaMemcpyAsync(d_tcid, tcid, n * 4, cudaMemcpyHostToDevice, st));
+    CK(c, cudaMemcpyAsync(d_s, start, n * 4, cudaMemcpyHostToDevice, st));
+    CK(c, cudaMemcpyAsync(d_e, end, n * 4, cudaMemcpyHostToDevice, st));
+    CK(c, cudaMemcpyAsync(d_rl, reflen, n * 4, cudaMemcpyHostToDevice, st));
+    CK(c, cudaMemcpyAsync(d_ro, ref_off, n * 8, cudaMemcpyHostToDevice, st));
+    CK(c, cudaMemcpyAsync(d_oo, out_off, n * 8, cudaMemcpyHostToDevice, st));
+    if (ref_bytes_len) CK(c, cudaMemcpyAsync(d_ref, ref_bytes, ref_bytes_len, cudaMemcpyHostToDevice, st));
+    MafArgs A;
+    A.T = d.T;
+    A.G = genome_view(d);
+    A.n = (uint32_t)n;
+    A.tcid = d_tcid;
+    A.start = d_s;
+    A.end = d_e;
+    A.reflen = d_rl;
+    A.ref_off = d_ro;
+    A.ref = d_ref;
+    A.out_off = d_oo;
+    A.nhits = d_nh;
+    A.out_qcid = d_oq;
+    A.out_start = d_os;
+    A.out_end = d_oe;
+    A.flags = d_fl;
+    A.out_reflen = d_orl;
+    A.out_ref = d_oref;
+    const int grid = (int)std::min<size_t>((n + 255) / 256, (size_t)d.sms * 8);
+    lift_maf_records_kernel<<<grid, 256, 0, st>>>(A);
+    c->launches++;
+    CK(c, cudaGetLastError());
+    CK(c, cudaMemcpyAsync(nhits, d_nh, n, cudaMemcpyDeviceToHost, st));
+    CK(c, cudaMemcpyAsync(flags, d_fl, n, cudaMemcpyDeviceToHost, st));
+    CK(c, cudaMemcpyAsync(out_qcid, d_oq, n * 4, cudaMemcpyDeviceToHost, st));
+    CK(c, cudaMemcpyAsync(out_start, d_os, n * 4, cudaMemcpyDeviceToHost, st));
+    CK(c, cudaMemcpyAsync(out_end, d_oe, n * 4, cudaMemcpyDeviceToHost, st));
+    CK(c, cudaMemcpyAsync(out_reflen, d_orl, n * 4, cudaMemcpyDeviceToHost, st));
+    if (out_ref_cap) CK(c, cudaMemcpyAsync(out_ref, d_oref, out_ref_cap, cudaMemcpyDeviceToHost, st));
+    CK(c, cudaStreamSynchronize(st));
+    return SWO_OK;
+}
+
+namespace {
+// std.conv.to!long (maf.d:180-181): optional sign, digits only
+bool token_to_i64(const char *s, size_t n, int64_t &out) {
+    size_t i = 0;
+    bool neg = false;
+    if (n && (s[0] == '-' || s[0] == '+')) {
+        neg = s[0] == '-';
+        i = 1;
+    }
+    if (i == n) return false;
+    uint64_t v = 0;
+    for (; i < n; i++) {
+        if (s[i] < '0' || s[i] > '9') return false;
+        const uint64_t dg = (uint64_t)(s[i] - '0');
+        if (v > (UINT64_MAX - dg) / 10) return false;
+        v = v * 10 + dg;
+    }
+    if (neg ? v > (uint64_t)INT64_MAX + 1 : v > (uint64_t)INT64_MAX) return false;
+    out = neg ? (int64_t)(0 - v) : (int64_t)v;
+    return true;
+}
+// NT_COMP_TABLE (maf.d:21-32): bytes outside ACGTacgt and '-' become NUL
+char nt_comp(unsigned char ch) {
+    switch (ch) {
+    case '-': return '-';
+    case 'A': return 'T';
+    case 'C': return 'G';
+    case 'G': return 'C';
+    case 'T': return 'A';
+    case 'a': return 't';
+    case 'c': return 'g';
+    case 'g': return 'c';
+    case 't': return 'a';
+    default: return 0;
+    }
+}
+// reverse_complement (maf.d:36-54)
+void append_revcomp(std::string &o, const char *a, size_t n) {
+    if (n == 2 && a[0] == 'N' && a[1] == 'A') {
+        o.append("NA");
+        return;
+    }
+    for (size_t k = n; k-- > 0;) o.push_back(nt_comp((unsigned char)a[k]));
+}
+bool maf_space(char ch) { return ch == ' ' || (ch >= 9 && ch <= 13); }
+}  // namespace
+
+int swo_lift_maf_text(swo_ctx *c, const char *in, size_t in_len, const char *genomebuild, swo_text_out *out,
+                      swo_maf_stats *stats) {
+    enum { M_BUILD = 3, M_CONTIG = 4, M_START = 5, M_END = 6, M_VTYPE = 9, M_REF = 10, M_T1 = 11, M_T2 = 12 };  // maf.d:57-72
+    if (!c || !out || (in_len && !in) || !genomebuild) return SWO_E_ARG;
+    memset(out, 0, sizeof *out);
+    if (stats) memset(stats, 0, sizeof *stats);
+    if (c->dev.empty()) return fail(c, SWO_E_CUDA, "inspection-only context: no CUDA device, and there is no CPU fallback");
+    if (!c->have_chain) return fail(c, SWO_E_STATE, "no chain loaded");
+    if (!c->dev[0].g_n) return fail(c, SWO_E_STATE, "no genome loaded");
+    std::string &L = c->vcf_l, &U = c->vcf_u;
+    L.clear();
+    U.clear();
+    size_t i = 0;
+    for (int h = 0; h < 2 && i < in_len; h++) {  // the two header lines, terminators kept (maf.d:166-171)
+        const char *nlp = (const char *)memchr(in + i, '\n', in_len - i);
+        const size_t e = nlp ? (size_t)(nlp - in) + 1 : in_len;
+        L.append(in + i, e - i);
+        U.append(in + i, e - i);
+        i = e;
+    }
+    int64_t longest = 0;  // no single hit is longer than the longest block
+    for (const Block &b : c->tab.blocks) longest = std::max<int64_t>(longest, (int64_t)b.tEnd - b.tStart);
+    // pass 1: fields of every record (splitter(): runs of white space, maf.d:175)
+    struct Rec {
+        size_t line, nf, f;  // byte offset of the line, field count, first entry in fld
+    };
+    std::vector<Rec> recs;
+    std::vector<std::pair<uint32_t, uint32_t>> fld;  // [begin,end) relative to the line
+    std::vector<int32_t> tcid, st0, en, rl;
+    std::vector<uint64_t> ro, oo;
+    std::string refb;
+    uint64_t ocap = 0;
+    while (i < in_len) {
+        const char *nlp = (const char *)memchr(in + i, '\n', in_len - i);
+        const size_t e = nlp ? (size_t)(nlp - in) : in_len;
+        const char *ln = in + i;
+        const size_t n = e - i, at = i;
+        i = e + 1;
+        if (n > 0xFFFFFFF0u) return fail(c, SWO_E_PARSE, "MAF line longer than 4 GiB at byte %zu", at);
+        Rec r{at, 0, fld.size()};
+        for (size_t k = 0; k < n;) {
+            while (k < n && maf_space(ln[k])) k++;
+            if (k == n) break;
+            const size_t a = k;
+            while (k < n && !maf_space(ln[k])) k++;
+            fld.emplace_back((uint32_t)a, (uint32_t)k);
+            r.nf++;
+        }
+        if (r.nf < 13) return fail(c, SWO_E_PARSE, "MAF record with fewer than 13 fields at byte %zu", at);
+        const auto *F = &fld[r.f];
+        int64_t s64, e64;
+        if (!token_to_i64(ln + F[M_START].first, F[M_START].second - F[M_START].first, s64) ||
+            !token_to_i64(ln + F[M_END].first, F[M_END].second - F[M_END].first, e64))
+            return fail(c, SWO_E_PARSE, "bad start/end at byte %zu", at);
+        if (s64 > e64) return fail(c, SWO_E_PARSE, "start > end at byte %zu", at);  // assert, maf.d:183
+        // to 32 bits: every block lies in [0, 2^31), so clamping the query keeps the hit set and the trimmed hit
+        const int64_t s0 = s64 == INT64_MIN ? INT64_MIN : s64 - 1;
+        const int32_t s32 = (int32_t)std::min<int64_t>(std::max<int64_t>(s0, INT32_MIN), INT32_MAX);
+        const int32_t e32 = (int32_t)std::min<int64_t>(std::max<int64_t>(e64, INT32_MIN), INT32_MAX);
+        recs.push_back(r);
+        tcid.push_back(c->tab.tcontig_id(std::string_view(ln + F[M_CONTIG].first, F[M_CONTIG].second - F[M_CONTIG].first)));
+        st0.push_back(s32);
+        en.push_back(e32);
+        const size_t rlen = F[M_REF].second - F[M_REF].first;
+        const bool dash = rlen == 1 && ln[F[M_REF].first] == '-';  // maf.d:263
+        if (rlen > 0x7FFFFFFFu) return fail(c, SWO_E_PARSE, "Reference_Allele longer than 2 GiB at byte %zu", at);
+        rl.push_back(dash ? -1 : (int32_t)rlen);
+        ro.push_back(refb.size());
+        if (!dash) refb.append(ln + F[M_REF].first, rlen);
+        oo.push_back(ocap);
+        if (!dash) ocap += (uint64_t)std::min<int64_t>(std::max<int64_t>((int64_t)e32 - s32, 0), longest);
+    }
+    // the record body on the GPU (maf.d:189-291)
+    const size_t n = recs.size();
+    std::vector<uint8_t> nh(n), fl(n);
+    std::vector<int32_t> oq(n), os(n), oe(n), orl(n);
+    std::string oref(ocap, '\0');
+    if (n) {
+        int rc = swo_lift_maf_records(c, n, tcid.data(), st0.data(), en.data(), rl.data(), ro.data(), refb.data(),
+                                      refb.size(), oo.data(), oref.size(), nh.data(), oq.data(), os.data(), oe.data(),
+                                      fl.data(), orl.data(), oref.data());
+        if (rc) return rc;
+    }
+    // pass 2: join
+    swo_maf_stats S;
+    memset(&S, 0, sizeof S);
+    S.n_records = n;
+    std::string t1, t2;
+    for (size_t k = 0; k < n; k++) {
+        const Rec &r = recs[k];
+        const char *ln = in + r.line;
+        const auto *F = &fld[r.f];
+        if (nh[k] == 0) {  // maf.d:192-195
+            S.n_unmatched++;
+            for (size_t j = 0; j < r.nf; j++) {
+                if (j) U.push_back('\t');
+                U.append(ln + F[j].first, F[j].second - F[j].first);
+            }
+            U.push_back('\n');
+            continue;
+        }
+        S.n_matched++;
+        if (nh[k] > 1) {  // maf.d:298-307
+            S.n_multiple++;
+            continue;
+        }
+        const bool neg = (fl[k] & 4) != 0, chg = (fl[k] & 2) != 0;
+        const char *a1 = ln + F[M_T1].first, *a2 = ln + F[M_T2].first;
+        size_t l1 = F[M_T1].second - F[M_T1].first, l2 = F[M_T2].second - F[M_T2].first;
+        if (neg) {  // maf.d:220-224
+            t1.clear();
+            t2.clear();
+            append_revcomp(t1, a1, l1);
+            append_revcomp(t2, a2, l2);
+            a1 = t1.data();
+            a2 = t2.data();
+        }
+        const char *nr = oref.data() + oo[k];
+        const size_t nrl = (size_t)orl[k];
+        if (chg) {
+            S.n_refchg++;
+            const bool del = F[M_VTYPE].second - F[M_VTYPE].first == 3 && !memcmp(ln + F[M_VTYPE].first, "DEL", 3);
+            const bool eq1 = nrl == l1 && !memcmp(nr, a1, l1), eq2 = nrl == l2 && !memcmp(nr, a2, l2);
+            if (!del && !eq1 && !eq2) S.n_neither++;  // maf.d:273-277
+        }
+        for (size_t j = 0; j < r.nf; j++) {  // maf.d:296
+            if (j) L.push_back('\t');
+            if (j == M_BUILD) L += genomebuild;
+            else if (j == M_CONTIG) L += c->tab.qnames[oq[k]];
+            else if (j == M_START) put_num(L, os[k]);
+            else if (j == M_END) put_num(L, oe[k]);
+            else if (j == M_REF && chg) L.append(nr, nrl);
+            else if (j == M_T1) L.append(a1, l1);
+            else if (j == M_T2) L.append(a2, l2);
+            else L.append(ln + F[j].first, F[j].second - F[j].first);
+        }
+        L.push_back('\n');
+    }
+    out->lifted = L.data();
+    out->lifted_len = L.size();
+    out->unmatched = U.data();
+    out->unmatched_len = U.size();
+    out->n_records = n;
+    out->n_rows = S.n_matched - S.n_multiple;
+    out->n_unmatched = S.n_unmatched;
+    if (stats) *stats = S;
     return SWO_OK;
 }
 

@@ -75,6 +75,14 @@ int swo_genome_has_seq(const(swo_ctx)* ctx, const(char)* name);
 long swo_genome_seq_len(const(swo_ctx)* ctx, const(char)* name);
 int swo_lift_vcf_text(swo_ctx* ctx, const(char)* inbuf, size_t in_len, const(char)* chainfile,
                       const(char)* genomefile, const(char)* filedate, swo_text_out* o);
+/// counters liftMAF logs (maf.d:160, 309-312)
+struct swo_maf_stats { ulong n_records, n_matched, n_unmatched, n_multiple, n_refchg, n_neither; }
+int swo_lift_maf_records(swo_ctx* ctx, size_t n, const(int)* tcid, const(int)* start, const(int)* end,
+                         const(int)* reflen, const(ulong)* ref_off, const(char)* ref_bytes, size_t ref_bytes_len,
+                         const(ulong)* out_off, size_t out_ref_cap, ubyte* nhits, int* out_qcid, int* out_start,
+                         int* out_end, ubyte* flags, int* out_reflen, char* out_ref);
+int swo_lift_maf_text(swo_ctx* ctx, const(char)* inbuf, size_t in_len, const(char)* genomebuild, swo_text_out* o,
+                      swo_maf_stats* stats);
 void* swo_host_alloc(size_t bytes);
 void swo_host_free(void* p);
 int swo_set_option(swo_ctx* ctx, const(char)* key, long value);

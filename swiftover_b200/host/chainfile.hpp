@@ -98,5 +98,8 @@ void liftBED(const std::string &chainfile, const std::string &infile, const std:
 // vcf.d:29-32 (uncompressed text VCF, uncompressed FASTA)
 void liftVCF(const std::string &chainfile, const std::string &genomefile, const std::string &infile,
              const std::string &outfile, const std::string &unmatched);
+// maf.d:119-121
+void liftMAF(const std::string &chainfile, const std::string &genomefile, const std::string &genomebuild,
+             const std::string &infile, const std::string &outfile, const std::string &unmatched);
 
 }  // namespace swiftover

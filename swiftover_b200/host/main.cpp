@@ -1,6 +1,6 @@
 // main.cpp — the `swiftover` command line over the CUDA engine: same flags, checks and
 // exit codes as the reference (/root/reference/source/swiftover/main.d:28-195).
-//   -t|--type bed|vcf   -c|--chainfile F   -g|--genome F   -b|--build S
+//   -t|--type bed|maf|vcf   -c|--chainfile F   -g|--genome F   -b|--build S
 //   -i|--infile F (- or omitted: stdin)    -o|--outfile F (- or omitted: stdout)   -u|--unmatched F
 #include <sys/stat.h>
 
@@ -93,7 +93,10 @@ int main(int argc, char **argv) {
                 throw Error(SWO_E_ARG, "VCF liftover needs -i and -o file names");
             liftVCF(chain, genome, in, out, unm);  // main.d:130-134
         } else if (type == "maf") {
-            throw Error(SWO_E_ARG, "maf is out of scope of this engine (experimental upstream)");
+            if (genome.empty()) throw Error(SWO_E_ARG, "Genome FASTA (for the destination build) required.");  // main.d:124-127
+            if (build.empty()) throw Error(SWO_E_ARG, "Genome build name (for the destination) required.");
+            if (!exists(genome)) throw Error(SWO_E_IO, "Genome FASTA does not exist");
+            liftMAF(chain, genome, build, in, out, unm);  // main.d:128
         } else {
             throw Error(SWO_E_ARG, "Unknown file type. Use \"bed\" or \"vcf\".");  // main.d:136
         }

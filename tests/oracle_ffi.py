@@ -128,6 +128,15 @@ class Oracle:
             raise OracleError(-1, err.value.decode())
         return OracleChain(self, h)
 
+    def reverse_complement(self, allele: bytes) -> bytes:
+        """reverse_complement (maf.d:36-54)"""
+        out = C.create_string_buffer(len(allele) + 1)
+        fn = self.L.orc_reverse_complement
+        fn.restype = C.c_size_t
+        fn.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p]
+        n = fn(allele, len(allele), out)
+        return out.raw[:n]
+
     def count_links(self, text: bytes) -> int:
         return self.L.orc_chain_count_links(text, len(text))
 
@@ -271,6 +280,28 @@ class OracleChain:
         out = (C.string_at(lifted.data, lifted.len) if lifted.len else b"",
                C.string_at(unm.data, unm.len) if unm.len else b"",
                dict(n_records=st.n_records, n_matched=st.n_matched, n_unmatched=st.n_unmatched, n_refchg=st.n_refchg))
+        self.L.orc_buf_free(C.byref(lifted))
+        self.L.orc_buf_free(C.byref(unm))
+        if rc:
+            raise OracleError(rc, err.value.decode())
+        return out
+
+    def lift_maf_text(self, fasta: bytes, text: bytes, genomebuild="B"):
+        """liftMAF on text (maf.d:119-319): (lifted, unmatched, stats)."""
+        keys = ("n_records", "n_matched", "n_unmatched", "n_multiple", "n_refchg", "n_neither")
+
+        class St(C.Structure):
+            _fields_ = [(k, C.c_uint64) for k in keys]
+        fn = self.L.orc_lift_maf_text
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_char_p, C.POINTER(OrcBuf),
+                       C.POINTER(OrcBuf), C.POINTER(St), C.c_char_p, C.c_size_t]
+        lifted, unm, st = OrcBuf(), OrcBuf(), St()
+        err = C.create_string_buffer(256)
+        rc = fn(self.h, fasta, len(fasta), text, len(text), genomebuild.encode(), C.byref(lifted), C.byref(unm),
+                C.byref(st), err, 256)
+        out = (C.string_at(lifted.data, lifted.len) if lifted.len else b"",
+               C.string_at(unm.data, unm.len) if unm.len else b"", {k: getattr(st, k) for k in keys})
         self.L.orc_buf_free(C.byref(lifted))
         self.L.orc_buf_free(C.byref(unm))
         if rc:
