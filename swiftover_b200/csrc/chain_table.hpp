@@ -15,6 +15,10 @@
 #include <utility>
 #include <vector>
 
+#ifndef SWO_EY_CAP
+#define SWO_EY_CAP 2048  // Eytzinger samples staged in shared memory (16 KiB)
+#endif
+
 namespace swo {
 
 // One alignment block as the device sees it: a single 128-bit load.
@@ -40,7 +44,7 @@ struct ChainTable {
     // consecutive blocks, stored in Eytzinger (BFS) order as {key, block index}
     // pairs at ey[eyoff[c] ...].  S is the smallest power of two for which all
     // samples fit in EY_CAP entries.
-    static constexpr int EY_CAP = 2048;
+    static constexpr int EY_CAP = SWO_EY_CAP;
     int eyShift = 0;
     std::vector<int32_t> eyKey, eyIdx;  // [nsamples] each
     std::vector<int32_t> eyoff;         // [ntc+1]

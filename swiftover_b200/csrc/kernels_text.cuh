@@ -52,7 +52,10 @@ namespace swo {
 #endif
 constexpr int TX_TPB = TX_THREADS;
 constexpr int TX_NW = TX_TPB / 32;
-constexpr int TX_TILE = 16384;               // largest tile (bytes of text); TextArgs.tile_bytes picks 16, 8 or 4 KiB
+#ifndef TX_TILE_V
+#define TX_TILE_V 16384
+#endif
+constexpr int TX_TILE = TX_TILE_V;               // largest tile (bytes of text); TextArgs.tile_bytes picks 16, 8 or 4 KiB
 constexpr int TX_MSEG = 64;                  // bytes per newline-mask word
 static_assert(TX_TILE / TX_TPB == 64 || TX_TILE / TX_TPB == 32, "TX_THREADS must be 256 or 512");
 constexpr int TX_PRE = 64;                   // bytes staged before the tile
@@ -60,10 +63,10 @@ constexpr int TX_LOOK = 1024;                // bytes staged after the tile
 constexpr int TX_WIN = TX_PRE + TX_TILE + TX_LOOK;
 constexpr int TX_PAD = 32;                   // always '\n' after the window
 constexpr int TX_NSEG = TX_WIN / TX_MSEG;    // 273
-constexpr int TX_OUT_STAGE = 20480;          // lifted bytes staged per tile
+constexpr int TX_OUT_STAGE = TX_TILE / 4 * 5;       // lifted bytes staged per tile
 constexpr int TX_ROUND_SLACK = 4096;         // multi-round emit: a line's rows may run this far past its round's window
 constexpr int TX_UNM_STAGE = TX_TILE + TX_LOOK;  // unmatched bytes staged per tile: a tile's unmatched text never exceeds its input
-constexpr int TX_LCAP = 2048;                // line-start table entries
+constexpr int TX_LCAP = TX_TILE / 8;           // line-start table entries
 constexpr int TX_QN_MAX = 256;               // destination contig names kept in shared memory ...
 constexpr int TX_QCHARS = 3072;              // ... if their characters fit here
 constexpr int TX_WL_CAP = 256;
@@ -1466,24 +1469,36 @@ __global__ void __launch_bounds__(TX_TPB, TX_MIN_CTAS) lift_bed_text_kernel(cons
         H.len0 = 0;
         LineState st[TX_NB];
         unsigned long long v[TX_NB], ex[TX_NB], bt[TX_NB];
+        // one copy of the (large) per-line code: the batch loop is not unrolled, the cached states
+        // rotate through st[] so that every index stays static (registers)
 #pragma unroll
+        for (int b = 0; b < TX_NB; b++) st[b] = LineState{};
+#pragma unroll 1
         for (int b = 0; b < TX_NB; b++) {
             const int li = b * TX_TPB + tid;
-            st[b].meta = FL_NONE;
-            v[b] = 0;
+            LineState cur = LineState{};
+            cur.meta = FL_NONE;
+            unsigned long long cv = 0;
             if (li < nlines) {
                 uint32_t ll, lu;
-                const int nh = line_count(A, X, S.lstart[li], st[b], ll, lu, true, H);
-                v[b] = ((unsigned long long)ll << 32) | lu;
+                const int nh = line_count(A, X, S.lstart[li], cur, ll, lu, true, H);
+                cv = ((unsigned long long)ll << 32) | lu;
                 if (nh == -2)  // max(~p0) == first bad line
                     atomicMax((unsigned long long *)(A.sizes + 5),
-                              ~(unsigned long long)(X.g0 + ((st[b].pq & 0xFFFFu) - X.s0)));
+                              ~(unsigned long long)(X.g0 + ((cur.pq & 0xFFFFu) - X.s0)));
                 if (nh >= 0) {
                     c_rec++;
                     c_rows += (uint32_t)nh;
                     c_unm += nh == 0 ? 1u : 0u;
                 }
             }
+#pragma unroll
+            for (int k = 0; k + 1 < TX_NB; k++) {
+                st[k] = st[k + 1];
+                v[k] = v[k + 1];
+            }
+            st[TX_NB - 1] = cur;
+            v[TX_NB - 1] = cv;
         }
         block_scan_multi<TX_NB>(v, ex, bt, S.scan64);
         // lines with heavy fan-out: the block sums their output lengths (a single thread would
@@ -1621,10 +1636,19 @@ __global__ void __launch_bounds__(TX_TPB, TX_MIN_CTAS) lift_bed_text_kernel(cons
 
         if (!direct_l) {
             // ---- phase E: format from the cached state into the stages; no barrier inside ---
+#pragma unroll 1
+            for (int b = 0; b < TX_NB; b++) {  // same rotation: one copy of line_emit
+                const uint32_t o_l = (uint32_t)(ex[0] >> 32), o_u = (uint32_t)ex[0];
+                line_emit(A, X, S, st[0], stage_l + o_l, base_u ? base_u + o_u : nullptr, o_l);
+                const LineState t = st[0];
+                const unsigned long long te = ex[0];
 #pragma unroll
-            for (int b = 0; b < TX_NB; b++) {
-                const uint32_t o_l = (uint32_t)(ex[b] >> 32), o_u = (uint32_t)ex[b];
-                line_emit(A, X, S, st[b], stage_l + o_l, base_u ? base_u + o_u : nullptr, o_l);
+                for (int k = 0; k + 1 < TX_NB; k++) {
+                    st[k] = st[k + 1];
+                    ex[k] = ex[k + 1];
+                }
+                st[TX_NB - 1] = t;
+                ex[TX_NB - 1] = te;
             }
             emit_uncached(stage_l);
             run_expansions(stage_l);

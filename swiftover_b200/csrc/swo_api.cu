@@ -335,6 +335,7 @@ int launch_lift_text(swo_ctx *c, Device &d, const char *d_in, size_t in_len, cha
         int per = 0;
         CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, lift_bed_text_kernel, TX_TPB, smem));
         d.text_grid = std::max(1, per) * d.sms;
+        if (getenv("SWO_TRACE")) fprintf(stderr, "[swo] text kernel: %zu B shared memory, %d CTAs/SM x %d threads\n", smem, per, TX_TPB);
     }
     const int grid = std::min(ntiles, d.text_grid);
     CK(c, d.gscr.reserve((size_t)d.text_grid * (TX_GSCR + TX_GSCR / 2) * sizeof(unsigned long long)));
@@ -625,7 +626,8 @@ int swo_set_option(swo_ctx *c, const char *key, int64_t value) {
             c->tile_bytes = TX_TILE;
             return SWO_OK;
         }
-        if (value != 4096 && value != 8192 && value != 16384) return fail(c, SWO_E_ARG, "tile_bytes must be 0 (auto), 4096, 8192 or 16384");
+        if ((value != 4096 && value != 8192 && value != 16384) || value > TX_TILE)
+            return fail(c, SWO_E_ARG, "tile_bytes must be 0 (auto), 4096, 8192 or 16384");
         c->tile_bytes = (uint32_t)value;
         c->tile_auto = false;
         return SWO_OK;
