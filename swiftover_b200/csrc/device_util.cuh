@@ -55,11 +55,22 @@ __device__ __forceinline__ T warp_sum(T v) {
 // Exclusive scan of one value per thread over a block of NWARPS*32 threads.
 // `scratch` is NWARPS+1 elements of shared memory.  Returns the exclusive prefix;
 // *total receives the block sum (same value in every thread).
-// Contains two __syncthreads(); safe to call repeatedly with the same scratch.
+// Contains two block barriers; safe to call repeatedly with the same scratch.
+//
+// The first barrier is a barrier-with-vote whose result gates the shuffles.  That is on
+// purpose: with a plain __syncthreads() ptxas (12.9, sm_100a) schedules the first SHFL of the
+// warp scan ABOVE the BAR.SYNC and elides a __syncwarp() in front of it (it takes the warp for
+// converged behind a BSYNC.RECONVERGENT), so after a long divergent region — per-thread block
+// searches — early lanes read a neighbour's register before that lane had produced its value
+// and the scan came out short (seen in lift_intervals_kernel: per-thread counts right, prefix
+// wrong).  Shuffles that are control-dependent on the barrier's result cannot move above it.
 template <typename T, int NWARPS>
 __device__ __forceinline__ T block_exclusive_scan(T v, T *scratch, T *total) {
+    if (!__syncthreads_or(v != 0)) {  // also: previous users of scratch are done
+        *total = 0;
+        return 0;
+    }
     const T inc = warp_inclusive_scan(v);
-    __syncthreads();  // previous users of scratch are done
     if (lane_id() == 31) scratch[warp_id()] = inc;
     __syncthreads();
     T wbase = 0, tot = 0;

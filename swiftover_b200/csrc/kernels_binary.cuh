@@ -32,6 +32,9 @@ constexpr int LI_NW = LI_TPB / 32;
 constexpr int LI_WL_CAP = 256;      // multi-hit queries queued per tile
 constexpr int LI_HEAVY_MIN = 128;   // candidates above this: the whole block expands the query
 constexpr int LI_XSCR = 1024;       // shared-memory sort scratch (= LI_NW warp regions of LI_HEAVY_MIN)
+constexpr int LI_WIN = 64;          // blocks of the tile bracket staged in shared memory (sorted batches)
+constexpr int LI_STAGE = 1152;       // rows of a tile staged in shared memory for the deferred copy-out
+constexpr int LI_BRK_RETRY = 16;    // a CTA that switched the bracket off tries it again every this many tiles
 
 struct LiftArgs {
     TableView T;
@@ -49,17 +52,26 @@ struct LiftArgs {
     uint64_t *totals;   // [0] rows, [1] unmatched   (zeroed)
 };
 
+// Where a tile's rows go: global memory (positions are global row indices) or the tile's
+// shared-memory stage (positions are offsets inside the tile).
+struct RowSink {
+    swo_row *rows;
+    swo_thick *thick;
+    uint64_t cap;
+};
+
 // Expand one multi-hit query: every candidate block computes its own sorted
 // position (rank by (key, candidate index)), the cumulative strand byte and
 // the thick clamp, and writes its row.  Work is strided by (first, stride) so
 // the same code serves one thread, one warp or one block.
-__device__ __forceinline__ void expand_query(const LiftArgs &A, const int2 *ey, uint32_t q, int lo, int ncand,
-                                             uint64_t rowbase, int first, int stride) {
+template <bool THICK>
+__device__ __forceinline__ void expand_query(const LiftArgs &A, const RowSink &K, const int2 *ey, uint32_t q, int lo,
+                                             int ncand, uint64_t rowbase, int first, int stride) {
     const TableView &T = A.T;
     const int start = __ldg(A.start + q), end = __ldg(A.end + q);
     const unsigned char orig = A.strand ? __ldg(A.strand + q) : 0;
     Thick th{0, 0, 0};
-    if (A.thick_s) th = lift_thick(T, ey, __ldg(A.tcid + q), __ldg(A.thick_s + q), __ldg(A.thick_e + q));
+    if (THICK) th = lift_thick(T, ey, __ldg(A.tcid + q), __ldg(A.thick_s + q), __ldg(A.thick_e + q));
     for (int c = first; c < ncand; c += stride) {
         const Block bj = load_block(T, lo + c);
         if (!T.disjoint && !block_hits(bj, start)) continue;
@@ -81,18 +93,18 @@ __device__ __forceinline__ void expand_query(const LiftArgs &A, const int2 *ey, 
             }
         }
         const uint64_t pos = rowbase + (uint64_t)rank;
-        if (pos < A.rows_cap) {
+        if (pos < K.cap) {
             const unsigned char sb = A.strand ? strand_at_rank(orig, best_inv, rank, negs) : 0;
             swo_row r;
             r.qcid_strand = rj.qcid | ((int)sb << 16);
             r.start = rj.s;
             r.end = rj.e;
             r.src = q;
-            A.rows[pos] = r;
-            if (A.thick_s) {
+            K.rows[pos] = r;
+            if (THICK) {
                 swo_thick t;
                 thick_clamp(th, rj.s, rj.e, t.thick_start, t.thick_end);
-                A.thick[pos] = t;
+                K.thick[pos] = t;
             }
         }
     }
@@ -102,15 +114,15 @@ __device__ __forceinline__ void expand_query(const LiftArgs &A, const int2 *ey, 
 // fan-out): one 64-bit key (qStart, candidate, invert) per candidate in shared memory, a bitonic
 // sort only if the keys are not already ascending, then every sorted position writes its row;
 // the cumulative strand byte comes from a running count of inverted rows (bed.d:173).
-template <bool BLOCK>
-__device__ __noinline__ void expand_query_coop(const LiftArgs &A, const int2 *ey, uint32_t q, int lo, int ncand,
-                                               uint64_t rowbase, unsigned long long *scr, uint32_t *scan_scr, int first,
-                                               int stride) {
+template <bool BLOCK, bool THICK>
+__device__ __noinline__ void expand_query_coop(const LiftArgs &A, const RowSink &K, const int2 *ey, uint32_t q, int lo,
+                                               int ncand, uint64_t rowbase, unsigned long long *scr, uint32_t *scan_scr,
+                                               int first, int stride) {
     const TableView &T = A.T;
     const int start = __ldg(A.start + q), end = __ldg(A.end + q);
     const unsigned char orig = A.strand ? __ldg(A.strand + q) : 0;
     Thick th{0, 0, 0};
-    if (A.thick_s) th = lift_thick(T, ey, __ldg(A.tcid + q), __ldg(A.thick_s + q), __ldg(A.thick_e + q));
+    if (THICK) th = lift_thick(T, ey, __ldg(A.tcid + q), __ldg(A.thick_s + q), __ldg(A.thick_e + q));
     int P = 32;
     while (P < ncand) P <<= 1;
     for (int c = first; c < P; c += stride) {
@@ -164,7 +176,7 @@ __device__ __noinline__ void expand_query_coop(const LiftArgs &A, const int2 *ey
             tot = __shfl_sync(FULL, inc, 31);
         }
         const uint64_t pos = rowbase + (uint64_t)j;
-        if (hit && pos < A.rows_cap) {
+        if (hit && pos < K.cap) {
             const int c = (int)(((uint32_t)e) >> 1);
             const RowCore r = make_row(load_block(T, lo + c), start, end);
             const unsigned char sb = A.strand ? strand_at_rank(orig, inv_first, j, (int)(carry + ex + neg)) : 0;
@@ -173,11 +185,11 @@ __device__ __noinline__ void expand_query_coop(const LiftArgs &A, const int2 *ey
             row.start = r.s;
             row.end = r.e;
             row.src = q;
-            A.rows[pos] = row;
-            if (A.thick_s) {
+            K.rows[pos] = row;
+            if (THICK) {
                 swo_thick t;
                 thick_clamp(th, r.s, r.e, t.thick_start, t.thick_end);
-                A.thick[pos] = t;
+                K.thick[pos] = t;
             }
         }
         carry += tot;
@@ -185,33 +197,157 @@ __device__ __noinline__ void expand_query_coop(const LiftArgs &A, const int2 *ey
     if (BLOCK) __syncthreads();  // scratch is reused by the next heavy query
 }
 
-__global__ void __launch_bounds__(LI_TPB, 4) lift_intervals_kernel(const __grid_constant__ LiftArgs A) {
-    __shared__ int s_tile;
-    __shared__ uint32_t s_scan[LI_NW + 1];
-    __shared__ unsigned long long s_lb_part[LI_NW];
-    __shared__ int s_lb_found[LI_NW];
-    __shared__ int s_wl_n;
-    __shared__ uint32_t s_wl_q[LI_WL_CAP];
-    __shared__ int s_wl_lo[LI_WL_CAP];
-    __shared__ int s_wl_cnt[LI_WL_CAP];
-    __shared__ uint32_t s_wl_off[LI_WL_CAP];
-    __shared__ int2 s_ey[ChainTable::EY_CAP];  // upper search levels (Eytzinger order)
-    __shared__ unsigned long long s_xscr[LI_XSCR];
+
+// lower_gt_ey for a whole warp with one (uniform) key: the Eytzinger descent is the same, the
+// group of S <= 32 keys is settled by one coalesced load and a ballot instead of three
+// dependent probe rounds.
+__device__ __forceinline__ int lower_gt_ey_warp(const TableView &T, const int2 *__restrict__ ey, const int4 cm, int x) {
+    if (T.ey_shift > 5) return lower_gt_ey(T, ey, cm, x);
+    const int b = cm.y, m = cm.w;
+    const int2 *__restrict__ e = ey + cm.z - 1;  // 1-based
+    int k = 1;
+    while (k <= m) k = 2 * k + (e[k].x <= x ? 1 : 0);
+    k >>= __ffs(~k);
+    int lo, hi;  // answer in [lo,hi], hi == b means "none"
+    if (k) {
+        hi = e[k].y;
+        lo = hi - ((1 << T.ey_shift) - 1);
+    } else {
+        lo = cm.x + (m << T.ey_shift);
+        hi = b;
+    }
+    const int j = lo + lane_id();
+    const bool gt = j < hi && j < b && __ldg(T.pmaxKey + j) > x;
+    const unsigned mask = __ballot_sync(FULL, gt);
+    return mask ? lo + __ffs(mask) - 1 : hi;
+}
+
+// Tile bracket (sorted batches): the blocks a sorted tile can touch start at the lower bound L of
+// its first query; LI_WIN of them are staged in shared memory, so that every query of the tile
+// that names the same contig and does not start earlier finds its candidates with shared-memory
+// probes only (a merge of the tile's queries against its slice of the table).  Slots past the
+// contig's last block hold sentinels (no query reaches them as a hit).
+struct TileBracket {
+    int tc;    // contig of the bracket, -2 = none
+    int st;    // start of the tile's first query
+    int L;     // global index of window slot 0
+    int cend;  // contig's block end
+};
+
+// Shared memory of one CTA (dynamic: > 48 KiB).  The 16-byte aligned arrays come first.
+template <bool THICK>
+struct LiftSmem {
+    int4 wblk[LI_WIN];                   // tile bracket: blocks L .. L+LI_WIN-1
+    int4 st_rows[LI_STAGE];              // staged rows of the pending tile (index = row offset inside the tile)
+    uint32_t st_off[LI_TILE];            //   and the tile-local row offset of each of its queries
+    int2 st_thick[THICK ? LI_STAGE : 1];
+    int2 ey[ChainTable::EY_CAP];         // upper search levels (Eytzinger order)
+    unsigned long long xscr[LI_XSCR];    // sort scratch of the multi-hit expansion
+    unsigned long long lb_part[LI_NW];
+    int wpm[LI_WIN];                     // pmaxKey of the bracket's blocks
+    uint32_t wl_q[LI_WL_CAP];
+    int wl_lo[LI_WL_CAP];
+    int wl_cnt[LI_WL_CAP];
+    uint32_t wl_off[LI_WL_CAP];
+    unsigned long long scan[LI_NW + 1];
+    int lb_found[LI_NW];
+    TileBracket brk;
+    int tile, wl_n, wl_heavy;
+    int brk_on, brk_skip;
+    int p_tile;                          // pending tile (staged, not yet copied out), -1 = none
+    uint32_t p_total, p_nq;
+};
+
+// Warp 0: search the tile's first query and stage the LI_WIN blocks from its lower bound.
+// Out of line on purpose: it runs once per tile and must not share the search loop's registers.
+template <bool THICK>
+__device__ __noinline__ void stage_bracket(const LiftArgs &A, LiftSmem<THICK> &S, int tile) {
+    const TableView &T = A.T;
+    const uint32_t qf = (uint32_t)tile * LI_TILE;
+    const int tc_f = __ldg(A.tcid + qf), st_f = __ldg(A.start + qf);
+    const bool valid = tc_f >= 0 && tc_f < T.ntc;
+    int L = 0, cend = 0;
+    if (valid) {
+        const int4 cm = load_cmeta(T, tc_f);
+        L = lower_gt_ey_warp(T, S.ey, cm, st_f);
+        cend = cm.y;
+    }
+    for (int i = lane_id(); i < LI_WIN; i += 32) {
+        const int j = L + i;
+        int4 b = make_int4(0x7fffffff, 0x7fffffff, 0, 0);
+        int pm = 0x7fffffff;
+        if (j < cend) {
+            b = __ldg(reinterpret_cast<const int4 *>(T.blk) + j);
+            pm = T.disjoint ? b.y : __ldg(T.pmaxKey + j);
+        }
+        S.wblk[i] = b;
+        S.wpm[i] = pm;
+    }
+    if (lane_id() == 0) S.brk = TileBracket{valid ? tc_f : -2, st_f, L, cend};
+}
+
+// Resolve the pending tile's look-back and copy its staged rows and row offsets out (coalesced
+// 128-bit stores).  The tile published its aggregate a whole tile earlier, so its predecessors
+// have long published theirs: the walk does not spin.  Block-uniform; ends with a barrier.
+template <bool THICK>
+__device__ __forceinline__ void flush_pending(const LiftArgs &A, LiftSmem<THICK> &S) {
+    const int pt = S.p_tile;
+    if (pt < 0) return;
+    const int tid = threadIdx.x;
+    const uint32_t total = S.p_total, nq = S.p_nq;
+    const uint64_t gb = lookback_resolve_block<LI_NW>(A.desc, pt, (uint64_t)total, S.lb_part, S.lb_found);
+    for (uint32_t i = tid; i < total; i += LI_TPB) {
+        const uint64_t pos = gb + i;
+        if (pos < A.rows_cap) {
+            st_stream_v4(A.rows + pos, S.st_rows[i]);
+            if (THICK) *reinterpret_cast<int2 *>(A.thick + pos) = S.st_thick[i];
+        }
+    }
+    const uint32_t q0 = (uint32_t)pt * LI_TILE + (uint32_t)tid * LI_IPT;
+    const uint32_t g32 = (uint32_t)gb;  // wraps only if rows >= 2^32 (host rejects)
+    if ((uint32_t)tid * LI_IPT + LI_IPT <= nq) {
+        const uint32_t *o = S.st_off + tid * LI_IPT;
+        st_stream_v4(A.row_offset + q0, make_int4((int)(g32 + o[0]), (int)(g32 + o[1]), (int)(g32 + o[2]), (int)(g32 + o[3])));
+    } else {
+        for (int k = 0; k < LI_IPT; k++)
+            if ((uint32_t)tid * LI_IPT + k < nq) A.row_offset[q0 + k] = g32 + S.st_off[tid * LI_IPT + k];
+    }
+    if (pt == A.ntiles - 1 && tid == 0) {
+        A.row_offset[A.n] = (uint32_t)(gb + total);
+        A.totals[0] = gb + total;
+    }
+    __syncthreads();  // the stage is free again
+    if (tid == 0) S.p_tile = -1;
+}
+
+template <bool THICK>
+__global__ void __launch_bounds__(LI_TPB, THICK ? 3 : 4) lift_intervals_kernel(const __grid_constant__ LiftArgs A) {
+    extern __shared__ __align__(16) unsigned char li_smem_raw[];
+    LiftSmem<THICK> &S = *reinterpret_cast<LiftSmem<THICK> *>(li_smem_raw);
 
     const int tid = threadIdx.x;
     const TableView &T = A.T;
-    for (int i = tid; i < T.ey_n; i += LI_TPB) s_ey[i] = __ldg(T.ey + i);
-    const int2 *const ey = s_ey;
+    for (int i = tid; i < T.ey_n; i += LI_TPB) S.ey[i] = __ldg(T.ey + i);
+    const int2 *const ey = S.ey;
+    if (tid == 0) {
+        S.brk_on = 1;
+        S.brk_skip = 0;
+        S.p_tile = -1;
+    }
 
     for (;;) {
         __syncthreads();
         if (tid == 0) {
-            s_tile = (int)atomicAdd(A.ticket, 1u);
-            s_wl_n = 0;
+            S.tile = (int)atomicAdd(A.ticket, 1u);
+            S.wl_n = 0;
+            S.wl_heavy = 0;
         }
         __syncthreads();
-        const int tile = s_tile;
-        if (tile >= A.ntiles) break;
+        const int tile = S.tile;
+        if (tile >= A.ntiles) {
+            flush_pending<THICK>(A, S);
+            break;
+        }
 
         const uint32_t q0 = (uint32_t)tile * LI_TILE + (uint32_t)tid * LI_IPT;
         int tc[LI_IPT], st[LI_IPT], en[LI_IPT];
@@ -229,20 +365,65 @@ __global__ void __launch_bounds__(LI_TPB, 4) lift_intervals_kernel(const __grid_
                 en[k] = ok ? A.end[q0 + k] : 0;
             }
         }
+        // tile bracket: warp 0 searches the tile's first query and stages the LI_WIN blocks from its
+        // lower bound (block-uniform switch; a CTA whose tiles do not use it — unsorted batches —
+        // turns it off and retries every LI_BRK_RETRY tiles)
+        const bool brk_on = S.brk_on != 0;
+        if (brk_on) {
+            if (warp_id() == 0) stage_bracket<THICK>(A, S, tile);
+            __syncthreads();
+        }
+        const int b_tc = brk_on ? S.brk.tc : -2,
+        b_st = S.brk.st, b_L = S.brk.L, b_cend = S.brk.cend;
+
         Cand cd[LI_IPT];
         int nh[LI_IPT];
-        // row of a single-hit query, computed before the look-back is resolved
+        // row of a single-hit query
         int r_meta[LI_IPT], r_s[LI_IPT], r_e[LI_IPT];
-        uint32_t tsum = 0, unm = 0;
+        uint32_t tsum = 0, unm = 0, nwin = 0;
 #pragma unroll
         for (int k = 0; k < LI_IPT; k++) {
             Block b0;
-            // sorted batches: same contig and a start that did not move back -> the lower bound only moves
-            // forward from the previous query's (a short gallop instead of a full search)
-            if (k > 0 && tc[k] == tc[k - 1] && st[k] >= st[k - 1] && tc[k] >= 0 && tc[k] < T.ntc)
-                cd[k] = find_candidates_from(T, load_cmeta(T, tc[k]).y, cd[k - 1].lo, st[k], en[k], b0);
-            else
-                cd[k] = find_candidates_b0(T, ey, tc[k], st[k], en[k], b0);
+            // hint < 0: full search; else the lower bound is known to lie at or after block `hint`
+            // (gallop from there).  Sorted batches: same contig as the previous query and a start
+            // that did not move back -> hint = the previous lower bound.  Inside the tile bracket the
+            // lower bound comes from shared memory, and the 0- and 1-hit cases are settled there.
+            int hint = -1, cend_k = 0;
+            bool done = false;
+            if (tc[k] == b_tc && tc[k] >= 0 && st[k] >= b_st) {
+                nwin++;
+                cend_k = b_cend;
+                int j = 0;
+                if (k > 0 && tc[k] == tc[k - 1] && st[k] >= st[k - 1] && cd[k - 1].lo >= b_L) {
+                    j = min(cd[k - 1].lo - b_L, LI_WIN);
+                    while (j < LI_WIN && S.wpm[j] <= st[k]) j++;
+                } else if (S.wpm[LI_WIN - 1] <= st[k]) {
+                    j = LI_WIN;
+                } else {
+#pragma unroll
+                    for (int step = LI_WIN / 2; step > 0; step >>= 1)
+                        if (S.wpm[j + step - 1] <= st[k]) j += step;
+                }
+                // j == LI_WIN only when every slot is a real block, so b_L + j <= b_cend
+                hint = b_L + j;
+                if (j < LI_WIN - 1) {
+                    const int4 v = S.wblk[j];
+                    const int s1 = S.wblk[j + 1].x;
+                    if (v.x >= en[k] || s1 >= en[k]) {
+                        b0 = Block{v.x, v.y, v.z, v.w};
+                        cd[k].lo = hint;
+                        cd[k].hi = v.x >= en[k] ? hint : hint + 1;
+                        done = true;
+                    }
+                }
+            } else if (k > 0 && tc[k] == tc[k - 1] && st[k] >= st[k - 1] && tc[k] >= 0 && tc[k] < T.ntc) {
+                hint = cd[k - 1].lo;
+                cend_k = load_cmeta(T, tc[k]).y;
+            }
+            if (!done) {
+                if (hint >= 0) cd[k] = find_candidates_from(T, cend_k, hint, st[k], en[k], b0);
+                else cd[k] = find_candidates_b0(T, ey, tc[k], st[k], en[k], b0);
+            }
             nh[k] = count_hits(T, cd[k], st[k]);
             tsum += (uint32_t)nh[k];
             unm += (q0 + k < A.n && nh[k] == 0) ? 1u : 0u;
@@ -258,23 +439,57 @@ __global__ void __launch_bounds__(LI_TPB, 4) lift_intervals_kernel(const __grid_
                 r_e[k] = r.e;
             }
         }
-        uint32_t tile_total;
-        const uint32_t excl = block_exclusive_scan<uint32_t, LI_NW>(tsum, s_scan, &tile_total);
+        // One packed block scan carries the three per-tile sums (a warp collective behind the
+        // divergent search is only safe behind the scan's barrier, see block_exclusive_scan):
+        // bits 0-39 rows, 40-51 unmatched queries, 52-63 queries that used the bracket.
+        unsigned long long packed_total;
+        const unsigned long long packed =
+            block_exclusive_scan<unsigned long long, LI_NW>((unsigned long long)tsum | ((unsigned long long)unm << 40) |
+                                                                ((unsigned long long)nwin << 52),
+                                                            S.scan, &packed_total);
+        const uint32_t excl = (uint32_t)(packed & 0xFFFFFFFFFFull);
+        const uint32_t tile_total = (uint32_t)(packed_total & 0xFFFFFFFFFFull);
         if (warp_id() == 0) lookback_publish(A.desc, tile, (uint64_t)tile_total);
-        unm = warp_sum(unm);
-        if (lane_id() == 0 && unm) atomicAdd((unsigned long long *)(A.totals + 1), (unsigned long long)unm);
-        const uint64_t gbase = lookback_resolve_block<LI_NW>(A.desc, tile, (uint64_t)tile_total, s_lb_part, s_lb_found);
+        if (tid == 0) {
+            const unsigned tile_unm = (unsigned)(packed_total >> 40) & 0xFFFu;
+            if (tile_unm) atomicAdd((unsigned long long *)(A.totals + 1), (unsigned long long)tile_unm);
+            // bracket switch for this CTA's next tile (read again only after the barriers at the
+            // top of the loop)
+            if (brk_on) {
+                S.brk_on = (unsigned)(packed_total >> 52) >= (unsigned)LI_TILE / 2;
+                S.brk_skip = 0;
+            } else if (++S.brk_skip >= LI_BRK_RETRY) {
+                S.brk_on = 1;
+            }
+        }
+
+        // The previous tile of this CTA is resolved and copied out now, one whole search phase after
+        // it published its aggregate.
+        flush_pending<THICK>(A, S);
+
+        // A tile whose rows fit the stage is deferred the same way: rows and row offsets go to shared
+        // memory under tile-local offsets and the look-back is resolved after the NEXT tile's search.
+        // Other tiles (heavy fan-out) resolve now and write to global memory directly.
+        const bool defer = tile_total <= (uint32_t)LI_STAGE;
+        uint64_t gbase = 0;
+        RowSink sink{reinterpret_cast<swo_row *>(S.st_rows), reinterpret_cast<swo_thick *>(S.st_thick), (uint64_t)LI_STAGE};
+        if (!defer) {
+            gbase = lookback_resolve_block<LI_NW>(A.desc, tile, (uint64_t)tile_total, S.lb_part, S.lb_found);
+            sink = RowSink{A.rows, A.thick, A.rows_cap};
+        }
 
         // row_offset: four consecutive values per thread
-        uint32_t off[LI_IPT];
         {
+            uint32_t off[LI_IPT];
             uint32_t run = (uint32_t)(gbase + excl);  // wraps only if rows >= 2^32 (host rejects)
 #pragma unroll
             for (int k = 0; k < LI_IPT; k++) {
                 off[k] = run;
                 run += (uint32_t)nh[k];
             }
-            if (q0 + LI_IPT <= A.n) {
+            if (defer) {
+                *reinterpret_cast<int4 *>(S.st_off + tid * LI_IPT) = make_int4((int)off[0], (int)off[1], (int)off[2], (int)off[3]);
+            } else if (q0 + LI_IPT <= A.n) {
                 st_stream_v4(A.row_offset + q0, make_int4((int)off[0], (int)off[1], (int)off[2], (int)off[3]));
             } else {
 #pragma unroll
@@ -282,7 +497,7 @@ __global__ void __launch_bounds__(LI_TPB, 4) lift_intervals_kernel(const __grid_
                     if (q0 + k < A.n) A.row_offset[q0 + k] = off[k];
             }
         }
-        if (tile == A.ntiles - 1 && tid == 0) {
+        if (!defer && tile == A.ntiles - 1 && tid == 0) {
             const uint64_t total = gbase + tile_total;
             A.row_offset[A.n] = (uint32_t)total;
             A.totals[0] = total;
@@ -295,14 +510,16 @@ __global__ void __launch_bounds__(LI_TPB, 4) lift_intervals_kernel(const __grid_
         for (int k = 0; k < LI_IPT; k++) {
             const uint32_t q = q0 + k;
             if (nh[k] == 1) {
-                if (run64 < A.rows_cap) {
-                    st_stream_v4(A.rows + run64, make_int4(r_meta[k], r_s[k], r_e[k], (int)q));
-                    if (A.thick_s) {
+                if (run64 < sink.cap) {
+                    const int4 row = make_int4(r_meta[k], r_s[k], r_e[k], (int)q);
+                    if (defer) S.st_rows[run64] = row;
+                    else st_stream_v4(A.rows + run64, row);
+                    if (THICK) {
                         const Thick th = lift_thick_from(T, ey, tc[k], __ldg(A.thick_s + q), __ldg(A.thick_e + q), st[k],
                                                          cd[k].lo, load_cmeta(T, tc[k]).y);
                         swo_thick t;
                         thick_clamp(th, r_s[k], r_e[k], t.thick_start, t.thick_end);
-                        A.thick[run64] = t;
+                        sink.thick[run64] = t;
                     }
                 }
             } else if (nh[k] >= 2) {
@@ -312,45 +529,59 @@ __global__ void __launch_bounds__(LI_TPB, 4) lift_intervals_kernel(const __grid_
         }
         // multi-hit queries: rounds of (fill the work list, expand it cooperatively) until none is
         // pending — batches where most queries have many hits need more than one round
-        for (;;) {
-            {
-                uint64_t rb = gbase + excl;
+        if (__syncthreads_or(pending != 0)) {
+            for (;;) {
+                {
+                    uint64_t rb = excl;
 #pragma unroll
-                for (int k = 0; k < LI_IPT; k++) {
-                    if ((pending >> k) & 1u) {
-                        const int slot = atomicAdd(&s_wl_n, 1);
-                        if (slot < LI_WL_CAP) {
-                            s_wl_q[slot] = q0 + k;
-                            s_wl_lo[slot] = cd[k].lo;
-                            s_wl_cnt[slot] = cd[k].hi - cd[k].lo;
-                            s_wl_off[slot] = (uint32_t)(rb - gbase);
-                            pending &= ~(1u << k);
+                    for (int k = 0; k < LI_IPT; k++) {
+                        if ((pending >> k) & 1u) {
+                            const int slot = atomicAdd(&S.wl_n, 1);
+                            if (slot < LI_WL_CAP) {
+                                S.wl_q[slot] = q0 + k;
+                                S.wl_lo[slot] = cd[k].lo;
+                                S.wl_cnt[slot] = cd[k].hi - cd[k].lo;
+                                S.wl_off[slot] = (uint32_t)rb;
+                                if (cd[k].hi - cd[k].lo > LI_HEAVY_MIN) S.wl_heavy = 1;
+                                pending &= ~(1u << k);
+                            }
                         }
+                        rb += (uint64_t)nh[k];
                     }
-                    rb += (uint64_t)nh[k];
                 }
+                __syncthreads();
+                const int nwl = min(S.wl_n, LI_WL_CAP);
+                const bool heavy = S.wl_heavy != 0;
+                // light and medium fan-out: one warp per query
+                for (int e = warp_id(); e < nwl; e += LI_NW) {
+                    if (S.wl_cnt[e] <= LI_HEAVY_MIN)
+                        expand_query_coop<false, THICK>(A, sink, ey, S.wl_q[e], S.wl_lo[e], S.wl_cnt[e], gbase + S.wl_off[e],
+                                                        S.xscr + warp_id() * LI_HEAVY_MIN, nullptr, lane_id(), 32);
+                }
+                if (heavy) {
+                    __syncthreads();
+                    // heavy fan-out: the whole block per query
+                    for (int e = 0; e < nwl; e++) {
+                        if (S.wl_cnt[e] <= LI_HEAVY_MIN) continue;
+                        if (S.wl_cnt[e] <= LI_XSCR)
+                            expand_query_coop<true, THICK>(A, sink, ey, S.wl_q[e], S.wl_lo[e], S.wl_cnt[e], gbase + S.wl_off[e],
+                                                           S.xscr, reinterpret_cast<uint32_t *>(S.scan), tid, LI_TPB);
+                        else
+                            expand_query<THICK>(A, sink, ey, S.wl_q[e], S.wl_lo[e], S.wl_cnt[e], gbase + S.wl_off[e], tid, LI_TPB);
+                    }
+                }
+                if (!__syncthreads_or(pending != 0)) break;
+                if (tid == 0) {
+                    S.wl_n = 0;
+                    S.wl_heavy = 0;
+                }
+                __syncthreads();
             }
-        __syncthreads();
-        const int nwl = min(s_wl_n, LI_WL_CAP);
-        // light and medium fan-out: one warp per query
-        for (int e = warp_id(); e < nwl; e += LI_NW) {
-            if (s_wl_cnt[e] <= LI_HEAVY_MIN)
-                expand_query_coop<false>(A, ey, s_wl_q[e], s_wl_lo[e], s_wl_cnt[e], gbase + s_wl_off[e],
-                                         s_xscr + warp_id() * LI_HEAVY_MIN, nullptr, lane_id(), 32);
         }
-        if (nwl > 0) __syncthreads();
-        // heavy fan-out: the whole block per query
-        for (int e = 0; e < nwl; e++) {
-            if (s_wl_cnt[e] <= LI_HEAVY_MIN) continue;
-            if (s_wl_cnt[e] <= LI_XSCR)
-                expand_query_coop<true>(A, ey, s_wl_q[e], s_wl_lo[e], s_wl_cnt[e], gbase + s_wl_off[e], s_xscr, s_scan, tid,
-                                        LI_TPB);
-            else
-                expand_query(A, ey, s_wl_q[e], s_wl_lo[e], s_wl_cnt[e], gbase + s_wl_off[e], tid, LI_TPB);
-        }
-            if (!__syncthreads_or(pending != 0)) break;
-            if (tid == 0) s_wl_n = 0;
-            __syncthreads();
+        if (defer && tid == 0) {
+            S.p_tile = tile;
+            S.p_total = tile_total;
+            S.p_nq = min((uint32_t)LI_TILE, A.n - (uint32_t)tile * LI_TILE);
         }
     }
 }

@@ -105,7 +105,7 @@ struct Device {
     PinBuf h_sizes;  // N_SLOTS * 6 u64
     // per-shard host output arenas (multi-shard runs)
     PinBuf a_lifted, a_unm;
-    int text_grid = 0, bin_grid = 0;
+    int text_grid = 0, bin_grid[2] = {0, 0};
 };
 
 }  // namespace
@@ -285,13 +285,22 @@ int launch_lift_intervals(swo_ctx *c, Device &d, size_t n, const int32_t *tcid, 
     A.ticket = d.scratch.as<unsigned>();
     A.desc = reinterpret_cast<uint64_t *>(d.scratch.as<char>() + 16);
     A.totals = totals;
-    if (!d.bin_grid) {
+    const int v = ths ? 1 : 0;  // kernel variant: with / without the thick columns
+    const size_t smem = v ? sizeof(LiftSmem<true>) : sizeof(LiftSmem<false>);
+    if (!d.bin_grid[v]) {
         int per = 0;
-        CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, lift_intervals_kernel, LI_TPB, 0));
-        d.bin_grid = std::max(1, per) * d.sms;
+        if (v) {
+            CK(c, cudaFuncSetAttribute(lift_intervals_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, lift_intervals_kernel<true>, LI_TPB, smem));
+        } else {
+            CK(c, cudaFuncSetAttribute(lift_intervals_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, lift_intervals_kernel<false>, LI_TPB, smem));
+        }
+        d.bin_grid[v] = std::max(1, per) * d.sms;
     }
-    const int grid = std::min(ntiles, d.bin_grid);
-    lift_intervals_kernel<<<grid, LI_TPB, 0, st>>>(A);
+    const int grid = std::min(ntiles, d.bin_grid[v]);
+    if (v) lift_intervals_kernel<true><<<grid, LI_TPB, smem, st>>>(A);
+    else lift_intervals_kernel<false><<<grid, LI_TPB, smem, st>>>(A);
     c->launches++;
     CK(c, cudaGetLastError());
     return SWO_OK;
