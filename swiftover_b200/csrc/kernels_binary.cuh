@@ -5,7 +5,8 @@
 //   liftCoordOnly x2 for thickStart/End  bed.d:134-148, chain.d:637-654
 //   sort by qStart, orderStartEnd, strand table, thick clamp   bed.d:156-196
 //
-// One persistent kernel.  A tile is 1024 consecutive queries (256 threads x 4,
+// One persistent kernel in two variants (sorted / unsorted batches, picked on the device by
+// sample_sorted_kernel).  A tile is 1024 consecutive queries (256 threads x 4,
 // 128-bit loads).  Each thread searches its four queries (Eytzinger upper levels
 // in shared memory + quaternary bottom search; in sorted batches queries 2-4
 // gallop forward from the previous lower bound), computes the rows of its
@@ -32,9 +33,7 @@ constexpr int LI_NW = LI_TPB / 32;
 constexpr int LI_WL_CAP = 256;      // multi-hit queries queued per tile
 constexpr int LI_HEAVY_MIN = 128;   // candidates above this: the whole block expands the query
 constexpr int LI_XSCR = 1024;       // shared-memory sort scratch (= LI_NW warp regions of LI_HEAVY_MIN)
-constexpr int LI_WIN = 64;          // blocks of the tile bracket staged in shared memory (sorted batches)
 constexpr int LI_STAGE = 1152;       // rows of a tile staged in shared memory for the deferred copy-out
-constexpr int LI_BRK_RETRY = 16;    // a CTA that switched the bracket off tries it again every this many tiles
 
 struct LiftArgs {
     TableView T;
@@ -50,6 +49,7 @@ struct LiftArgs {
     uint64_t *desc;     // [ntiles] look-back descriptors, zeroed
     unsigned *ticket;   // zeroed
     uint64_t *totals;   // [0] rows, [1] unmatched   (zeroed)
+    const uint32_t *sorted_flag;  // written by sample_sorted_kernel: which kernel variant does the work
 };
 
 // Where a tile's rows go: global memory (positions are global row indices) or the tile's
@@ -198,99 +198,32 @@ __device__ __noinline__ void expand_query_coop(const LiftArgs &A, const RowSink 
 }
 
 
-// lower_gt_ey for a whole warp with one (uniform) key: the Eytzinger descent is the same, the
-// group of S <= 32 keys is settled by one coalesced load and a ballot instead of three
-// dependent probe rounds.
-__device__ __forceinline__ int lower_gt_ey_warp(const TableView &T, const int2 *__restrict__ ey, const int4 cm, int x) {
-    if (T.ey_shift > 5) return lower_gt_ey(T, ey, cm, x);
-    const int b = cm.y, m = cm.w;
-    const int2 *__restrict__ e = ey + cm.z - 1;  // 1-based
-    int k = 1;
-    while (k <= m) k = 2 * k + (e[k].x <= x ? 1 : 0);
-    k >>= __ffs(~k);
-    int lo, hi;  // answer in [lo,hi], hi == b means "none"
-    if (k) {
-        hi = e[k].y;
-        lo = hi - ((1 << T.ey_shift) - 1);
-    } else {
-        lo = cm.x + (m << T.ey_shift);
-        hi = b;
-    }
-    const int j = lo + lane_id();
-    const bool gt = j < hi && j < b && __ldg(T.pmaxKey + j) > x;
-    const unsigned mask = __ballot_sync(FULL, gt);
-    return mask ? lo + __ffs(mask) - 1 : hi;
-}
-
-// Tile bracket (sorted batches): the blocks a sorted tile can touch start at the lower bound L of
-// its first query; LI_WIN of them are staged in shared memory, so that every query of the tile
-// that names the same contig and does not start earlier finds its candidates with shared-memory
-// probes only (a merge of the tile's queries against its slice of the table).  Slots past the
-// contig's last block hold sentinels (no query reaches them as a hit).
-struct TileBracket {
-    int tc;    // contig of the bracket, -2 = none
-    int st;    // start of the tile's first query
-    int L;     // global index of window slot 0
-    int cend;  // contig's block end
-};
-
-// Shared memory of one CTA (dynamic: > 48 KiB).  The 16-byte aligned arrays come first.
-template <bool THICK>
+// Shared memory of one CTA (dynamic: > 48 KiB with the stage).  The 16-byte aligned arrays come first.
+template <bool THICK, bool DEFER>
 struct LiftSmem {
-    int4 wblk[LI_WIN];                   // tile bracket: blocks L .. L+LI_WIN-1
-    int4 st_rows[LI_STAGE];              // staged rows of the pending tile (index = row offset inside the tile)
-    uint32_t st_off[LI_TILE];            //   and the tile-local row offset of each of its queries
-    int2 st_thick[THICK ? LI_STAGE : 1];
+    int4 st_rows[DEFER ? LI_STAGE : 1];  // staged rows of the pending tile (index = row offset inside the tile)
+    uint32_t st_off[DEFER ? LI_TILE : 4];  //   and the tile-local row offset of each of its queries
+    int2 st_thick[DEFER && THICK ? LI_STAGE : 1];
     int2 ey[ChainTable::EY_CAP];         // upper search levels (Eytzinger order)
     unsigned long long xscr[LI_XSCR];    // sort scratch of the multi-hit expansion
     unsigned long long lb_part[LI_NW];
-    int wpm[LI_WIN];                     // pmaxKey of the bracket's blocks
+    unsigned long long scan[LI_NW + 1];
     uint32_t wl_q[LI_WL_CAP];
     int wl_lo[LI_WL_CAP];
     int wl_cnt[LI_WL_CAP];
     uint32_t wl_off[LI_WL_CAP];
-    unsigned long long scan[LI_NW + 1];
     int lb_found[LI_NW];
-    TileBracket brk;
     int tile, wl_n, wl_heavy;
-    int brk_on, brk_skip;
     int p_tile;                          // pending tile (staged, not yet copied out), -1 = none
     uint32_t p_total, p_nq;
 };
 
-// Warp 0: search the tile's first query and stage the LI_WIN blocks from its lower bound.
-// Out of line on purpose: it runs once per tile and must not share the search loop's registers.
-template <bool THICK>
-__device__ __noinline__ void stage_bracket(const LiftArgs &A, LiftSmem<THICK> &S, int tile) {
-    const TableView &T = A.T;
-    const uint32_t qf = (uint32_t)tile * LI_TILE;
-    const int tc_f = __ldg(A.tcid + qf), st_f = __ldg(A.start + qf);
-    const bool valid = tc_f >= 0 && tc_f < T.ntc;
-    int L = 0, cend = 0;
-    if (valid) {
-        const int4 cm = load_cmeta(T, tc_f);
-        L = lower_gt_ey_warp(T, S.ey, cm, st_f);
-        cend = cm.y;
-    }
-    for (int i = lane_id(); i < LI_WIN; i += 32) {
-        const int j = L + i;
-        int4 b = make_int4(0x7fffffff, 0x7fffffff, 0, 0);
-        int pm = 0x7fffffff;
-        if (j < cend) {
-            b = __ldg(reinterpret_cast<const int4 *>(T.blk) + j);
-            pm = T.disjoint ? b.y : __ldg(T.pmaxKey + j);
-        }
-        S.wblk[i] = b;
-        S.wpm[i] = pm;
-    }
-    if (lane_id() == 0) S.brk = TileBracket{valid ? tc_f : -2, st_f, L, cend};
-}
-
 // Resolve the pending tile's look-back and copy its staged rows and row offsets out (coalesced
 // 128-bit stores).  The tile published its aggregate a whole tile earlier, so its predecessors
 // have long published theirs: the walk does not spin.  Block-uniform; ends with a barrier.
-template <bool THICK>
-__device__ __forceinline__ void flush_pending(const LiftArgs &A, LiftSmem<THICK> &S) {
+template <bool THICK, bool DEFER>
+__device__ __forceinline__ void flush_pending(const LiftArgs &A, LiftSmem<THICK, DEFER> &S) {
+    if (!DEFER) return;
     const int pt = S.p_tile;
     if (pt < 0) return;
     const int tid = threadIdx.x;
@@ -320,20 +253,40 @@ __device__ __forceinline__ void flush_pending(const LiftArgs &A, LiftSmem<THICK>
     if (tid == 0) S.p_tile = -1;
 }
 
-template <bool THICK>
-__global__ void __launch_bounds__(LI_TPB, THICK ? 3 : 4) lift_intervals_kernel(const __grid_constant__ LiftArgs A) {
+// Is the batch (mostly) sorted by position?  256 threads look at 2048 adjacent pairs spread over
+// the batch; a pair counts when both queries name the same contig and the start does not move
+// back.  *flag = 1 when at least 7 of 8 pairs do.  Decides which kernel variant does the work.
+__global__ void __launch_bounds__(256) sample_sorted_kernel(const int32_t *__restrict__ tcid, const int32_t *__restrict__ start,
+                                                            uint32_t n, uint32_t *flag) {
+    __shared__ unsigned s_cnt;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    unsigned ok = 0;
+    const uint32_t pairs = n > 1 ? n - 1 : 0, want = pairs < 2048u ? pairs : 2048u;
+    for (uint32_t j = threadIdx.x; j < want; j += 256) {
+        const uint32_t i = (uint32_t)(((unsigned long long)j * pairs) / want);
+        ok += (__ldg(tcid + i) == __ldg(tcid + i + 1) && __ldg(start + i) <= __ldg(start + i + 1)) ? 1u : 0u;
+    }
+    atomicAdd(&s_cnt, ok);
+    __syncthreads();
+    if (threadIdx.x == 0) *flag = (s_cnt * 8u >= want * 7u) ? 1u : 0u;
+}
+
+// DEFER = the variant for sorted batches (A.sorted_flag says which variant works; the other one
+// returns at once): a tile's rows and row offsets are staged in shared memory and its look-back
+// is resolved one tile later.  The other variant resolves every tile right after its scan and
+// keeps the shared memory for L1 (random probes of the block table).
+template <bool THICK, bool DEFER>
+__global__ void __launch_bounds__(LI_TPB, THICK && DEFER ? 3 : 4) lift_intervals_kernel(const __grid_constant__ LiftArgs A) {
     extern __shared__ __align__(16) unsigned char li_smem_raw[];
-    LiftSmem<THICK> &S = *reinterpret_cast<LiftSmem<THICK> *>(li_smem_raw);
+    LiftSmem<THICK, DEFER> &S = *reinterpret_cast<LiftSmem<THICK, DEFER> *>(li_smem_raw);
+    if ((__ldg(A.sorted_flag) != 0u) != DEFER) return;
 
     const int tid = threadIdx.x;
     const TableView &T = A.T;
     for (int i = tid; i < T.ey_n; i += LI_TPB) S.ey[i] = __ldg(T.ey + i);
     const int2 *const ey = S.ey;
-    if (tid == 0) {
-        S.brk_on = 1;
-        S.brk_skip = 0;
-        S.p_tile = -1;
-    }
+    if (tid == 0) S.p_tile = -1;
 
     for (;;) {
         __syncthreads();
@@ -345,7 +298,7 @@ __global__ void __launch_bounds__(LI_TPB, THICK ? 3 : 4) lift_intervals_kernel(c
         __syncthreads();
         const int tile = S.tile;
         if (tile >= A.ntiles) {
-            flush_pending<THICK>(A, S);
+            flush_pending<THICK, DEFER>(A, S);
             break;
         }
 
@@ -365,65 +318,20 @@ __global__ void __launch_bounds__(LI_TPB, THICK ? 3 : 4) lift_intervals_kernel(c
                 en[k] = ok ? A.end[q0 + k] : 0;
             }
         }
-        // tile bracket: warp 0 searches the tile's first query and stages the LI_WIN blocks from its
-        // lower bound (block-uniform switch; a CTA whose tiles do not use it — unsorted batches —
-        // turns it off and retries every LI_BRK_RETRY tiles)
-        const bool brk_on = S.brk_on != 0;
-        if (brk_on) {
-            if (warp_id() == 0) stage_bracket<THICK>(A, S, tile);
-            __syncthreads();
-        }
-        const int b_tc = brk_on ? S.brk.tc : -2,
-        b_st = S.brk.st, b_L = S.brk.L, b_cend = S.brk.cend;
-
         Cand cd[LI_IPT];
         int nh[LI_IPT];
         // row of a single-hit query
         int r_meta[LI_IPT], r_s[LI_IPT], r_e[LI_IPT];
-        uint32_t tsum = 0, unm = 0, nwin = 0;
+        uint32_t tsum = 0, unm = 0;
 #pragma unroll
         for (int k = 0; k < LI_IPT; k++) {
             Block b0;
-            // hint < 0: full search; else the lower bound is known to lie at or after block `hint`
-            // (gallop from there).  Sorted batches: same contig as the previous query and a start
-            // that did not move back -> hint = the previous lower bound.  Inside the tile bracket the
-            // lower bound comes from shared memory, and the 0- and 1-hit cases are settled there.
-            int hint = -1, cend_k = 0;
-            bool done = false;
-            if (tc[k] == b_tc && tc[k] >= 0 && st[k] >= b_st) {
-                nwin++;
-                cend_k = b_cend;
-                int j = 0;
-                if (k > 0 && tc[k] == tc[k - 1] && st[k] >= st[k - 1] && cd[k - 1].lo >= b_L) {
-                    j = min(cd[k - 1].lo - b_L, LI_WIN);
-                    while (j < LI_WIN && S.wpm[j] <= st[k]) j++;
-                } else if (S.wpm[LI_WIN - 1] <= st[k]) {
-                    j = LI_WIN;
-                } else {
-#pragma unroll
-                    for (int step = LI_WIN / 2; step > 0; step >>= 1)
-                        if (S.wpm[j + step - 1] <= st[k]) j += step;
-                }
-                // j == LI_WIN only when every slot is a real block, so b_L + j <= b_cend
-                hint = b_L + j;
-                if (j < LI_WIN - 1) {
-                    const int4 v = S.wblk[j];
-                    const int s1 = S.wblk[j + 1].x;
-                    if (v.x >= en[k] || s1 >= en[k]) {
-                        b0 = Block{v.x, v.y, v.z, v.w};
-                        cd[k].lo = hint;
-                        cd[k].hi = v.x >= en[k] ? hint : hint + 1;
-                        done = true;
-                    }
-                }
-            } else if (k > 0 && tc[k] == tc[k - 1] && st[k] >= st[k - 1] && tc[k] >= 0 && tc[k] < T.ntc) {
-                hint = cd[k - 1].lo;
-                cend_k = load_cmeta(T, tc[k]).y;
-            }
-            if (!done) {
-                if (hint >= 0) cd[k] = find_candidates_from(T, cend_k, hint, st[k], en[k], b0);
-                else cd[k] = find_candidates_b0(T, ey, tc[k], st[k], en[k], b0);
-            }
+            // sorted batches: same contig and a start that did not move back -> the lower bound only moves
+            // forward from the previous query's (a short gallop instead of a full search)
+            if (k > 0 && tc[k] == tc[k - 1] && st[k] >= st[k - 1] && tc[k] >= 0 && tc[k] < T.ntc)
+                cd[k] = find_candidates_from(T, load_cmeta(T, tc[k]).y, cd[k - 1].lo, st[k], en[k], b0);
+            else
+                cd[k] = find_candidates_b0(T, ey, tc[k], st[k], en[k], b0);
             nh[k] = count_hits(T, cd[k], st[k]);
             tsum += (uint32_t)nh[k];
             unm += (q0 + k < A.n && nh[k] == 0) ? 1u : 0u;
@@ -439,38 +347,28 @@ __global__ void __launch_bounds__(LI_TPB, THICK ? 3 : 4) lift_intervals_kernel(c
                 r_e[k] = r.e;
             }
         }
-        // One packed block scan carries the three per-tile sums (a warp collective behind the
-        // divergent search is only safe behind the scan's barrier, see block_exclusive_scan):
-        // bits 0-39 rows, 40-51 unmatched queries, 52-63 queries that used the bracket.
+        // One packed block scan carries both per-tile sums (a warp collective behind the divergent
+        // search is only safe behind the scan's barrier, see block_exclusive_scan):
+        // bits 0-39 rows, 40-51 unmatched queries.
         unsigned long long packed_total;
-        const unsigned long long packed =
-            block_exclusive_scan<unsigned long long, LI_NW>((unsigned long long)tsum | ((unsigned long long)unm << 40) |
-                                                                ((unsigned long long)nwin << 52),
-                                                            S.scan, &packed_total);
+        const unsigned long long packed = block_exclusive_scan<unsigned long long, LI_NW>(
+            (unsigned long long)tsum | ((unsigned long long)unm << 40), S.scan, &packed_total);
         const uint32_t excl = (uint32_t)(packed & 0xFFFFFFFFFFull);
         const uint32_t tile_total = (uint32_t)(packed_total & 0xFFFFFFFFFFull);
         if (warp_id() == 0) lookback_publish(A.desc, tile, (uint64_t)tile_total);
         if (tid == 0) {
             const unsigned tile_unm = (unsigned)(packed_total >> 40) & 0xFFFu;
             if (tile_unm) atomicAdd((unsigned long long *)(A.totals + 1), (unsigned long long)tile_unm);
-            // bracket switch for this CTA's next tile (read again only after the barriers at the
-            // top of the loop)
-            if (brk_on) {
-                S.brk_on = (unsigned)(packed_total >> 52) >= (unsigned)LI_TILE / 2;
-                S.brk_skip = 0;
-            } else if (++S.brk_skip >= LI_BRK_RETRY) {
-                S.brk_on = 1;
-            }
         }
 
         // The previous tile of this CTA is resolved and copied out now, one whole search phase after
         // it published its aggregate.
-        flush_pending<THICK>(A, S);
+        flush_pending<THICK, DEFER>(A, S);
 
         // A tile whose rows fit the stage is deferred the same way: rows and row offsets go to shared
         // memory under tile-local offsets and the look-back is resolved after the NEXT tile's search.
         // Other tiles (heavy fan-out) resolve now and write to global memory directly.
-        const bool defer = tile_total <= (uint32_t)LI_STAGE;
+        const bool defer = DEFER && tile_total <= (uint32_t)LI_STAGE;
         uint64_t gbase = 0;
         RowSink sink{reinterpret_cast<swo_row *>(S.st_rows), reinterpret_cast<swo_thick *>(S.st_thick), (uint64_t)LI_STAGE};
         if (!defer) {

@@ -105,7 +105,7 @@ struct Device {
     PinBuf h_sizes;  // N_SLOTS * 6 u64
     // per-shard host output arenas (multi-shard runs)
     PinBuf a_lifted, a_unm;
-    int text_grid = 0, bin_grid[2] = {0, 0};
+    int text_grid = 0, bin_grid[4] = {0, 0, 0, 0};
 };
 
 }  // namespace
@@ -285,23 +285,34 @@ int launch_lift_intervals(swo_ctx *c, Device &d, size_t n, const int32_t *tcid, 
     A.ticket = d.scratch.as<unsigned>();
     A.desc = reinterpret_cast<uint64_t *>(d.scratch.as<char>() + 16);
     A.totals = totals;
-    const int v = ths ? 1 : 0;  // kernel variant: with / without the thick columns
-    const size_t smem = v ? sizeof(LiftSmem<true>) : sizeof(LiftSmem<false>);
-    if (!d.bin_grid[v]) {
-        int per = 0;
-        if (v) {
-            CK(c, cudaFuncSetAttribute(lift_intervals_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, lift_intervals_kernel<true>, LI_TPB, smem));
-        } else {
-            CK(c, cudaFuncSetAttribute(lift_intervals_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, lift_intervals_kernel<false>, LI_TPB, smem));
-        }
-        d.bin_grid[v] = std::max(1, per) * d.sms;
-    }
-    const int grid = std::min(ntiles, d.bin_grid[v]);
-    if (v) lift_intervals_kernel<true><<<grid, LI_TPB, smem, st>>>(A);
-    else lift_intervals_kernel<false><<<grid, LI_TPB, smem, st>>>(A);
+    // sortedness sample -> flag word behind the look-back descriptors; both variants of the kernel
+    // are launched and the one the flag does not name returns at once (no host round trip)
+    uint32_t *flag = reinterpret_cast<uint32_t *>(d.scratch.as<char>() + 8);
+    A.sorted_flag = flag;
+    sample_sorted_kernel<<<1, 256, 0, st>>>(tcid, start, (uint32_t)n, flag);
     c->launches++;
+    const int th = ths ? 1 : 0;
+    for (int defer = 0; defer < 2; defer++) {
+        const int v = th * 2 + defer;
+        const void *fn = v == 0   ? (const void *)lift_intervals_kernel<false, false>
+                         : v == 1 ? (const void *)lift_intervals_kernel<false, true>
+                         : v == 2 ? (const void *)lift_intervals_kernel<true, false>
+                                  : (const void *)lift_intervals_kernel<true, true>;
+        const size_t smem = v == 0   ? sizeof(LiftSmem<false, false>)
+                            : v == 1 ? sizeof(LiftSmem<false, true>)
+                            : v == 2 ? sizeof(LiftSmem<true, false>)
+                                     : sizeof(LiftSmem<true, true>);
+        if (!d.bin_grid[v]) {
+            int per = 0;
+            CK(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, fn, LI_TPB, smem));
+            d.bin_grid[v] = std::max(1, per) * d.sms;
+        }
+        const int grid = std::min(ntiles, d.bin_grid[v]);
+        void *args[] = {(void *)&A};
+        CK(c, cudaLaunchKernel(fn, dim3(grid), dim3(LI_TPB), args, smem, st));
+        c->launches++;
+    }
     CK(c, cudaGetLastError());
     return SWO_OK;
 }
