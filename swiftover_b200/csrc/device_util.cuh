@@ -55,22 +55,12 @@ __device__ __forceinline__ T warp_sum(T v) {
 // Exclusive scan of one value per thread over a block of NWARPS*32 threads.
 // `scratch` is NWARPS+1 elements of shared memory.  Returns the exclusive prefix;
 // *total receives the block sum (same value in every thread).
-// Contains two block barriers; safe to call repeatedly with the same scratch.
-//
-// The first barrier is a barrier-with-vote whose result gates the shuffles.  That is on
-// purpose: with a plain __syncthreads() ptxas (12.9, sm_100a) schedules the first SHFL of the
-// warp scan ABOVE the BAR.SYNC and elides a __syncwarp() in front of it (it takes the warp for
-// converged behind a BSYNC.RECONVERGENT), so after a long divergent region — per-thread block
-// searches — early lanes read a neighbour's register before that lane had produced its value
-// and the scan came out short (seen in lift_intervals_kernel: per-thread counts right, prefix
-// wrong).  Shuffles that are control-dependent on the barrier's result cannot move above it.
+// Contains two __syncthreads(); safe to call repeatedly with the same scratch.
+// Warp shuffles: only for call sites whose lanes arrive together (see block_exclusive_scan_lds).
 template <typename T, int NWARPS>
 __device__ __forceinline__ T block_exclusive_scan(T v, T *scratch, T *total) {
-    if (!__syncthreads_or(v != 0)) {  // also: previous users of scratch are done
-        *total = 0;
-        return 0;
-    }
     const T inc = warp_inclusive_scan(v);
+    __syncthreads();  // previous users of scratch are done
     if (lane_id() == 31) scratch[warp_id()] = inc;
     __syncthreads();
     T wbase = 0, tot = 0;
@@ -82,6 +72,46 @@ __device__ __forceinline__ T block_exclusive_scan(T v, T *scratch, T *total) {
     }
     *total = tot;
     return wbase + inc - v;
+}
+
+// The same scan of 32-bit values without any warp collective: every thread parks its value in
+// shared memory, and after a block barrier adds up the values of the lower lanes of its warp
+// (eight 128-bit broadcast loads) and the totals of the lower warps.
+// For use right behind long divergent per-thread work (the block-table searches).  There the
+// shuffle version is not safe with ptxas 12.9 / sm_100a: it issues the scan's first SHFL behind a
+// BSYNC.RECONVERGENT, ahead of the barrier and without a WARPSYNC (an explicit __syncwarp() is
+// dropped as redundant), and lanes that got there early read a neighbour's register before it
+// held its value — per-thread counts right, prefix short (seen in lift_intervals_kernel on
+// batches with heavy multi-hit queries).  Gating the shuffles on a barrier-with-vote result keeps
+// them behind the barrier but makes ptxas add a BRA.DIV / WARPSYNC.COLLECTIVE slow path, which
+// raised "illegal instruction" on half-sorted batches.  Shared memory and block barriers only
+// depend on every THREAD having arrived.
+// vals: NWARPS*32 words (16-byte aligned), wtot: NWARPS words.  Two block barriers.
+template <int NWARPS>
+__device__ __forceinline__ uint32_t block_exclusive_scan_lds(uint32_t v, uint32_t *vals, uint32_t *wtot, uint32_t *total) {
+    const int lane = lane_id(), w = warp_id();
+    vals[threadIdx.x] = v;
+    __syncthreads();
+    const uint4 *row = reinterpret_cast<const uint4 *>(vals + w * 32);
+    uint32_t below = 0, all = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const uint4 x = row[i];
+        below += (4 * i + 0 < lane ? x.x : 0u) + (4 * i + 1 < lane ? x.y : 0u) + (4 * i + 2 < lane ? x.z : 0u) +
+                 (4 * i + 3 < lane ? x.w : 0u);
+        all += x.x + x.y + x.z + x.w;
+    }
+    if (lane == 0) wtot[w] = all;
+    __syncthreads();
+    uint32_t wbase = 0, tot = 0;
+#pragma unroll
+    for (int k = 0; k < NWARPS; k++) {
+        const uint32_t s = wtot[k];
+        if (k < w) wbase += s;
+        tot += s;
+    }
+    *total = tot;
+    return wbase + below;
 }
 
 // ---- decoupled look-back ---------------------------------------------------

@@ -30,7 +30,10 @@ constexpr int LI_TPB = 256;
 constexpr int LI_IPT = 4;
 constexpr int LI_TILE = LI_TPB * LI_IPT;
 constexpr int LI_NW = LI_TPB / 32;
-constexpr int LI_WL_CAP = 256;      // multi-hit queries queued per tile
+#ifndef LI_WL_CAP_OVR
+#define LI_WL_CAP_OVR 256
+#endif
+constexpr int LI_WL_CAP = LI_WL_CAP_OVR;      // multi-hit queries queued per tile
 constexpr int LI_HEAVY_MIN = 128;   // candidates above this: the whole block expands the query
 constexpr int LI_XSCR = 1024;       // shared-memory sort scratch (= LI_NW warp regions of LI_HEAVY_MIN)
 constexpr int LI_STAGE = 1152;       // rows of a tile staged in shared memory for the deferred copy-out
@@ -50,7 +53,20 @@ struct LiftArgs {
     unsigned *ticket;   // zeroed
     uint64_t *totals;   // [0] rows, [1] unmatched   (zeroed)
     const uint32_t *sorted_flag;  // written by sample_sorted_kernel: which kernel variant does the work
+    unsigned full_mask;           // 0xffffffff, as a run-time value: see converge()
 };
+
+// Reconverge the warp behind long divergent per-thread work, before a block barrier (bar.sync
+// counts arrivals per WARP, so a split warp arriving twice breaks the barrier) or a warp
+// collective.  Out of line and with the mask as a run-time value on purpose: ptxas 12.9 (sm_100a)
+// drops a __syncwarp() — also one with a mask it cannot see through — wherever it takes the warp
+// for converged (behind a BSYNC.RECONVERGENT), and it is not always right: on tiles whose lanes
+// mix the hinted and the full search one lane was seen (progress markers in host-mapped memory)
+// still behind the search loop while the other 31 had passed the scan's barriers; the block
+// scan came out short or the kernel died with "illegal instruction".  Inside a function that is
+// not inlined nothing is known about the callers' convergence, so the WARPSYNC stays.
+__device__ __noinline__ void converge_warp(unsigned mask) { __syncwarp(mask); }
+__device__ __forceinline__ void converge(const LiftArgs &A) { converge_warp(A.full_mask); }
 
 // Where a tile's rows go: global memory (positions are global row indices) or the tile's
 // shared-memory stage (positions are offsets inside the tile).
@@ -136,8 +152,8 @@ __device__ __noinline__ void expand_query_coop(const LiftArgs &A, const RowSink 
         }
         scr[c] = key;
     }
+    converge(A);
     if (BLOCK) __syncthreads();
-    else __syncwarp();
     bool mine = true;
     for (int c = first; c < P; c += stride)
         if (c > 0 && scr[c - 1] > scr[c]) mine = false;
@@ -155,8 +171,8 @@ __device__ __noinline__ void expand_query_coop(const LiftArgs &A, const RowSink 
                         }
                     }
                 }
+                converge(A);
                 if (BLOCK) __syncthreads();
-                else __syncwarp();
             }
         }
     }
@@ -201,18 +217,21 @@ __device__ __noinline__ void expand_query_coop(const LiftArgs &A, const RowSink 
 // Shared memory of one CTA (dynamic: > 48 KiB with the stage).  The 16-byte aligned arrays come first.
 template <bool THICK, bool DEFER>
 struct LiftSmem {
+    uint32_t scan_vals[LI_TPB];          // block scan: one value per thread
     int4 st_rows[DEFER ? LI_STAGE : 1];  // staged rows of the pending tile (index = row offset inside the tile)
     uint32_t st_off[DEFER ? LI_TILE : 4];  //   and the tile-local row offset of each of its queries
     int2 st_thick[DEFER && THICK ? LI_STAGE : 1];
     int2 ey[ChainTable::EY_CAP];         // upper search levels (Eytzinger order)
     unsigned long long xscr[LI_XSCR];    // sort scratch of the multi-hit expansion
     unsigned long long lb_part[LI_NW];
-    unsigned long long scan[LI_NW + 1];
+    uint32_t scan[LI_NW + 1];            // scratch of the block scan inside the heavy expansion
     uint32_t wl_q[LI_WL_CAP];
     int wl_lo[LI_WL_CAP];
     int wl_cnt[LI_WL_CAP];
     uint32_t wl_off[LI_WL_CAP];
     int lb_found[LI_NW];
+    uint32_t scan_wtot[LI_NW];
+    uint32_t unm;                        // unmatched queries of the tile (shared-memory atomic)
     int tile, wl_n, wl_heavy;
     int p_tile;                          // pending tile (staged, not yet copied out), -1 = none
     uint32_t p_total, p_nq;
@@ -286,7 +305,10 @@ __global__ void __launch_bounds__(LI_TPB, THICK && DEFER ? 3 : 4) lift_intervals
     const TableView &T = A.T;
     for (int i = tid; i < T.ey_n; i += LI_TPB) S.ey[i] = __ldg(T.ey + i);
     const int2 *const ey = S.ey;
-    if (tid == 0) S.p_tile = -1;
+    if (tid == 0) {
+        S.p_tile = -1;
+        S.unm = 0;
+    }
 
     for (;;) {
         __syncthreads();
@@ -347,18 +369,17 @@ __global__ void __launch_bounds__(LI_TPB, THICK && DEFER ? 3 : 4) lift_intervals
                 r_e[k] = r.e;
             }
         }
-        // One packed block scan carries both per-tile sums (a warp collective behind the divergent
-        // search is only safe behind the scan's barrier, see block_exclusive_scan):
-        // bits 0-39 rows, 40-51 unmatched queries.
-        unsigned long long packed_total;
-        const unsigned long long packed = block_exclusive_scan<unsigned long long, LI_NW>(
-            (unsigned long long)tsum | ((unsigned long long)unm << 40), S.scan, &packed_total);
-        const uint32_t excl = (uint32_t)(packed & 0xFFFFFFFFFFull);
-        const uint32_t tile_total = (uint32_t)(packed_total & 0xFFFFFFFFFFull);
+        converge(A);
+        // Block scan of the per-thread fan-out through shared memory (no warp collective behind the
+        // divergent searches, see block_exclusive_scan_lds); the unmatched count goes through a
+        // shared-memory atomic.
+        if (unm) atomicAdd(&S.unm, unm);
+        uint32_t tile_total;
+        const uint32_t excl = block_exclusive_scan_lds<LI_NW>(tsum, S.scan_vals, S.scan_wtot, &tile_total);
         if (warp_id() == 0) lookback_publish(A.desc, tile, (uint64_t)tile_total);
-        if (tid == 0) {
-            const unsigned tile_unm = (unsigned)(packed_total >> 40) & 0xFFFu;
-            if (tile_unm) atomicAdd((unsigned long long *)(A.totals + 1), (unsigned long long)tile_unm);
+        if (tid == 0 && S.unm) {  // every thread's atomicAdd is behind the scan's barriers
+            atomicAdd((unsigned long long *)(A.totals + 1), (unsigned long long)S.unm);
+            S.unm = 0;
         }
 
         // The previous tile of this CTA is resolved and copied out now, one whole search phase after
@@ -427,6 +448,7 @@ __global__ void __launch_bounds__(LI_TPB, THICK && DEFER ? 3 : 4) lift_intervals
         }
         // multi-hit queries: rounds of (fill the work list, expand it cooperatively) until none is
         // pending — batches where most queries have many hits need more than one round
+        converge(A);
         if (__syncthreads_or(pending != 0)) {
             for (;;) {
                 {
@@ -447,6 +469,7 @@ __global__ void __launch_bounds__(LI_TPB, THICK && DEFER ? 3 : 4) lift_intervals
                         rb += (uint64_t)nh[k];
                     }
                 }
+                converge(A);
                 __syncthreads();
                 const int nwl = min(S.wl_n, LI_WL_CAP);
                 const bool heavy = S.wl_heavy != 0;
@@ -463,11 +486,12 @@ __global__ void __launch_bounds__(LI_TPB, THICK && DEFER ? 3 : 4) lift_intervals
                         if (S.wl_cnt[e] <= LI_HEAVY_MIN) continue;
                         if (S.wl_cnt[e] <= LI_XSCR)
                             expand_query_coop<true, THICK>(A, sink, ey, S.wl_q[e], S.wl_lo[e], S.wl_cnt[e], gbase + S.wl_off[e],
-                                                           S.xscr, reinterpret_cast<uint32_t *>(S.scan), tid, LI_TPB);
+                                                           S.xscr, S.scan, tid, LI_TPB);
                         else
                             expand_query<THICK>(A, sink, ey, S.wl_q[e], S.wl_lo[e], S.wl_cnt[e], gbase + S.wl_off[e], tid, LI_TPB);
                     }
                 }
+                converge(A);
                 if (!__syncthreads_or(pending != 0)) break;
                 if (tid == 0) {
                     S.wl_n = 0;

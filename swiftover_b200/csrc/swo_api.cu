@@ -289,6 +289,7 @@ int launch_lift_intervals(swo_ctx *c, Device &d, size_t n, const int32_t *tcid, 
     // are launched and the one the flag does not name returns at once (no host round trip)
     uint32_t *flag = reinterpret_cast<uint32_t *>(d.scratch.as<char>() + 8);
     A.sorted_flag = flag;
+    A.full_mask = 0xffffffffu;
     sample_sorted_kernel<<<1, 256, 0, st>>>(tcid, start, (uint32_t)n, flag);
     c->launches++;
     const int th = ths ? 1 : 0;

@@ -100,6 +100,55 @@ def test_binary_random_chains(oracle, seed):
     cf.close()
 
 
+@pytest.mark.parametrize("seed", range(4))
+def test_binary_sorted_batches_take_the_deferred_variant(oracle, seed):
+    """Batches sorted by (contig, start) run the kernel variant that stages a tile's rows in shared
+    memory and resolves its look-back one tile later; heavy tiles inside such a batch resolve at once.
+    Same rows as the oracle in either case, with strand and thick columns, across many tiles."""
+    rng = np.random.default_rng(700 + seed)
+    chain, tn = synth.random_chain(rng, n_chains=int(rng.integers(3, 12)), overlap=bool(seed % 2), max_blocks=80)
+    cf, oc = pair(oracle, chain)
+    n = 20_000 + 1000 * seed + seed
+    tc = rng.integers(0, len(cf.sourceContigs), n).astype(np.int32)
+    s = rng.integers(0, 30_000, n).astype(np.int32)
+    ln = rng.integers(1, 400, n)
+    heavy = rng.random(n) < 0.02  # a few intervals spanning most of the contig: tiles that overflow the stage
+    ln = np.where(heavy, rng.integers(5_000, 30_000, n), ln)
+    order = np.lexsort((s, tc))
+    tc, s, ln = tc[order], s[order], ln[order]
+    e = (s + ln).astype(np.int32)
+    strand = rng.choice(np.frombuffer(b"+-.", np.uint8), n)
+    ts = (s + rng.integers(0, 200, n)).astype(np.int32)
+    te = (ts + rng.integers(0, 200, n)).astype(np.int32)
+    keys = ("row_offset", "qcid", "start", "end", "src", "strand")
+    assert_rows_equal(cf.lift_intervals(tc, s, e, strand), oc.lift_intervals(tc, s, e, strand), keys)
+    assert_rows_equal(cf.lift_intervals(tc, s, e, strand, ts, te), oc.lift_intervals(tc, s, e, strand, ts, te),
+                      keys + ("thick_start", "thick_end"))
+    # the same records with the second half shuffled: still sorted enough for the sample (>= 7/8 pairs)
+    # or not, the rows must not depend on which variant ran
+    half = n // 2
+    perm = np.concatenate([np.arange(half), half + rng.permutation(n - half)])
+    for frac in (0.05, 0.5):
+        m = int(n * frac)
+        p2 = np.concatenate([np.arange(n - m), (n - m) + rng.permutation(m)])
+        assert_rows_equal(cf.lift_intervals(tc[p2], s[p2], e[p2], strand[p2]),
+                          oc.lift_intervals(tc[p2], s[p2], e[p2], strand[p2]), keys)
+    assert_rows_equal(cf.lift_intervals(tc[perm], s[perm], e[perm]), oc.lift_intervals(tc[perm], s[perm], e[perm]))
+    cf.close()
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 1024, 1025, 2049])
+def test_binary_sorted_small_batches(hg, n):
+    cf, oc = hg
+    rng = np.random.default_rng(900 + n)
+    tc = np.sort(rng.integers(0, 3, n)).astype(np.int32)
+    s = rng.integers(0, 60_000_000, n).astype(np.int32)
+    order = np.lexsort((s, tc))
+    tc, s = tc[order], s[order]
+    e = (s + rng.integers(1, 50_000, n)).astype(np.int32)
+    assert_rows_equal(cf.lift_intervals(tc, s, e), oc.lift_intervals(tc, s, e))
+
+
 def test_binary_heavy_fanout(hg):
     cf, oc = hg
     names = [b"chr9", b"chr1", b"chrX", b"chr9", b"chr1"]
