@@ -35,6 +35,18 @@ __device__ __forceinline__ void st_relaxed_u64(uint64_t *p, uint64_t v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// ---- warp reconvergence ---------------------------------------------------
+// Reconverge the warp behind long divergent per-thread work, before a block barrier (bar.sync
+// counts arrivals per WARP, so a split warp arriving twice breaks the barrier) or a warp
+// collective.  Out of line and with the mask as a run-time value on purpose: ptxas 12.9 (sm_100a)
+// drops a __syncwarp() — also one with a mask it cannot see through — wherever it takes the warp
+// for converged (behind a BSYNC.RECONVERGENT), and it is not always right: on tiles whose lanes
+// mix the hinted and the full search one lane was seen (progress markers in host-mapped memory)
+// still behind the search loop while the other 31 had passed the scan's barriers; the block
+// scan came out short or the kernel died with "illegal instruction".  Inside a function that is
+// not inlined nothing is known about the callers' convergence, so the WARPSYNC stays.
+__device__ __noinline__ void converge_warp(unsigned mask) { __syncwarp(mask); }
+
 // ---- warp / block scans ----------------------------------------------------
 template <typename T>
 __device__ __forceinline__ T warp_inclusive_scan(T v) {
@@ -56,7 +68,7 @@ __device__ __forceinline__ T warp_sum(T v) {
 // `scratch` is NWARPS+1 elements of shared memory.  Returns the exclusive prefix;
 // *total receives the block sum (same value in every thread).
 // Contains two __syncthreads(); safe to call repeatedly with the same scratch.
-// Warp shuffles: only for call sites whose lanes arrive together (see block_exclusive_scan_lds).
+// Warp shuffles and two block barriers: the warp must arrive converged (converge_warp above).
 template <typename T, int NWARPS>
 __device__ __forceinline__ T block_exclusive_scan(T v, T *scratch, T *total) {
     const T inc = warp_inclusive_scan(v);
@@ -72,46 +84,6 @@ __device__ __forceinline__ T block_exclusive_scan(T v, T *scratch, T *total) {
     }
     *total = tot;
     return wbase + inc - v;
-}
-
-// The same scan of 32-bit values without any warp collective: every thread parks its value in
-// shared memory, and after a block barrier adds up the values of the lower lanes of its warp
-// (eight 128-bit broadcast loads) and the totals of the lower warps.
-// For use right behind long divergent per-thread work (the block-table searches).  There the
-// shuffle version is not safe with ptxas 12.9 / sm_100a: it issues the scan's first SHFL behind a
-// BSYNC.RECONVERGENT, ahead of the barrier and without a WARPSYNC (an explicit __syncwarp() is
-// dropped as redundant), and lanes that got there early read a neighbour's register before it
-// held its value — per-thread counts right, prefix short (seen in lift_intervals_kernel on
-// batches with heavy multi-hit queries).  Gating the shuffles on a barrier-with-vote result keeps
-// them behind the barrier but makes ptxas add a BRA.DIV / WARPSYNC.COLLECTIVE slow path, which
-// raised "illegal instruction" on half-sorted batches.  Shared memory and block barriers only
-// depend on every THREAD having arrived.
-// vals: NWARPS*32 words (16-byte aligned), wtot: NWARPS words.  Two block barriers.
-template <int NWARPS>
-__device__ __forceinline__ uint32_t block_exclusive_scan_lds(uint32_t v, uint32_t *vals, uint32_t *wtot, uint32_t *total) {
-    const int lane = lane_id(), w = warp_id();
-    vals[threadIdx.x] = v;
-    __syncthreads();
-    const uint4 *row = reinterpret_cast<const uint4 *>(vals + w * 32);
-    uint32_t below = 0, all = 0;
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        const uint4 x = row[i];
-        below += (4 * i + 0 < lane ? x.x : 0u) + (4 * i + 1 < lane ? x.y : 0u) + (4 * i + 2 < lane ? x.z : 0u) +
-                 (4 * i + 3 < lane ? x.w : 0u);
-        all += x.x + x.y + x.z + x.w;
-    }
-    if (lane == 0) wtot[w] = all;
-    __syncthreads();
-    uint32_t wbase = 0, tot = 0;
-#pragma unroll
-    for (int k = 0; k < NWARPS; k++) {
-        const uint32_t s = wtot[k];
-        if (k < w) wbase += s;
-        tot += s;
-    }
-    *total = tot;
-    return wbase + below;
 }
 
 // ---- decoupled look-back ---------------------------------------------------

@@ -56,16 +56,7 @@ struct LiftArgs {
     unsigned full_mask;           // 0xffffffff, as a run-time value: see converge()
 };
 
-// Reconverge the warp behind long divergent per-thread work, before a block barrier (bar.sync
-// counts arrivals per WARP, so a split warp arriving twice breaks the barrier) or a warp
-// collective.  Out of line and with the mask as a run-time value on purpose: ptxas 12.9 (sm_100a)
-// drops a __syncwarp() — also one with a mask it cannot see through — wherever it takes the warp
-// for converged (behind a BSYNC.RECONVERGENT), and it is not always right: on tiles whose lanes
-// mix the hinted and the full search one lane was seen (progress markers in host-mapped memory)
-// still behind the search loop while the other 31 had passed the scan's barriers; the block
-// scan came out short or the kernel died with "illegal instruction".  Inside a function that is
-// not inlined nothing is known about the callers' convergence, so the WARPSYNC stays.
-__device__ __noinline__ void converge_warp(unsigned mask) { __syncwarp(mask); }
+// see converge_warp (device_util.cuh)
 __device__ __forceinline__ void converge(const LiftArgs &A) { converge_warp(A.full_mask); }
 
 // Where a tile's rows go: global memory (positions are global row indices) or the tile's
@@ -217,20 +208,18 @@ __device__ __noinline__ void expand_query_coop(const LiftArgs &A, const RowSink 
 // Shared memory of one CTA (dynamic: > 48 KiB with the stage).  The 16-byte aligned arrays come first.
 template <bool THICK, bool DEFER>
 struct LiftSmem {
-    uint32_t scan_vals[LI_TPB];          // block scan: one value per thread
     int4 st_rows[DEFER ? LI_STAGE : 1];  // staged rows of the pending tile (index = row offset inside the tile)
     uint32_t st_off[DEFER ? LI_TILE : 4];  //   and the tile-local row offset of each of its queries
     int2 st_thick[DEFER && THICK ? LI_STAGE : 1];
     int2 ey[ChainTable::EY_CAP];         // upper search levels (Eytzinger order)
     unsigned long long xscr[LI_XSCR];    // sort scratch of the multi-hit expansion
     unsigned long long lb_part[LI_NW];
-    uint32_t scan[LI_NW + 1];            // scratch of the block scan inside the heavy expansion
+    uint32_t scan[LI_NW + 1];            // scratch of the block scans
     uint32_t wl_q[LI_WL_CAP];
     int wl_lo[LI_WL_CAP];
     int wl_cnt[LI_WL_CAP];
     uint32_t wl_off[LI_WL_CAP];
     int lb_found[LI_NW];
-    uint32_t scan_wtot[LI_NW];
     uint32_t unm;                        // unmatched queries of the tile (shared-memory atomic)
     int tile, wl_n, wl_heavy;
     int p_tile;                          // pending tile (staged, not yet copied out), -1 = none
@@ -268,6 +257,7 @@ __device__ __forceinline__ void flush_pending(const LiftArgs &A, LiftSmem<THICK,
         A.row_offset[A.n] = (uint32_t)(gb + total);
         A.totals[0] = gb + total;
     }
+    converge(A);
     __syncthreads();  // the stage is free again
     if (tid == 0) S.p_tile = -1;
 }
@@ -370,12 +360,12 @@ __global__ void __launch_bounds__(LI_TPB, THICK && DEFER ? 3 : 4) lift_intervals
             }
         }
         converge(A);
-        // Block scan of the per-thread fan-out through shared memory (no warp collective behind the
-        // divergent searches, see block_exclusive_scan_lds); the unmatched count goes through a
+        // Block scan of the per-thread fan-out (the warp was reconverged just above: the scan's
+        // shuffles and barriers need every lane there); the unmatched count goes through a
         // shared-memory atomic.
         if (unm) atomicAdd(&S.unm, unm);
         uint32_t tile_total;
-        const uint32_t excl = block_exclusive_scan_lds<LI_NW>(tsum, S.scan_vals, S.scan_wtot, &tile_total);
+        const uint32_t excl = block_exclusive_scan<uint32_t, LI_NW>(tsum, S.scan, &tile_total);
         if (warp_id() == 0) lookback_publish(A.desc, tile, (uint64_t)tile_total);
         if (tid == 0 && S.unm) {  // every thread's atomicAdd is behind the scan's barriers
             atomicAdd((unsigned long long *)(A.totals + 1), (unsigned long long)S.unm);

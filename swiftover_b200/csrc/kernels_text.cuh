@@ -95,6 +95,7 @@ struct NameEnt {
 
 struct TextArgs {
     TableView T;
+    unsigned full_mask;  // 0xffffffff as a run-time value (converge_warp, device_util.cuh)
     const NameEnt *thash;
     uint32_t thash_mask;
     const char *tname_chars;
@@ -1500,6 +1501,7 @@ __global__ void __launch_bounds__(TX_TPB, TX_MIN_CTAS) lift_bed_text_kernel(cons
             st[TX_NB - 1] = cur;
             v[TX_NB - 1] = cv;
         }
+        converge_warp(A.full_mask);  // the count phase is long divergent per-thread work
         block_scan_multi<TX_NB>(v, ex, bt, S.scan64);
         // lines with heavy fan-out: the block sums their output lengths (a single thread would
         // hold the whole tile, and every successor's look-back, for hundreds of microseconds),
@@ -1582,6 +1584,7 @@ __global__ void __launch_bounds__(TX_TPB, TX_MIN_CTAS) lift_bed_text_kernel(cons
         char *const base_u = direct_u ? (gb_u + tot_u <= A.unm_cap ? A.unm + gb_u : nullptr) : stage_u;
 
         auto run_expansions = [&](char *base) {  // cooperative expansion of the queued multi-hit lines (block-uniform)
+            converge_warp(A.full_mask);  // behind the emit phase
             __syncthreads();
             const int nwl = min(S.wl_n, TX_WL_CAP);
             if (nwl == 0) return;

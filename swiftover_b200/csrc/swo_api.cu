@@ -331,6 +331,7 @@ int launch_lift_text(swo_ctx *c, Device &d, const char *d_in, size_t in_len, cha
     if (in_len == 0) return SWO_OK;
     TextArgs A;
     A.T = d.T;
+    A.full_mask = 0xffffffffu;
     A.thash = d.thash.as<NameEnt>();
     A.thash_mask = d.thash_mask;
     A.tname_chars = d.tchars.as<char>();
