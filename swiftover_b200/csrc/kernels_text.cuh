@@ -1678,6 +1678,7 @@ __global__ void __launch_bounds__(TX_TPB, TX_MIN_CTAS) lift_bed_text_kernel(cons
                         S.rhi = 0;
                         S.wl_n = 0;
                     }
+                    converge_warp(A.full_mask);  // behind line_emit_cold / the previous round
                     if (!__syncthreads_or(any)) continue;
 #pragma unroll
                     for (int b = 0; b < TX_NB; b++) {
@@ -1699,6 +1700,7 @@ __global__ void __launch_bounds__(TX_TPB, TX_MIN_CTAS) lift_bed_text_kernel(cons
                 if (!have_base) resolve_now();
                 char *const glob_l = gb_l + tot_l <= A.lifted_cap ? A.lifted + gb_l : nullptr;
                 if (tid == 0) S.wl_n = 0;
+                converge_warp(A.full_mask);
                 __syncthreads();
                 if (glob_l) {
 #pragma unroll
@@ -1712,6 +1714,7 @@ __global__ void __launch_bounds__(TX_TPB, TX_MIN_CTAS) lift_bed_text_kernel(cons
             }
         }
         // resolve + copy-out of this tile are deferred until the next tile has been counted
+        converge_warp(A.full_mask);
         __syncthreads();  // (also orders this tile's last reads of S.P before the update)
         if (tid == 0) {
             PendTile &P = S.P;

@@ -252,6 +252,41 @@ def test_text_random(oracle, seed):
     cf.close()
 
 
+@pytest.mark.parametrize("seed", range(3))
+def test_text_half_sorted_few_contigs(oracle, seed):
+    """Lines on two or three contigs, first part sorted, rest shuffled, a few long intervals: inside a
+    warp some lines take the sorted-input hint and others the full search (the divergence pattern that
+    split warps in the binary kernel before converge_warp)."""
+    rng = np.random.default_rng(1200 + seed)
+    chain, tn = synth.random_chain(rng, n_chains=int(rng.integers(3, 12)), overlap=False, max_blocks=80)
+    cf, oc = pair(oracle, chain)
+    names = cf.sourceContigs
+    n = 30_000
+    tc = rng.integers(0, len(names), n)
+    s = rng.integers(0, 30_000, n)
+    ln = np.where(rng.random(n) < 0.02, rng.integers(5_000, 30_000, n), rng.integers(1, 400, n))
+    order = np.lexsort((s, tc))
+    tc, s, ln = tc[order], s[order], ln[order]
+    m = n // 2 + 1000 * seed
+    perm = np.concatenate([np.arange(n - m), (n - m) + rng.permutation(m)])
+    cols = [3, 6, 8][seed]
+    lines = []
+    for i in perm:
+        nm = names[tc[i]] if isinstance(names[tc[i]], bytes) else names[tc[i]].encode()
+        f = [nm, b"%d" % s[i], b"%d" % (s[i] + ln[i])]
+        if cols >= 6:
+            f += [b"n%d" % i, b"0", b"+-."[i % 3:i % 3 + 1]]
+        if cols >= 8:
+            f += [b"%d" % (s[i] + ln[i] // 4), b"%d" % (s[i] + ln[i] - ln[i] // 4)]
+        lines.append(b"\t".join(f))
+    bed = b"\n".join(lines) + b"\n"
+    lifted, unm, st = cf.lift_bed_text(bed)
+    o_l, o_u, o_st = oc.lift_bed(bed)
+    assert lifted == o_l and unm == o_u
+    assert st["n_rows"] == o_st["n_rows"] and st["n_unmatched"] == o_st["n_unmatched"]
+    cf.close()
+
+
 @pytest.mark.parametrize("chunk", [64, 1000, 16384, 100_000])
 def test_text_chunk_boundaries(oracle, chunk):
     cf, oc = pair(oracle, resource_bytes("hg19ToHg38.over.chain"))
