@@ -162,8 +162,11 @@ __device__ __noinline__ void expand_query_coop(const LiftArgs &A, const RowSink 
                         }
                     }
                 }
-                converge(A);
+                // warp form: the out-of-line barrier (a plain __syncwarp() is dropped here and the lanes
+                // then race on the keys: test_binary_* fail); block form: uniform trip counts behind
+                // the reconvergence above, the block barrier alone is enough
                 if (BLOCK) __syncthreads();
+                else converge(A);
             }
         }
     }

@@ -532,8 +532,8 @@ __device__ __noinline__ void expand_line_coop(const TextArgs &A, const int2 *ey,
         }
         scr[c] = key;
     }
+    converge_warp(A.full_mask);  // (a plain __syncwarp() may be dropped by ptxas: device_util.cuh)
     if (BLOCK) __syncthreads();
-    else __syncwarp();
     bool mine = true;
     for (int c = first; c < P; c += stride)
         if (c > 0 && scr[c - 1] > scr[c]) mine = false;
@@ -552,7 +552,7 @@ __device__ __noinline__ void expand_line_coop(const TextArgs &A, const int2 *ey,
                     }
                 }
                 if (BLOCK) __syncthreads();
-                else __syncwarp();
+                else converge_warp(A.full_mask);
             }
         }
     }
