@@ -284,15 +284,15 @@ __global__ void __launch_bounds__(256) sample_sorted_kernel(const int32_t *__res
     if (threadIdx.x == 0) *flag = (s_cnt * 8u >= want * 7u) ? 1u : 0u;
 }
 
-// DEFER = the variant for sorted batches (A.sorted_flag says which variant works; the other one
-// returns at once): a tile's rows and row offsets are staged in shared memory and its look-back
+// DEFER = the variant for sorted batches without thick columns (A.sorted_flag says which variant
+// works; the other one returns at once; batches with thick columns always take the immediate one): a tile's rows and row offsets are staged in shared memory and its look-back
 // is resolved one tile later.  The other variant resolves every tile right after its scan and
 // keeps the shared memory for L1 (random probes of the block table).
 template <bool THICK, bool DEFER>
-__global__ void __launch_bounds__(LI_TPB, THICK && DEFER ? 3 : 4) lift_intervals_kernel(const __grid_constant__ LiftArgs A) {
+__global__ void __launch_bounds__(LI_TPB, 4) lift_intervals_kernel(const __grid_constant__ LiftArgs A) {
     extern __shared__ __align__(16) unsigned char li_smem_raw[];
     LiftSmem<THICK, DEFER> &S = *reinterpret_cast<LiftSmem<THICK, DEFER> *>(li_smem_raw);
-    if ((__ldg(A.sorted_flag) != 0u) != DEFER) return;
+    if ((!THICK && __ldg(A.sorted_flag) != 0u) != DEFER) return;
 
     const int tid = threadIdx.x;
     const TableView &T = A.T;

@@ -285,24 +285,25 @@ int launch_lift_intervals(swo_ctx *c, Device &d, size_t n, const int32_t *tcid, 
     A.ticket = d.scratch.as<unsigned>();
     A.desc = reinterpret_cast<uint64_t *>(d.scratch.as<char>() + 16);
     A.totals = totals;
-    // sortedness sample -> flag word behind the look-back descriptors; both variants of the kernel
-    // are launched and the one the flag does not name returns at once (no host round trip)
+    // sortedness sample -> flag word in the scratch header; both variants of the kernel
+    // are launched and the one the flag does not name returns at once (no host round trip).
+    // Batches with thick columns always take the immediate variant (measured faster: the two extra
+    // point searches per row dominate and the stage costs a CTA per SM), so no sample for them.
     uint32_t *flag = reinterpret_cast<uint32_t *>(d.scratch.as<char>() + 8);
     A.sorted_flag = flag;
     A.full_mask = 0xffffffffu;
-    sample_sorted_kernel<<<1, 256, 0, st>>>(tcid, start, (uint32_t)n, flag);
-    c->launches++;
-    const int th = ths ? 1 : 0;
-    for (int defer = 0; defer < 2; defer++) {
-        const int v = th * 2 + defer;
+    const bool th = ths != nullptr;
+    if (!th) {
+        sample_sorted_kernel<<<1, 256, 0, st>>>(tcid, start, (uint32_t)n, flag);
+        c->launches++;
+    }
+    for (int v = th ? 2 : 0; v < (th ? 3 : 2); v++) {
         const void *fn = v == 0   ? (const void *)lift_intervals_kernel<false, false>
                          : v == 1 ? (const void *)lift_intervals_kernel<false, true>
-                         : v == 2 ? (const void *)lift_intervals_kernel<true, false>
-                                  : (const void *)lift_intervals_kernel<true, true>;
+                                  : (const void *)lift_intervals_kernel<true, false>;
         const size_t smem = v == 0   ? sizeof(LiftSmem<false, false>)
                             : v == 1 ? sizeof(LiftSmem<false, true>)
-                            : v == 2 ? sizeof(LiftSmem<true, false>)
-                                     : sizeof(LiftSmem<true, true>);
+                                     : sizeof(LiftSmem<true, false>);
         if (!d.bin_grid[v]) {
             int per = 0;
             CK(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
