@@ -516,3 +516,14 @@ def test_full_size_properties(hg):
     torch.cuda.synchronize()
     assert int(bufs.totals[0].item()) == nr and int(bufs.totals[1].item()) == nu
     assert chk(bufs.rows[:nr]) == sum_sorted
+
+
+def test_fuzz_parity_short():
+    """A few seconds of tools/fuzz_parity.py: random chains, random degrees of sortedness / contig counts /
+    fan-out, binary and text paths against the oracle (caught the split-warp defect within 7 cases)."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, FUZZ_SECONDS="10", FUZZ_SEED0="0")
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_parity.py")], capture_output=True, text=True, env=env,
+                       timeout=600)
+    assert r.returncode == 0 and "fuzz ok" in r.stdout, r.stdout[-500:] + r.stderr[-500:]
