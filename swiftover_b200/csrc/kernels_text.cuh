@@ -995,7 +995,8 @@ __device__ __forceinline__ int line_count(const TextArgs &A, const TileCtx &X, u
         } else {
             const uint32_t fixed = fast_fixed_len(F);
             Thick th{0, 0, 0};
-            if (F.numf >= 8) th = lift_thick(T, tx_ey(), F.tcid, F.v6, F.v7);
+            // thickStart / thickEnd normally lie inside the interval: gallop from its lower bound
+            if (F.numf >= 8) th = lift_thick_from(T, tx_ey(), F.tcid, F.v6, F.v7, F.start, cd.lo, H.contig_end);
             RowCore r;
             r.key = r.s = r.e = r.qcid = 0;
             r.inv = 1;
@@ -1071,7 +1072,7 @@ __device__ __noinline__ void fast_expand_small(const TextArgs &A, const unsigned
         uint32_t v6 = 0, v7 = 0, n6 = 0, n7 = 0, term;
         parse_uint_swar(W, F.a6, v6, n6, term);
         parse_uint_swar(W, F.a6 + n6 + 1, v7, n7, term);
-        th = lift_thick(T, tx_ey(), tcid, (int)v6, (int)v7);
+        th = lift_thick_from(T, tx_ey(), tcid, (int)v6, (int)v7, F.start, lo, load_cmeta(T, tcid).y);
     }
     for (int c = 0; c < ncand; c++) {
         const Block bj = load_block(T, lo + c);
@@ -1114,7 +1115,7 @@ __device__ __noinline__ void fast_expand_sorted(const TextArgs &A, const TileCtx
         uint32_t v6 = 0, v7 = 0, n6 = 0, n7 = 0, term;
         parse_uint_swar(W, F.a6, v6, n6, term);
         parse_uint_swar(W, F.a6 + n6 + 1, v7, n7, term);
-        th = lift_thick(T, tx_ey(), tcid, (int)v6, (int)v7);
+        th = lift_thick_from(T, tx_ey(), tcid, (int)v6, (int)v7, F.start, lo, load_cmeta(T, tcid).y);
     }
     unsigned char sb = F.strand;
     char *d = dst;
