@@ -2,7 +2,7 @@
 """GPU fuzz (not a test, not a bench): random chains and batches with random degrees of
 sortedness, contig counts and fan-out, binary and text paths against the CPU oracle.
 Each case runs in the calling process; a CUDA error or a mismatch stops the run and prints the
-seed.  FUZZ_SECONDS (default 120), FUZZ_SEED0 (default 0)."""
+seed.  FUZZ_SECONDS (default 120), FUZZ_SEED0 (default 0), FUZZ_BIG=1: 3e5-7e5 records per case."""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -21,7 +21,8 @@ while time.time() < t_end:
                                    overlap=bool(rng.random() < 0.3))
     cf, oc = ChainFile(text=chain), orc.chain_parse(chain)
     names = cf.sourceContigs
-    n = int(rng.choice([1, 7, 1023, 1025, 5000, 20_000, 60_000]))
+    big = bool(os.environ.get("FUZZ_BIG"))  # many tiles per CTA (the deferred flush / pipelining paths)
+    n = int(rng.choice([300_000, 700_000])) if big else int(rng.choice([1, 7, 1023, 1025, 5000, 20_000, 60_000]))
     tc = rng.integers(-1 if rng.random() < 0.2 else 0, len(names), n).astype(np.int32)
     span = int(rng.choice([3_000, 30_000, 120_000]))
     s = rng.integers(0, span, n).astype(np.int32)
@@ -49,7 +50,7 @@ while time.time() < t_end:
         ok = tc >= 0
         cols = int(rng.choice([3, 6, 8, 12]))
         lines = []
-        for i in np.nonzero(ok)[0][:30_000]:
+        for i in np.nonzero(ok)[0][: (10**9 if big else 30_000)]:
             nm = names[tc[i]] if isinstance(names[tc[i]], bytes) else names[tc[i]].encode()
             f = [nm, b"%d" % s[i], b"%d" % e[i]]
             if cols >= 6: f += [b"n%d" % i, b"0", bytes([strand[i]])]
