@@ -117,7 +117,9 @@ typedef struct swo_lifted {
 } swo_lifted;
 
 /* Host arrays in, pinned host arrays out.  tcid = swo_tcontig_id (negative ->
- * no hit).  strand, thick_start/thick_end may be NULL (BED3 / BED6). */
+ * no hit).  strand, thick_start/thick_end may be NULL (BED3 / BED6).
+ * Any record order is accepted and gives the same rows; a batch sorted by
+ * (contig, start) is recognised on the device and runs the faster variant. */
 int swo_lift_intervals(swo_ctx *ctx, size_t n, const int32_t *tcid, const int32_t *start,
                        const int32_t *end, const uint8_t *strand, const int32_t *thick_start,
                        const int32_t *thick_end, swo_lifted *out);

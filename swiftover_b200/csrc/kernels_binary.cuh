@@ -19,6 +19,13 @@
 // block for heavy fan-out) writes one sort key per candidate to shared memory,
 // sorts only if the keys are not already ascending, and stores every row at its
 // sorted position with the cumulative strand byte.
+//
+// Sorted batches (DEFER variant): the tile's rows and row offsets are staged in
+// shared memory, its aggregate is published, and its look-back is resolved after
+// the CTA's NEXT tile has been searched (flush_pending) — predecessors have had a
+// whole search phase to publish, so the walk does not wait; copy-out is coalesced.
+// Every block barrier / warp collective behind the divergent per-thread work is
+// preceded by converge() (device_util.cuh: converge_warp).
 #pragma once
 #include "device_util.cuh"
 #include "lift_core.cuh"
