@@ -43,6 +43,7 @@ constexpr int LI_NW = LI_TPB / 32;
 constexpr int LI_WL_CAP = LI_WL_CAP_OVR;      // multi-hit queries queued per tile
 constexpr int LI_HEAVY_MIN = 128;   // candidates above this: the whole block expands the query
 constexpr int LI_XSCR = 1024;       // shared-memory sort scratch (= LI_NW warp regions of LI_HEAVY_MIN)
+constexpr int LI_CM_CAP = 128;      // per-contig table entries kept in shared memory (more contigs: global loads)
 constexpr int LI_STAGE = 1152;       // rows of a tile staged in shared memory for the deferred copy-out
 
 struct LiftArgs {
@@ -221,6 +222,7 @@ struct LiftSmem {
     int4 st_rows[DEFER ? LI_STAGE : 1];  // staged rows of the pending tile (index = row offset inside the tile)
     uint32_t st_off[DEFER ? LI_TILE : 4];  //   and the tile-local row offset of each of its queries
     int2 st_thick[DEFER && THICK ? LI_STAGE : 1];
+    int4 cmeta[LI_CM_CAP];               // per-contig {first block, end block, ey offset, ey samples}
     int2 ey[ChainTable::EY_CAP];         // upper search levels (Eytzinger order)
     unsigned long long xscr[LI_XSCR];    // sort scratch of the multi-hit expansion
     unsigned long long lb_part[LI_NW];
@@ -305,6 +307,9 @@ __global__ void __launch_bounds__(LI_TPB, 4) lift_intervals_kernel(const __grid_
     const TableView &T = A.T;
     for (int i = tid; i < T.ey_n; i += LI_TPB) S.ey[i] = __ldg(T.ey + i);
     const int2 *const ey = S.ey;
+    const bool cm_smem = T.ntc <= LI_CM_CAP;  // the search then starts without a dependent global load
+    if (cm_smem)
+        for (int i = tid; i < T.ntc; i += LI_TPB) S.cmeta[i] = __ldg(T.cmeta + i);
     if (tid == 0) {
         S.p_tile = -1;
         S.unm = 0;
@@ -350,10 +355,14 @@ __global__ void __launch_bounds__(LI_TPB, 4) lift_intervals_kernel(const __grid_
             Block b0;
             // sorted batches: same contig and a start that did not move back -> the lower bound only moves
             // forward from the previous query's (a short gallop instead of a full search)
-            if (k > 0 && tc[k] == tc[k - 1] && st[k] >= st[k - 1] && tc[k] >= 0 && tc[k] < T.ntc)
-                cd[k] = find_candidates_from(T, load_cmeta(T, tc[k]).y, cd[k - 1].lo, st[k], en[k], b0);
+            const bool tc_ok = tc[k] >= 0 && tc[k] < T.ntc;
+            const int4 cm = !tc_ok ? make_int4(0, 0, 0, 0) : cm_smem ? S.cmeta[tc[k]] : load_cmeta(T, tc[k]);
+            if (k > 0 && tc[k] == tc[k - 1] && st[k] >= st[k - 1] && tc_ok)
+                cd[k] = find_candidates_from(T, cm.y, cd[k - 1].lo, st[k], en[k], b0);
+            else if (tc_ok)
+                cd[k] = find_candidates_cm(T, ey, cm, st[k], en[k], b0);
             else
-                cd[k] = find_candidates_b0(T, ey, tc[k], st[k], en[k], b0);
+                cd[k] = Cand{0, 0};
             nh[k] = count_hits(T, cd[k], st[k]);
             tsum += (uint32_t)nh[k];
             unm += (q0 + k < A.n && nh[k] == 0) ? 1u : 0u;
@@ -435,7 +444,7 @@ __global__ void __launch_bounds__(LI_TPB, 4) lift_intervals_kernel(const __grid_
                     else st_stream_v4(A.rows + run64, row);
                     if (THICK) {
                         const Thick th = lift_thick_from(T, ey, tc[k], __ldg(A.thick_s + q), __ldg(A.thick_e + q), st[k],
-                                                         cd[k].lo, load_cmeta(T, tc[k]).y);
+                                                         cd[k].lo, (cm_smem ? S.cmeta[tc[k]] : load_cmeta(T, tc[k])).y);
                         swo_thick t;
                         thick_clamp(th, r_s[k], r_e[k], t.thick_start, t.thick_end);
                         sink.thick[run64] = t;

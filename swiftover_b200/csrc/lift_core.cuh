@@ -150,6 +150,22 @@ SWO_HD Block load_block(const TableView &T, int j) {
 #endif
 }
 
+// Same with the contig's cmeta entry given (a caller that keeps the per-contig table in shared
+// memory saves the dependent global load at the head of the search).
+SWO_HD Cand find_candidates_cm(const TableView &T, const int2 *__restrict__ ey, const int4 cm, int start, int end,
+                               Block &b0) {
+    Cand c{0, 0};
+    b0 = Block{0, 0, 0, 0};
+    const int lo = lower_gt_ey(T, ey, cm, start);
+    c.lo = c.hi = lo;
+    if (lo >= cm.y) return c;
+    b0 = load_block(T, lo);
+    const int s1 = lo + 1 < cm.y ? SWO_LDG(T.tStartKey + lo + 1) : 0x7fffffff;
+    if (b0.tStart >= end) return c;
+    c.hi = s1 >= end ? lo + 1 : gallop_ge(T.tStartKey, lo + 2, cm.y, end);
+    return c;
+}
+
 SWO_HD Cand find_candidates_b0(const TableView &T, const int2 *__restrict__ ey, int tcid, int start, int end,
                                Block &b0) {
     Cand c{0, 0};
