@@ -15,6 +15,12 @@ from . import _lib as L
 LiftedInterval = namedtuple("LiftedInterval", "contig start end strand")
 
 
+
+def _bytes_at(ptr, n):
+    """bytes(n) copied from a host address; ctypes.string_at takes a C int size and fails past 2 GiB
+    (outputs of heavy fan-out inputs do get that large)."""
+    return bytes((C.c_char * n).from_address(ptr)) if n else b""
+
 class SwiftoverError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"swiftover_cuda error {code}: {msg}")
@@ -153,8 +159,8 @@ class ChainFile:
         buf = bytes(data)
         out = L.SwoTextOut()
         self._ck(self._lib.swo_lift_bed_text(self._h, buf, len(buf), C.byref(out)))
-        lifted = C.string_at(out.lifted, out.lifted_len) if out.lifted_len else b""
-        unm = C.string_at(out.unmatched, out.unmatched_len) if out.unmatched_len else b""
+        lifted = _bytes_at(out.lifted, out.lifted_len)
+        unm = _bytes_at(out.unmatched, out.unmatched_len)
         return lifted, unm, dict(n_records=out.n_records, n_rows=out.n_rows, n_unmatched=out.n_unmatched)
 
     def lift_bed_text_ptr(self, ptr, nbytes):
@@ -187,8 +193,8 @@ class ChainFile:
         fd = None if filedate is None else filedate.encode()
         self._ck(self._lib.swo_lift_vcf_text(self._h, buf, len(buf), chainfile.encode(), genomefile.encode(), fd,
                                              C.byref(out)))
-        lifted = C.string_at(out.lifted, out.lifted_len) if out.lifted_len else b""
-        unm = C.string_at(out.unmatched, out.unmatched_len) if out.unmatched_len else b""
+        lifted = _bytes_at(out.lifted, out.lifted_len)
+        unm = _bytes_at(out.unmatched, out.unmatched_len)
         return lifted, unm, dict(n_records=out.n_records, n_matched=out.n_rows, n_unmatched=out.n_unmatched)
 
     def lift_maf_text(self, data, genomebuild):
@@ -196,8 +202,8 @@ class ChainFile:
         buf = bytes(data)
         out, st = L.SwoTextOut(), L.SwoMafStats()
         self._ck(self._lib.swo_lift_maf_text(self._h, buf, len(buf), genomebuild.encode(), C.byref(out), C.byref(st)))
-        lifted = C.string_at(out.lifted, out.lifted_len) if out.lifted_len else b""
-        unm = C.string_at(out.unmatched, out.unmatched_len) if out.unmatched_len else b""
+        lifted = _bytes_at(out.lifted, out.lifted_len)
+        unm = _bytes_at(out.unmatched, out.unmatched_len)
         return lifted, unm, {k: getattr(st, k) for k, _ in st._fields_}
 
     def lift_maf_records(self, tcid, start, end, reflen, ref_off, ref_bytes, out_off, out_cap):

@@ -21,6 +21,14 @@ def build_oracle():
         subprocess.check_call(["make", "-C", ORACLE_DIR, "-s", "liboracle.so", "orc_cli"])
 
 
+
+def _bytes_at(ptr, n):
+    """ctypes.string_at takes a C int size: fails past 2 GiB."""
+    if not n:
+        return b""
+    addr = ptr if isinstance(ptr, int) else C.cast(ptr, C.c_void_p).value
+    return bytes((C.c_char * n).from_address(addr))
+
 class OrcLink(C.Structure):
     _fields_ = [("tStart", C.c_int64), ("tEnd", C.c_int64), ("qStart", C.c_int64),
                 ("qcid", C.c_int32), ("invert", C.c_int32)]
@@ -205,8 +213,8 @@ class OracleChain:
                                         C.byref(st), err, 256)
         else:
             rc = self.L.orc_lift_bed(self.h, text, len(text), C.byref(lifted), C.byref(unm), C.byref(st), err, 256)
-        a = C.string_at(lifted.data, lifted.len) if lifted.len else b""
-        b = C.string_at(unm.data, unm.len) if unm.len else b""
+        a = _bytes_at(lifted.data, lifted.len)
+        b = _bytes_at(unm.data, unm.len)
         self.L.orc_buf_free(C.byref(lifted))
         self.L.orc_buf_free(C.byref(unm))
         if rc:
@@ -277,8 +285,8 @@ class OracleChain:
         err = C.create_string_buffer(256)
         rc = fn(self.h, fasta, len(fasta), text, len(text), chainfile.encode(), genomefile.encode(), filedate.encode(),
                 C.byref(lifted), C.byref(unm), C.byref(st), err, 256)
-        out = (C.string_at(lifted.data, lifted.len) if lifted.len else b"",
-               C.string_at(unm.data, unm.len) if unm.len else b"",
+        out = (_bytes_at(lifted.data, lifted.len),
+               _bytes_at(unm.data, unm.len),
                dict(n_records=st.n_records, n_matched=st.n_matched, n_unmatched=st.n_unmatched, n_refchg=st.n_refchg))
         self.L.orc_buf_free(C.byref(lifted))
         self.L.orc_buf_free(C.byref(unm))
@@ -300,8 +308,8 @@ class OracleChain:
         err = C.create_string_buffer(256)
         rc = fn(self.h, fasta, len(fasta), text, len(text), genomebuild.encode(), C.byref(lifted), C.byref(unm),
                 C.byref(st), err, 256)
-        out = (C.string_at(lifted.data, lifted.len) if lifted.len else b"",
-               C.string_at(unm.data, unm.len) if unm.len else b"", {k: getattr(st, k) for k in keys})
+        out = (_bytes_at(lifted.data, lifted.len),
+               _bytes_at(unm.data, unm.len), {k: getattr(st, k) for k in keys})
         self.L.orc_buf_free(C.byref(lifted))
         self.L.orc_buf_free(C.byref(unm))
         if rc:
