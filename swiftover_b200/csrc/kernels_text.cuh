@@ -1217,6 +1217,7 @@ __device__ __noinline__ void coop_count_lines(const TextArgs &A, const TileCtx &
             if (!T.disjoint && !block_hits(b, F.start)) continue;
             part += fast_row_len(A, F, fixed, th, make_row(b, F.start, F.end));
         }
+        converge_warp(A.full_mask);  // lanes leave the loop above at different times
         part = warp_sum(part);
         if (lane_id() == 0) S.red32[warp_id()] = part;
         __syncthreads();
