@@ -2,7 +2,8 @@
 """GPU fuzz (not a test, not a bench): random chains and batches with random degrees of
 sortedness, contig counts and fan-out, binary and text paths against the CPU oracle.
 Each case runs in the calling process; a CUDA error or a mismatch stops the run and prints the
-seed.  FUZZ_SECONDS (default 120), FUZZ_SEED0 (default 0), FUZZ_BIG=1: 3e5-7e5 records per case."""
+seed.  FUZZ_SECONDS (default 120), FUZZ_SEED0 (default 0), FUZZ_BIG=1: 3e5-7e5 records per case,
+FUZZ_HG=1: the hg19ToHg38 chain instead of random chains."""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -19,15 +20,19 @@ while time.time() < t_end:
     ntc = int(rng.integers(1, 5))
     chain, tn = synth.random_chain(rng, n_chains=int(rng.integers(1, 16)), n_tcontigs=ntc, max_blocks=int(rng.choice([5, 40, 200])),
                                    overlap=bool(rng.random() < 0.3))
+    hg = bool(os.environ.get("FUZZ_HG"))  # the reference's hg19ToHg38 chain (53,950 blocks, grouped bottom search)
+    if hg:
+        import gzip
+        chain = gzip.open(os.path.join(ROOT, "tests/golden/resources/hg19ToHg38.over.chain.gz"), "rb").read()
     cf, oc = ChainFile(text=chain), orc.chain_parse(chain)
     names = cf.sourceContigs
     big = bool(os.environ.get("FUZZ_BIG"))  # many tiles per CTA (the deferred flush / pipelining paths)
     n = int(rng.choice([300_000, 700_000])) if big else int(rng.choice([1, 7, 1023, 1025, 5000, 20_000, 60_000]))
-    tc = rng.integers(-1 if rng.random() < 0.2 else 0, len(names), n).astype(np.int32)
-    span = int(rng.choice([3_000, 30_000, 120_000]))
+    tc = rng.integers(-1 if rng.random() < 0.2 else 0, min(len(names), ntc + 1) if hg else len(names), n).astype(np.int32)
+    span = int(rng.choice([3_000_000, 60_000_000, 150_000_000])) if hg else int(rng.choice([3_000, 30_000, 120_000]))
     s = rng.integers(0, span, n).astype(np.int32)
     heavy = rng.random(n) < float(rng.choice([0.0, 0.02, 0.3]))
-    ln = np.where(heavy, rng.integers(1_000, span + 2, n), rng.integers(1, int(rng.choice([20, 400, 4000])), n))
+    ln = np.where(heavy, rng.integers(1_000, (2_000_000 if hg else span) + 2, n), rng.integers(1, int(rng.choice([20, 400, 4000])), n))
     order = np.lexsort((s, tc))
     tc, s, ln = tc[order], s[order], ln[order]
     m = int(n * float(rng.choice([0.0, 0.05, 0.12, 0.2, 0.5, 0.9, 1.0])))
