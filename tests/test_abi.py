@@ -131,3 +131,12 @@ def test_chain_parser_file_and_errors(built, oracle, resources, tmp_path):
                  b"chain 9 z 100 + 0 50 y 100 + 0 50 9\nchain 1 a 100 + 0 50 b 100 + 0 50 1\n50\n",
                  b"chain 1 a 100 - 10 60 b 100 - 0 50 1\n20 5 5\n25\n\n"):
         same_table(ChainFile(text=text, inspect_only=True), oracle.chain_parse(text))
+
+
+def test_python_wrapper_copies_outputs_by_size_t():
+    """Outputs larger than 2 GiB must survive the ctypes layer (ctypes.string_at takes a C int)."""
+    import ctypes as C
+    from swiftover_b200.chain import _bytes_at
+    buf = C.create_string_buffer(b"lifted\tbytes\n", 13)
+    assert _bytes_at(C.addressof(buf), 13) == b"lifted\tbytes\n" and _bytes_at(0, 0) == b""
+    assert _bytes_at(C.addressof(buf), C.c_size_t(6).value) == b"lifted"
