@@ -62,6 +62,7 @@ struct LiftArgs {
     uint64_t *totals;   // [0] rows, [1] unmatched   (zeroed)
     const uint32_t *sorted_flag;  // written by sample_sorted_kernel: which kernel variant does the work
     unsigned full_mask;           // 0xffffffff, as a run-time value: see converge()
+    unsigned long long *gscr;     // sorted variant: per-warp sort scratch in global memory (kernels_merge.cuh)
 };
 
 // see converge_warp (device_util.cuh)
@@ -278,7 +279,7 @@ __device__ __forceinline__ void flush_pending(const LiftArgs &A, LiftSmem<THICK,
 // the batch; a pair counts when both queries name the same contig and the start does not move
 // back.  *flag = 1 when at least 7 of 8 pairs do.  Decides which kernel variant does the work.
 __global__ void __launch_bounds__(256) sample_sorted_kernel(const int32_t *__restrict__ tcid, const int32_t *__restrict__ start,
-                                                            uint32_t n, uint32_t *flag) {
+                                                            uint32_t n, uint32_t *flag, uint32_t allow) {
     __shared__ unsigned s_cnt;
     if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
@@ -290,7 +291,7 @@ __global__ void __launch_bounds__(256) sample_sorted_kernel(const int32_t *__res
     }
     atomicAdd(&s_cnt, ok);
     __syncthreads();
-    if (threadIdx.x == 0) *flag = (s_cnt * 8u >= want * 7u) ? 1u : 0u;
+    if (threadIdx.x == 0) *flag = (allow && s_cnt * 8u >= want * 7u) ? 1u : 0u;
 }
 
 // DEFER = the variant for sorted batches without thick columns (A.sorted_flag says which variant

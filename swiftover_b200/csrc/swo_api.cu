@@ -22,6 +22,7 @@
 #include "chain_table.hpp"
 #include "genome.hpp"
 #include "kernels_binary.cuh"
+#include "kernels_merge.cuh"
 #include "kernels_text.cuh"
 #include "kernels_maf.cuh"
 #include "kernels_vcf.cuh"
@@ -261,7 +262,12 @@ int launch_lift_intervals(swo_ctx *c, Device &d, size_t n, const int32_t *tcid, 
                           uint32_t *row_offset, swo_row *rows, swo_thick *thick, size_t rows_cap, uint64_t *totals,
                           cudaStream_t st) {
     const int ntiles = (int)((n + LI_TILE - 1) / LI_TILE);
-    const size_t scratch_bytes = 16 + (size_t)ntiles * 8;
+    // scratch: [ticket, -, sorted flag, -] [ntiles tile descriptors (per-query-search variants)]
+    // sorted variant (tiles of MG_TILE queries, two-level look-back): [nts tile words] [nts/32+1 acc] [nts/32+1 inc]
+    const int nts = (int)((n + MG_TILE - 1) / MG_TILE);
+    const size_t w_desc = (16 + (size_t)ntiles * 8 + 15) & ~(size_t)15;
+    const size_t w_acc = w_desc + (size_t)nts * 8, w_inc = w_acc + ((size_t)nts / LBG_TILES + 1) * 8;
+    const size_t scratch_bytes = w_inc + ((size_t)nts / LBG_TILES + 1) * 8;
     CK(c, d.scratch.reserve((scratch_bytes + 3) & ~(size_t)3));
     if (int rc = zero_async(c, d.scratch.p, scratch_bytes, totals, 16, st)) return rc;
     if (n == 0) {
@@ -284,36 +290,72 @@ int launch_lift_intervals(swo_ctx *c, Device &d, size_t n, const int32_t *tcid, 
     A.rows_cap = rows_cap;
     A.ticket = d.scratch.as<unsigned>();
     A.desc = reinterpret_cast<uint64_t *>(d.scratch.as<char>() + 16);
+    Lb2 L;
+    L.desc = reinterpret_cast<unsigned long long *>(d.scratch.as<char>() + w_desc);
+    L.acc = reinterpret_cast<unsigned long long *>(d.scratch.as<char>() + w_acc);
+    L.inc = reinterpret_cast<uint64_t *>(d.scratch.as<char>() + w_inc);
+    A.gscr = nullptr;
     A.totals = totals;
     // sortedness sample -> flag word in the scratch header; both variants of the kernel
     // are launched and the one the flag does not name returns at once (no host round trip).
-    // Batches with thick columns always take the immediate variant (measured faster: the two extra
-    // point searches per row dominate and the stage costs a CTA per SM), so no sample for them.
+    // Sorted batches: the warp-merge kernel (kernels_merge.cuh).  Batches with thick columns always
+    // take the immediate per-query-search variant (the two extra point searches per row dominate
+    // there), so no sample for them.
     uint32_t *flag = reinterpret_cast<uint32_t *>(d.scratch.as<char>() + 8);
     A.sorted_flag = flag;
     A.full_mask = 0xffffffffu;
     const bool th = ths != nullptr;
+    const bool merge_ok = d.T.disjoint != 0;  // the merge kernel assumes candidates == hits
     if (!th) {
-        sample_sorted_kernel<<<1, 256, 0, st>>>(tcid, start, (uint32_t)n, flag);
+        sample_sorted_kernel<<<1, 256, 0, st>>>(tcid, start, (uint32_t)n, flag, merge_ok ? 1u : 0u);
         c->launches++;
     }
     for (int v = th ? 2 : 0; v < (th ? 3 : 2); v++) {
         const void *fn = v == 0   ? (const void *)lift_intervals_kernel<false, false>
-                         : v == 1 ? (const void *)lift_intervals_kernel<false, true>
+                         : v == 1 ? (strand ? (const void *)lift_sorted_kernel<true> : (const void *)lift_sorted_kernel<false>)
                                   : (const void *)lift_intervals_kernel<true, false>;
         const size_t smem = v == 0   ? sizeof(LiftSmem<false, false>)
-                            : v == 1 ? sizeof(LiftSmem<false, true>)
+                            : v == 1 ? sizeof(MergeSmem)
                                      : sizeof(LiftSmem<true, false>);
-        if (!d.bin_grid[v]) {
+        if (v == 1 && !merge_ok) continue;
+        const int gi = v == 1 && strand ? 3 : v;
+        if (!d.bin_grid[gi]) {
             int per = 0;
             CK(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, fn, LI_TPB, smem));
-            d.bin_grid[v] = std::max(1, per) * d.sms;
+            CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, fn, v == 1 ? MG_TPB : LI_TPB, smem));
+            d.bin_grid[gi] = std::max(1, per) * d.sms;
         }
-        const int grid = std::min(ntiles, d.bin_grid[v]);
-        void *args[] = {(void *)&A};
-        CK(c, cudaLaunchKernel(fn, dim3(grid), dim3(LI_TPB), args, smem, st));
+        LiftArgs Aw = A;
+        int grid = std::min(ntiles, d.bin_grid[gi]);
+        if (v == 1) {  // its own tile size; per-warp sort scratch in global memory
+            Aw.ntiles = nts;
+            grid = std::min(nts, d.bin_grid[gi]);
+            CK(c, d.gscr.reserve((size_t)d.bin_grid[gi] * MG_NW * MG_GXS * sizeof(unsigned long long)));
+            Aw.gscr = d.gscr.as<unsigned long long>();
+        }
+        void *args[] = {(void *)&Aw, (void *)&L};
+#ifdef MG_TRACE
+        unsigned long long *trbuf = nullptr;
+        if (v == 1 && getenv("SWO_MG_TRACE")) {
+            cudaMalloc(&trbuf, (size_t)nts * 64);
+            cudaMemset(trbuf, 0, (size_t)nts * 64);
+            cudaMemcpyToSymbol(mg_trace, &trbuf, sizeof trbuf);
+        }
+#endif
+        CK(c, cudaLaunchKernel(fn, dim3(grid), dim3(v == 1 ? MG_TPB : LI_TPB), args, smem, st));
         c->launches++;
+#ifdef MG_TRACE
+        if (trbuf) {
+            cudaStreamSynchronize(st);
+            std::vector<unsigned long long> h((size_t)nts * 8);
+            cudaMemcpy(h.data(), trbuf, h.size() * 8, cudaMemcpyDeviceToHost);
+            FILE *f = fopen(getenv("SWO_MG_TRACE"), "wb");
+            if (f) { fwrite(h.data(), 8, h.size(), f); fclose(f); }
+            unsigned long long *z = nullptr;
+            cudaMemcpyToSymbol(mg_trace, &z, sizeof z);
+            cudaFree(trbuf);
+        }
+#endif
     }
     CK(c, cudaGetLastError());
     return SWO_OK;
