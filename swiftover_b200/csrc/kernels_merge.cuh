@@ -25,16 +25,22 @@
 //     adds its row total to the tile's and the group's look-back words right after its search
 //     (device_util.cuh: two-level look-back with per-warp publication), parks its results in a
 //     shared-memory ring, and the CTA stores a tile MG_DEPTH iterations later, when its exclusive
-//     prefix is available without waiting (one warp resolves it in front of the barrier at which
-//     the warps exchange their totals).
-//   * The next ticket is drawn by the warp that finishes its stores LAST: a ticket held while
-//     anything but its own search lies ahead delays that tile's publication, every later tile's
-//     look-back waits for it, and the waiting CTAs hold tickets too (a convoy; measured 2-4x
-//     slower with the ticket drawn ahead of the barrier or by a fixed thread).
+//     prefix is available without waiting (the first warp to finish its search resolves it in front
+//     of the one barrier at which the warps exchange their totals).
+//   * Tiles are dealt round-robin (tile = CTA + k * grid) and the kernel is launched COOPERATIVELY
+//     (all CTAs resident: a CTA may wait for any other's publication).  A ticket counter would
+//     not need that, but it puts an atomic round trip and a second barrier on every iteration
+//     and — worse — any ticket drawn before its search can start at once delays that tile's
+//     publication, every later tile's look-back waits for it, and the waiting CTAs hold
+//     tickets too: a convoy (measured 2-4x slower whenever a ticket was drawn ahead of a barrier,
+//     of the stores or of a look-back).  With the static deal the next tile is known, so its
+//     queries are in shared memory before they are needed: one thread arms an mbarrier and issues
+//     three 1-D bulk copies (TMA, cp.async.bulk: UBLKCP in the SASS) two iterations ahead.
 //   * Queries with 2..MG_SMALL candidate blocks are expanded by their own thread at store time
-//     (sequentially when their rows are already in qStart order, forwards or backwards); larger
-//     ones by their warp (expand_query_coop, kernels_binary.cuh).
-//   * The queries of the tile one grid ahead in ticket order are prefetched into L2.
+//     (sequentially when their rows are already in qStart order, forwards or backwards).  Larger
+//     ones — whose cost would throw the static deal off balance — are appended to a list
+//     {query, first block, candidates, row position} and expanded by expand_wide_kernel, a warp
+//     per query, after this kernel (list full: by their warp, on the spot).
 // Only for target-disjoint tables (every UCSC over.chain; the host sends other tables to the
 // per-query-search variant): candidates == hits, and pmaxKey[j] == tEnd[j].
 #pragma once
@@ -62,9 +68,6 @@ __device__ __forceinline__ unsigned long long gtimer() {
 // A pending query's three words: w0 = code << 24 | row meta; code = hits (0, 1, ... 254; 255 = "255 or
 // more": the count is in w2).  One hit: w0 also holds the row's {qcid, strand byte}, w1/w2 its
 // {start, end}.  Several hits: w1 = first candidate block, w2 = candidates (= hits).
-#ifndef MG_PF_AHEAD
-#define MG_PF_AHEAD 1  // L2 prefetch distance in grids of tiles (0 = off)
-#endif
 constexpr int MG_SMALL = 16;   // candidates up to which a multi-hit query is expanded by its own thread
 constexpr int MG_XS = 128;     // per-warp sort scratch in shared memory (entries)
 constexpr int MG_GXS = 2048;   // per-warp sort scratch in global memory (entries)
@@ -87,17 +90,23 @@ constexpr int MG_TPB = MG_NW * 32;
 constexpr int MG_TILE = MG_NW * MG_QPW;  // queries per tile
 
 struct MergeSmem {
+    int4 q[2][3][MG_TPB];                  // the queries of the tile in work / the one after the next: {tcid}, {start}, {end}
     int4 carry[MG_RING][3][MG_TPB];        // a thread's four pending queries per tile in flight: {w0}, {w1}, {w2}
     uint32_t poff[MG_RING][MG_TPB];        //   and the tile-local offset of its first row
     int4 cmeta[LI_CM_CAP];                 // per-contig {first block, end block, sample offset, samples}
     int32_t smp[ChainTable::EY_CAP];       // group maxima of pmaxKey in SORTED order (per contig)
     unsigned long long xscr[MG_NW][MG_XS]; // sort scratch of a warp's cooperative expansion
-    unsigned long long gbase;              // exclusive prefix of the tile being stored
-    int ptile[MG_RING];                    // the tiles in flight
-    uint32_t wtot[MG_NW];                  // rows of each warp's 128 queries
-    int next;                              // ticket of the next tile
-    unsigned done;                         // warps that have finished their stores (running count)
+    unsigned long long gbase[2];           // exclusive prefix of the tile being stored (alternating)
+    uint64_t qbar[2];                      // mbarriers of the two query stages
+    uint32_t wtot[2][MG_NW];               // rows of each warp's 128 queries (alternating)
     unsigned arrive;                       // warps that have finished their searches (running count)
+};
+
+// Multi-hit queries left for expand_wide_kernel: {query, first candidate block, candidates, row position}
+struct WideList {
+    unsigned *count;  // appended so far (may run past cap: those were expanded on the spot)
+    uint4 *ent;
+    unsigned cap;
 };
 
 // first i in [lo, hi] with key[i] > x, where hi is either a position known to hold a key > x or
@@ -305,13 +314,24 @@ __device__ __noinline__ void expand_small(const LiftArgs &A, uint32_t q, int lo,
     }
 }
 
+// one multi-hit query by a whole warp: sort keys in shared memory, in the warp's global scratch, or
+// (beyond that) every candidate ranks itself against all others
+__device__ __forceinline__ void expand_wide(const LiftArgs &A, const RowSink &sink, uint32_t q, int lo, int cnt, uint64_t pos,
+                                            unsigned long long *xs, unsigned long long *gxs) {
+    if (cnt <= MG_XS) expand_query_coop<false, false>(A, sink, A.T.ey, q, lo, cnt, pos, xs, nullptr, lane_id(), 32);
+    else if (cnt <= MG_GXS) expand_query_coop<false, false>(A, sink, A.T.ey, q, lo, cnt, pos, gxs, nullptr, lane_id(), 32);
+    else expand_query<false>(A, sink, A.T.ey, q, lo, cnt, pos, lane_id(), 32);
+}
+
 template <bool STRAND>
-__global__ void __launch_bounds__(MG_TPB, MG_CTAS) lift_sorted_kernel(const __grid_constant__ LiftArgs A, const __grid_constant__ Lb2 L) {
+__global__ void __launch_bounds__(MG_TPB, MG_CTAS) lift_sorted_kernel(const __grid_constant__ LiftArgs A, const __grid_constant__ Lb2 L,
+                                                                      const __grid_constant__ WideList W) {
     extern __shared__ __align__(16) unsigned char li_smem_raw[];
     MergeSmem &S = *reinterpret_cast<MergeSmem *>(li_smem_raw);
     if (__ldg(A.sorted_flag) == 0u) return;
 
     const int tid = threadIdx.x, lane = lane_id(), w = warp_id();
+    const int G = (int)gridDim.x;
     const TableView &T = A.T;
     const bool cm_smem = T.ntc <= LI_CM_CAP;
     if (cm_smem)
@@ -322,42 +342,49 @@ __global__ void __launch_bounds__(MG_TPB, MG_CTAS) lift_sorted_kernel(const __gr
         for (int i = lane; i < cm.w; i += 32) S.smp[cm.z + i] = __ldg(T.pmaxKey + cm.x + ((i + 1) << T.ey_shift) - 1);
     }
     const int last_block = __ldg(&T.cmeta[T.ntc - 1].y) - 1;
-    if (tid < MG_RING) S.ptile[tid] = -1;
+    // a tile's queries come through shared memory when the whole tile exists (not the batch's last, partial tile)
+    const auto tile_staged = [&](long long t) { return (t + 1) * MG_TILE <= (long long)A.n; };
+    const auto stage_tile = [&](int t, int st) {  // one thread: arm the stage's barrier, issue the three copies
+        mbar_expect_tx(&S.qbar[st], 3u * MG_TILE * 4u);
+        bulk_g2s(S.q[st][0], A.tcid + (size_t)t * MG_TILE, MG_TILE * 4u, &S.qbar[st]);
+        bulk_g2s(S.q[st][1], A.start + (size_t)t * MG_TILE, MG_TILE * 4u, &S.qbar[st]);
+        bulk_g2s(S.q[st][2], A.end + (size_t)t * MG_TILE, MG_TILE * 4u, &S.qbar[st]);
+    };
     if (tid == 0) {
-        S.next = (int)atomicAdd(A.ticket, 1u);
-        S.done = 0;
         S.arrive = 0;
+        mbar_init(&S.qbar[0], 1);
+        mbar_init(&S.qbar[1], 1);
+        mbar_init_fence();
+        const long long t0 = blockIdx.x, t1 = t0 + G;
+        if (t0 < A.ntiles && tile_staged(t0)) stage_tile((int)t0, 0);
+        if (t1 < A.ntiles && tile_staged(t1)) stage_tile((int)t1, 1);
     }
     __syncthreads();
-    int tile = S.next;
 
     const RowSink sink{A.rows, A.thick, A.rows_cap};
     unsigned long long *const gxs = A.gscr + ((size_t)blockIdx.x * MG_NW + w) * MG_GXS;
     const uint32_t cap32 = A.rows_cap > 0xffffffffull ? 0xffffffffu : (uint32_t)A.rows_cap;
-    int slot = 0;          // ring slot of the current tile; the tile stored in this iteration sits in slot+1 (mod MG_RING)
-    int drain = MG_DEPTH;  // iterations left once the tickets have run out
+    int slot = 0;  // ring slot of the current tile; the tile stored in this iteration sits in slot+1 (mod MG_RING)
     uint32_t unm_acc = 0;
 
-    for (;;) {
-        const bool live = tile < A.ntiles;
+    // iteration k: search tile blockIdx.x + k*G (while there is one) and store the tile of iteration k - MG_DEPTH
+    const int my_tiles = (int)blockIdx.x < A.ntiles ? (A.ntiles - (int)blockIdx.x + G - 1) / G : 0;
+    for (int k = 0; k < my_tiles + MG_DEPTH; k++) {
+        const long long tile_ll = (long long)blockIdx.x + (long long)k * G;
+        const bool live = k < my_tiles;
+        const int tile = live ? (int)tile_ll : A.ntiles;
+        const int par = k & 1;
+        const int o_tile = k >= MG_DEPTH ? (int)(tile_ll - (long long)MG_DEPTH * G) : -1;
         uint32_t tsum = 0;
         if (live) {
             if (tid == 0) MG_TR(tile, 0);
-            // the queries of the tile one grid ahead in ticket order (some CTA draws it about one iteration
-            // from now) are fetched into L2
-            {
-                const long long pt = (long long)tile + (long long)gridDim.x * MG_PF_AHEAD;
-                if (MG_PF_AHEAD && tid < 3 * MG_NW * 4 && (pt + 1) * MG_TILE <= (long long)A.n) {
-                    const int arr = tid / (MG_NW * 4);
-                    const int32_t *base = arr == 0 ? A.tcid : arr == 1 ? A.start : A.end;
-                    prefetch_l2(base + pt * MG_TILE + (tid % (MG_NW * 4)) * 32);
-                }
-            }
             const uint32_t q0 = (uint32_t)tile * MG_TILE + (uint32_t)tid * LI_IPT;
             int tc[LI_IPT], st[LI_IPT], en[LI_IPT];
-            const bool warp_full = (uint32_t)tile * MG_TILE + (uint32_t)(w + 1) * MG_QPW <= A.n;
-            if (warp_full) {
-                const int4 a = ld_stream_v4(A.tcid + q0), b = ld_stream_v4(A.start + q0), c = ld_stream_v4(A.end + q0);
+            const bool staged = tile_staged(tile_ll);
+            const bool warp_full = staged;
+            if (staged) {
+                mbar_wait(&S.qbar[par], (k >> 1) & 1);  // this stage's (k/2)-th use
+                const int4 a = S.q[par][0][tid], b = S.q[par][1][tid], c = S.q[par][2][tid];
                 tc[0] = a.x, tc[1] = a.y, tc[2] = a.z, tc[3] = a.w;
                 st[0] = b.x, st[1] = b.y, st[2] = b.z, st[3] = b.w;
                 en[0] = c.x, en[1] = c.y, en[2] = c.z, en[3] = c.w;
@@ -474,12 +501,10 @@ __global__ void __launch_bounds__(MG_TPB, MG_CTAS) lift_sorted_kernel(const __gr
         // the warp's rows: published at once (no tile waits for this CTA any more); hand-over at the barrier
         const uint32_t inc = warp_inclusive_scan(tsum);
         if (lane == 31) {
-            S.wtot[w] = inc;
+            S.wtot[par][w] = inc;
             if (live) lookback2_add(L, tile, (uint64_t)inc);
             if (live) MG_TRMAX(tile, 1);
         }
-        const int oslot = slot + 1 == MG_RING ? 0 : slot + 1;  // the tile searched MG_DEPTH iterations ago
-        const int o_tile = S.ptile[oslot];
         // the first warp to get here resolves the old tile's prefix while the others finish their searches
         int resolver = 0;
         if (o_tile >= 0) {
@@ -490,16 +515,25 @@ __global__ void __launch_bounds__(MG_TPB, MG_CTAS) lift_sorted_kernel(const __gr
             if (lane == 0) MG_TR(o_tile, 2);
             const uint64_t gb = lookback2_resolve<MG_NW>(L, o_tile);
             if (lane == 0) MG_TR(o_tile, 3);
-            if (lane == 0) S.gbase = gb;
+            if (lane == 0) S.gbase[par] = gb;
         }
-        __syncthreads();
+        __syncthreads();  // the only barrier of an iteration
+        // every thread has its queries of this stage in registers: the tile after the next goes in
+        if (tid == 0) {
+            const long long t2 = tile_ll + 2ll * G;
+            if (t2 < A.ntiles && tile_staged(t2)) {
+                fence_proxy_async();
+                stage_tile((int)t2, par);
+            }
+        }
         uint32_t wbase = 0;
 #pragma unroll
-        for (int i = 0; i < MG_NW; i++) wbase += i < w ? S.wtot[i] : 0u;
+        for (int i = 0; i < MG_NW; i++) wbase += i < w ? S.wtot[par][i] : 0u;
+        const int oslot = slot + 1 == MG_RING ? 0 : slot + 1;  // the tile searched MG_DEPTH iterations ago
 
-        // store the tile searched MG_DEPTH iterations ago: row offsets, single-hit rows, multi-hit queries
+        // store that tile: row offsets, single-hit rows, multi-hit queries
         if (o_tile >= 0) {
-            const uint64_t gb = S.gbase;
+            const uint64_t gb = S.gbase[par];
             const uint32_t p_q0 = (uint32_t)o_tile * MG_TILE + (uint32_t)tid * LI_IPT;
             const int4 c0 = S.carry[oslot][0][tid], c1 = S.carry[oslot][1][tid], c2 = S.carry[oslot][2][tid];
             const int p0[LI_IPT] = {c0.x, c0.y, c0.z, c0.w}, p1[LI_IPT] = {c1.x, c1.y, c1.z, c1.w},
@@ -509,50 +543,51 @@ __global__ void __launch_bounds__(MG_TPB, MG_CTAS) lift_sorted_kernel(const __gr
             pos[0] = (uint32_t)gb + S.poff[oslot][tid];
             unsigned multi = 0;
 #pragma unroll
-            for (int k = 0; k < LI_IPT; k++) {
-                const uint32_t code = (uint32_t)p0[k] >> 24;
-                pos[k + 1] = pos[k] + (code == 255u ? (uint32_t)p2[k] : code);
-                multi |= code >= 2u ? 1u << k : 0u;
-                if (code == 1u && pos[k] < cap32)
-                    st_stream_v4(A.rows + pos[k], make_int4(p0[k] & 0xffffff, p1[k], p2[k], (int)(p_q0 + k)));
+            for (int k2 = 0; k2 < LI_IPT; k2++) {
+                const uint32_t code = (uint32_t)p0[k2] >> 24;
+                pos[k2 + 1] = pos[k2] + (code == 255u ? (uint32_t)p2[k2] : code);
+                multi |= code >= 2u ? 1u << k2 : 0u;
+                if (code == 1u && pos[k2] < cap32)
+                    st_stream_v4(A.rows + pos[k2], make_int4(p0[k2] & 0xffffff, p1[k2], p2[k2], (int)(p_q0 + k2)));
             }
             if (p_q0 + LI_IPT <= A.n) {
                 st_stream_v4(A.row_offset + p_q0, make_int4((int)pos[0], (int)pos[1], (int)pos[2], (int)pos[3]));
             } else {
 #pragma unroll
-                for (int k = 0; k < LI_IPT; k++)
-                    if (p_q0 + k < A.n) A.row_offset[p_q0 + k] = pos[k];
+                for (int k2 = 0; k2 < LI_IPT; k2++)
+                    if (p_q0 + k2 < A.n) A.row_offset[p_q0 + k2] = pos[k2];
             }
             if (o_tile == A.ntiles - 1 && tid == MG_TPB - 1) {  // the batch's last thread: its last position is the total
                 const uint64_t all = gb + (uint64_t)(uint32_t)(pos[LI_IPT] - (uint32_t)gb);
                 A.row_offset[A.n] = (uint32_t)all;
                 A.totals[0] = all;
             }
-            // multi-hit queries: up to MG_SMALL candidates by their own thread, larger ones by the warp —
-            // all of it ahead of the ticket draw (no ticket is held meanwhile)
             if (__any_sync(FULL, multi != 0u)) {
-                unsigned wide = 0;  // queries for the whole warp
+                unsigned wide = 0;  // list full: queries for the whole warp
 #pragma unroll
-                for (int k = 0; k < LI_IPT; k++) {
-                    if ((multi >> k) & 1u) {
-                        if (p2[k] <= MG_SMALL) expand_small(A, p_q0 + k, p1[k], p2[k], gb + (uint64_t)(uint32_t)(pos[k] - (uint32_t)gb));
-                        else wide |= 1u << k;
+                for (int k2 = 0; k2 < LI_IPT; k2++) {
+                    if ((multi >> k2) & 1u) {
+                        if (p2[k2] <= MG_SMALL) {
+                            expand_small(A, p_q0 + k2, p1[k2], p2[k2], gb + (uint64_t)(uint32_t)(pos[k2] - (uint32_t)gb));
+                        } else {
+                            const unsigned e = atomicAdd(W.count, 1u);
+                            if (e < W.cap) W.ent[e] = make_uint4(p_q0 + k2, (unsigned)p1[k2], (unsigned)p2[k2], pos[k2]);
+                            else wide |= 1u << k2;
+                        }
                     }
                 }
                 converge(A);
                 if (__any_sync(FULL, wide != 0u)) {
 #pragma unroll 1
-                    for (int k = 0; k < LI_IPT; k++) {
-                        unsigned m = __ballot_sync(FULL, (wide >> k) & 1u);
+                    for (int k2 = 0; k2 < LI_IPT; k2++) {
+                        unsigned m = __ballot_sync(FULL, (wide >> k2) & 1u);
                         while (m) {
                             const int src = __ffs(m) - 1;
                             m &= m - 1;
-                            const uint32_t q = __shfl_sync(FULL, p_q0, src) + (uint32_t)k;
-                            const int qlo = __shfl_sync(FULL, p1[k], src), qcnt = __shfl_sync(FULL, p2[k], src);
-                            const uint64_t qpos = gb + (uint64_t)(uint32_t)(__shfl_sync(FULL, pos[k], src) - (uint32_t)gb);
-                            if (qcnt <= MG_XS) expand_query_coop<false, false>(A, sink, T.ey, q, qlo, qcnt, qpos, S.xscr[w], nullptr, lane, 32);
-                            else if (qcnt <= MG_GXS) expand_query_coop<false, false>(A, sink, T.ey, q, qlo, qcnt, qpos, gxs, nullptr, lane, 32);
-                            else expand_query<false>(A, sink, T.ey, q, qlo, qcnt, qpos, lane, 32);
+                            const uint32_t q = __shfl_sync(FULL, p_q0, src) + (uint32_t)k2;
+                            const int qlo = __shfl_sync(FULL, p1[k2], src), qcnt = __shfl_sync(FULL, p2[k2], src);
+                            const uint64_t qpos = gb + (uint64_t)(uint32_t)(__shfl_sync(FULL, pos[k2], src) - (uint32_t)gb);
+                            expand_wide(A, sink, q, qlo, qcnt, qpos, S.xscr[w], gxs);
                             converge(A);
                         }
                     }
@@ -561,18 +596,27 @@ __global__ void __launch_bounds__(MG_TPB, MG_CTAS) lift_sorted_kernel(const __gr
         }
         // the current tile enters the ring
         S.poff[slot][tid] = wbase + inc - tsum;
-        if (tid == 0) S.ptile[slot] = live ? tile : -1;
-        // The warp that finishes its stores last draws the next ticket (see the head of this file).
         __syncwarp();
-        if (lane == 0 && (atomicAdd(&S.done, 1u) & (MG_NW - 1)) == MG_NW - 1) S.next = live ? (int)atomicAdd(A.ticket, 1u) : A.ntiles;
-        __syncthreads();
         slot = oslot;
-        if (!live && --drain <= 0) break;
-        tile = live ? S.next : A.ntiles;
     }
-
     const uint32_t unm = warp_sum(unm_acc);
     if (lane == 0 && unm) atomicAdd((unsigned long long *)(A.totals + 1), (unsigned long long)unm);
+}
+
+// The queries lift_sorted_kernel left on the list: a warp per query.  Row positions are 32-bit
+// (the host rejects batches with 2^32 rows or more).
+__global__ void __launch_bounds__(256) expand_wide_kernel(const __grid_constant__ LiftArgs A, const __grid_constant__ WideList W) {
+    __shared__ unsigned long long xs[8][MG_XS];
+    if (__ldg(A.sorted_flag) == 0u) return;
+    const unsigned n = min(*W.count, W.cap);
+    const int w = warp_id();
+    const RowSink sink{A.rows, A.thick, A.rows_cap};
+    unsigned long long *const gxs = A.gscr + ((size_t)blockIdx.x * 8 + w) * MG_GXS;
+    for (unsigned e = blockIdx.x * 8 + w; e < n; e += gridDim.x * 8) {
+        const uint4 v = W.ent[e];
+        expand_wide(A, sink, v.x, (int)v.y, (int)v.z, (uint64_t)v.w, xs[w], gxs);
+        converge(A);
+    }
 }
 
 }  // namespace swo

@@ -97,7 +97,7 @@ struct Device {
     bool g_has_lower = false;
     int g_n = 0;
     // scratch for the look-back chains
-    DevBuf scratch, gscr;
+    DevBuf scratch, gscr, wide;
     // binary path buffers
     DevBuf b_in, b_off, b_rows, b_thick, b_tot;
     // text path: per-slot chunk buffers
@@ -327,35 +327,50 @@ int launch_lift_intervals(swo_ctx *c, Device &d, size_t n, const int32_t *tcid, 
         }
         LiftArgs Aw = A;
         int grid = std::min(ntiles, d.bin_grid[gi]);
-        if (v == 1) {  // its own tile size; per-warp sort scratch in global memory
+        if (v == 1) {
+            // Sorted variant: its own tile size, tiles dealt round-robin => every CTA must be resident
+            // (cooperative launch); per-warp sort scratch and the wide-query list in global memory;
+            // expand_wide_kernel works the list off afterwards.
             Aw.ntiles = nts;
             grid = std::min(nts, d.bin_grid[gi]);
             CK(c, d.gscr.reserve((size_t)d.bin_grid[gi] * MG_NW * MG_GXS * sizeof(unsigned long long)));
             Aw.gscr = d.gscr.as<unsigned long long>();
+            WideList W;
+            W.cap = (unsigned)std::min<size_t>(n / 128 + 65536, 0x7fffffffu);
+            CK(c, d.wide.reserve((size_t)W.cap * sizeof(uint4)));
+            W.ent = d.wide.as<uint4>();
+            W.count = reinterpret_cast<unsigned *>(d.scratch.as<char>() + 4);
+            void *cargs[] = {(void *)&Aw, (void *)&L, (void *)&W};
+#ifdef MG_TRACE
+            unsigned long long *trbuf = nullptr;
+            if (v == 1 && getenv("SWO_MG_TRACE")) {
+                cudaMalloc(&trbuf, (size_t)nts * 64);
+                cudaMemset(trbuf, 0, (size_t)nts * 64);
+                cudaMemcpyToSymbol(mg_trace, &trbuf, sizeof trbuf);
+            }
+#endif
+            CK(c, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(MG_TPB), cargs, smem, st));
+            c->launches++;
+#ifdef MG_TRACE
+            if (trbuf) {
+                cudaStreamSynchronize(st);
+                std::vector<unsigned long long> h((size_t)nts * 8);
+                cudaMemcpy(h.data(), trbuf, h.size() * 8, cudaMemcpyDeviceToHost);
+                FILE *f = fopen(getenv("SWO_MG_TRACE"), "wb");
+                if (f) { fwrite(h.data(), 8, h.size(), f); fclose(f); }
+                unsigned long long *z = nullptr;
+                cudaMemcpyToSymbol(mg_trace, &z, sizeof z);
+                cudaFree(trbuf);
+            }
+#endif
+            const int wgrid = std::max(1, grid * MG_NW / 8);
+            expand_wide_kernel<<<wgrid, 256, 0, st>>>(Aw, W);
+            c->launches++;
+            continue;
         }
         void *args[] = {(void *)&Aw, (void *)&L};
-#ifdef MG_TRACE
-        unsigned long long *trbuf = nullptr;
-        if (v == 1 && getenv("SWO_MG_TRACE")) {
-            cudaMalloc(&trbuf, (size_t)nts * 64);
-            cudaMemset(trbuf, 0, (size_t)nts * 64);
-            cudaMemcpyToSymbol(mg_trace, &trbuf, sizeof trbuf);
-        }
-#endif
         CK(c, cudaLaunchKernel(fn, dim3(grid), dim3(v == 1 ? MG_TPB : LI_TPB), args, smem, st));
         c->launches++;
-#ifdef MG_TRACE
-        if (trbuf) {
-            cudaStreamSynchronize(st);
-            std::vector<unsigned long long> h((size_t)nts * 8);
-            cudaMemcpy(h.data(), trbuf, h.size() * 8, cudaMemcpyDeviceToHost);
-            FILE *f = fopen(getenv("SWO_MG_TRACE"), "wb");
-            if (f) { fwrite(h.data(), 8, h.size(), f); fclose(f); }
-            unsigned long long *z = nullptr;
-            cudaMemcpyToSymbol(mg_trace, &z, sizeof z);
-            cudaFree(trbuf);
-        }
-#endif
     }
     CK(c, cudaGetLastError());
     return SWO_OK;
@@ -643,7 +658,7 @@ void swo_destroy(swo_ctx *c) {
         cudaSetDevice(d.ordinal);
         cudaDeviceSynchronize();
         for (DevBuf *b : {&d.blk, &d.tkey, &d.pkey, &d.toff, &d.cmeta, &d.ey, &d.thash, &d.tchars, &d.tnoff, &d.qoff, &d.qchars, &d.g_packed,
-                          &d.g_off, &d.g_len, &d.g_lower, &d.g_chunk, &d.g_estart, &d.g_elen, &d.g_ebyte, &d.scratch, &d.gscr, &d.b_in, &d.b_off, &d.b_rows, &d.b_thick, &d.b_tot})
+                          &d.g_off, &d.g_len, &d.g_lower, &d.g_chunk, &d.g_estart, &d.g_elen, &d.g_ebyte, &d.scratch, &d.gscr, &d.wide, &d.b_in, &d.b_off, &d.b_rows, &d.b_thick, &d.b_tot})
             b->release();
         for (int s = 0; s < N_SLOTS; s++) {
             d.t_in[s].release();
