@@ -198,88 +198,6 @@ __device__ __forceinline__ uint64_t lookback_resolve_block(uint64_t *desc, int t
     return excl;
 }
 
-// ---- two-level look-back with per-warp publication ------------------------------
-// For kernels whose tiles are small (many tiles in flight) and whose warps work on their own:
-// a tile's aggregate is the sum of its NW warps' totals, and every warp adds its total by
-// itself (no block exchange in front of the publication, so a tile's publication never waits
-// for anything but its own search).  Words, all 64-bit:
-//   desc[t]  count << 54 | sum   of the tile's warps            (complete at NW)
-//   acc[g]   count << 54 | sum   of a GROUP of 32 tiles' warps  (complete at 32*NW)
-//   inc[g]   LB_INC | inclusive prefix through group g — stored by EVERY resolver that has
-//            worked it out (same value from all), in an array of its own, so that the words the
-//            atomic adds hammer are polled only by the first resolver(s) of the next group.
-// A resolver reads, in one round trip, the (at most 31) earlier tiles of its group and inc of the
-// group before; only if that is missing does it walk the groups (32 per round, 1024 tiles).  All
-// waiting loops are warp-uniform (the round is read again), there is no divergent spin.
-constexpr int LBG_SHIFT = 5, LBG_TILES = 1 << LBG_SHIFT;
-constexpr int LBG_CNT_SHIFT = 54;
-constexpr unsigned long long LBG_SUM = (1ull << LBG_CNT_SHIFT) - 1;
-struct Lb2 {
-    unsigned long long *desc;  // [ntiles]
-    unsigned long long *acc;   // [ntiles/32 + 1]
-    uint64_t *inc;             // [ntiles/32 + 1]
-};
-// one thread per warp: add the warp's total to its tile and to the tile's group
-__device__ __forceinline__ void lookback2_add(const Lb2 &L, int tile, uint64_t warp_total) {
-    const unsigned long long v = (1ull << LBG_CNT_SHIFT) | warp_total;
-    atomicAdd(L.desc + tile, v);
-    atomicAdd(L.acc + (tile >> LBG_SHIFT), v);
-}
-__device__ __forceinline__ uint64_t warp_sum_u64(uint64_t v) {
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
-    return v;
-}
-// Inclusive prefix through group g (g >= 0) by walking back to the nearest published one; stores
-// it for everybody else.  One full, converged warp; GROUP_FULL = contributions of a complete group.
-template <int GROUP_FULL>
-__device__ __noinline__ uint64_t lookback2_walk(const Lb2 &L, int g) {
-    const int lane = lane_id();
-    uint64_t sum = 0;
-    int look = g;
-    for (;;) {
-        const int idx = look - lane;
-        unsigned long long inc = LB_INC, acc = 0;  // virtual group before group 0: inclusive prefix 0
-        if (idx >= 0) {
-            inc = ld_relaxed_u64(L.inc + idx);
-            acc = ld_relaxed_u64(reinterpret_cast<const uint64_t *>(L.acc + idx));
-        }
-        const unsigned m = __ballot_sync(FULL, (inc & LB_STATE) == LB_INC);
-        const unsigned full = __ballot_sync(FULL, (acc >> LBG_CNT_SHIFT) == (unsigned long long)GROUP_FULL);
-        const int f = m ? (__ffs(m) - 1) : 32;
-        const unsigned need = f >= 32 ? FULL : ((1u << f) - 1u);  // groups nearer than the first inclusive one
-        if ((need & ~full) != 0u) {
-            __nanosleep(100);  // one of them has not been published completely yet: look again
-            continue;
-        }
-        sum += lane < f ? (acc & LBG_SUM) : (lane == f ? (inc & LB_VALUE) : 0ull);
-        if (m != 0u) break;
-        look -= 32;
-    }
-    sum = warp_sum_u64(sum);
-    if (lane == 0) st_relaxed_u64(L.inc + g, LB_INC | sum);
-    return sum;
-}
-// one full, converged warp; NW = contributions per tile; returns the EXCLUSIVE prefix of `tile`
-// in every lane
-template <int NW>
-__device__ __forceinline__ uint64_t lookback2_resolve(const Lb2 &L, int tile) {
-    const int lane = lane_id();
-    const int g = tile >> LBG_SHIFT, r = tile & (LBG_TILES - 1);
-    uint64_t v, inc;
-    for (;;) {
-        v = (uint64_t)NW << LBG_CNT_SHIFT;
-        inc = LB_INC;
-        if (lane < r) v = ld_relaxed_u64(reinterpret_cast<const uint64_t *>(L.desc + (g << LBG_SHIFT) + lane));
-        if (g > 0) inc = ld_relaxed_u64(L.inc + g - 1);  // every lane the same word
-        if (__all_sync(FULL, (v >> LBG_CNT_SHIFT) == (uint64_t)NW)) break;
-        __nanosleep(100);  // an earlier tile of the group has not been published completely yet
-    }
-    uint64_t base = inc & LB_VALUE;
-    if ((inc & LB_STATE) != LB_INC) base = lookback2_walk<NW * LBG_TILES>(L, g - 1);  // warp-uniform
-    return base + warp_sum_u64(lane < r ? (v & LBG_SUM) : 0ull);
-}
-
 __device__ __forceinline__ uint64_t lookback_exclusive(uint64_t *desc, int tile, uint64_t aggregate) {
     lookback_publish(desc, tile, aggregate);
     return lookback_resolve(desc, tile, aggregate);

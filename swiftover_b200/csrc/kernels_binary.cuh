@@ -275,21 +275,27 @@ __device__ __forceinline__ void flush_pending(const LiftArgs &A, LiftSmem<THICK,
     if (tid == 0) S.p_tile = -1;
 }
 
-// Is the batch (mostly) sorted by position?  256 threads look at 2048 adjacent pairs spread over
+// Is the batch (mostly) sorted by position?  1024 threads look at 2048 adjacent pairs spread over
 // the batch; a pair counts when both queries name the same contig and the start does not move
-// back.  *flag = 1 when at least 7 of 8 pairs do.  Decides which kernel variant does the work.
-__global__ void __launch_bounds__(256) sample_sorted_kernel(const int32_t *__restrict__ tcid, const int32_t *__restrict__ start,
-                                                            uint32_t n, uint32_t *flag, uint32_t allow) {
+// back.  *flag = 1 when at least 7 of 8 pairs do (and the caller allows the sorted variant at all).
+// Decides which kernel variant does the work.
+__global__ void __launch_bounds__(1024) sample_sorted_kernel(const int32_t *__restrict__ tcid, const int32_t *__restrict__ start,
+                                                             uint32_t n, uint32_t *flag, uint32_t allow) {
     __shared__ unsigned s_cnt;
     if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
-    unsigned ok = 0;
     const uint32_t pairs = n > 1 ? n - 1 : 0, want = pairs < 2048u ? pairs : 2048u;
-    for (uint32_t j = threadIdx.x; j < want; j += 256) {
-        const uint32_t i = (uint32_t)(((unsigned long long)j * pairs) / want);
-        ok += (__ldg(tcid + i) == __ldg(tcid + i + 1) && __ldg(start + i) <= __ldg(start + i + 1)) ? 1u : 0u;
-    }
-    atomicAdd(&s_cnt, ok);
+    unsigned ok = 0;
+    const uint32_t j0 = threadIdx.x, j1 = threadIdx.x + 1024u;
+    const uint32_t i0 = j0 < want ? (uint32_t)(((unsigned long long)j0 * pairs) / want) : 0u;
+    const uint32_t i1 = j1 < want ? (uint32_t)(((unsigned long long)j1 * pairs) / want) : 0u;
+    int a0 = 0, a1 = 0, b0 = 0, b1 = 0, c0 = 0, c1 = 0, d0 = 0, d1 = 0;
+    if (j0 < want) a0 = __ldg(tcid + i0), a1 = __ldg(tcid + i0 + 1), b0 = __ldg(start + i0), b1 = __ldg(start + i0 + 1);
+    if (j1 < want) c0 = __ldg(tcid + i1), c1 = __ldg(tcid + i1 + 1), d0 = __ldg(start + i1), d1 = __ldg(start + i1 + 1);
+    ok += (j0 < want && a0 == a1 && b0 <= b1) ? 1u : 0u;
+    ok += (j1 < want && c0 == c1 && d0 <= d1) ? 1u : 0u;
+    ok = warp_sum(ok);
+    if (lane_id() == 0 && ok) atomicAdd(&s_cnt, ok);
     __syncthreads();
     if (threadIdx.x == 0) *flag = (allow && s_cnt * 8u >= want * 7u) ? 1u : 0u;
 }

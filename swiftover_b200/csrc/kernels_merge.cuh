@@ -1,5 +1,6 @@
-// kernels_merge.cuh — the lift kernel for batches sorted by (contig, start): a warp-level
-// merge of queries against blocks instead of one tree search per query.
+// kernels_merge.cuh — the lift kernels for batches sorted by (contig, start): a warp-level
+// merge of queries against blocks instead of one tree search per query, as a count pass, a
+// prefix scan and a write pass.
 //
 // Replaces, like kernels_binary.cuh, the reference's per-record cf.lift(contig,start,end)
 // (chain.d:664-713) + sort by qStart + orderStartEnd + strand table (bed.d:156-173) for a whole
@@ -19,28 +20,23 @@
 //     where a block holds ~1,850 queries.  A query that runs past the window is finished by its
 //     thread (four lockstep gallops); a warp with several contigs (contig boundaries, the batch
 //     tail) takes the per-thread search of kernels_binary.cuh.  Any order inside the warp is fine.
+//   * Variable-length output, three launches (the count / scan / write scheme of the task's
+//     north star): merge_count_kernel stores every warp's row total and window position,
+//     scan_tiles_kernel{1,2} turn the totals into exclusive prefixes, merge_write_kernel repeats
+//     the merge from the stored window position (no search) and stores row offsets and rows at
+//     their final places.  The queries are read twice (24 instead of 12 bytes per query of DRAM
+//     traffic) — measured against single-pass forms of the same merge with a chained look-back
+//     (block tiles or warp tiles, tickets or a static deal, 1-3 tiles of deferral; all in this
+//     file's history) the two-pass form wins: there every tile's store waits for the slowest of
+//     the ~500-10,000 tiles in flight before it, a ticket held for anything but its own search
+//     starts a convoy, and the per-tile chain ticket -> load -> search -> publish -> resolve ->
+//     store leaves the SMs idle; here no warp ever waits for another.
 //   * The first candidate's row is computed without branches for every query (four block loads in
-//     flight per lane) and kept for single-hit queries.
-//   * Variable-length output without a count pass: a tile is MG_NW warps x 128 queries.  Every warp
-//     adds its row total to the tile's and the group's look-back words right after its search
-//     (device_util.cuh: two-level look-back with per-warp publication), parks its results in a
-//     shared-memory ring, and the CTA stores a tile MG_DEPTH iterations later, when its exclusive
-//     prefix is available without waiting (the first warp to finish its search resolves it in front
-//     of the one barrier at which the warps exchange their totals).
-//   * Tiles are dealt round-robin (tile = CTA + k * grid) and the kernel is launched COOPERATIVELY
-//     (all CTAs resident: a CTA may wait for any other's publication).  A ticket counter would
-//     not need that, but it puts an atomic round trip and a second barrier on every iteration
-//     and — worse — any ticket drawn before its search can start at once delays that tile's
-//     publication, every later tile's look-back waits for it, and the waiting CTAs hold
-//     tickets too: a convoy (measured 2-4x slower whenever a ticket was drawn ahead of a barrier,
-//     of the stores or of a look-back).  With the static deal the next tile is known, so its
-//     queries are in shared memory before they are needed: one thread arms an mbarrier and issues
-//     three 1-D bulk copies (TMA, cp.async.bulk: UBLKCP in the SASS) two iterations ahead.
-//   * Queries with 2..MG_SMALL candidate blocks are expanded by their own thread at store time
-//     (sequentially when their rows are already in qStart order, forwards or backwards).  Larger
-//     ones — whose cost would throw the static deal off balance — are appended to a list
-//     {query, first block, candidates, row position} and expanded by expand_wide_kernel, a warp
-//     per query, after this kernel (list full: by their warp, on the spot).
+//     flight per lane) and kept for single-hit queries.  Queries with 2..MG_SMALL candidate blocks
+//     are expanded by their own thread (sequentially when their rows are already in qStart order,
+//     forwards or backwards).  Larger ones are appended to a list {query, first block, candidates,
+//     row position} and expanded by expand_wide_kernel, a warp per query (list full: by their
+//     warp, on the spot).
 // Only for target-disjoint tables (every UCSC over.chain; the host sends other tables to the
 // per-query-search variant): candidates == hits, and pmaxKey[j] == tEnd[j].
 #pragma once
@@ -48,65 +44,35 @@
 
 namespace swo {
 
-#ifdef MG_TRACE
-// debug build: per tile {draw, last warp published, resolve begin, resolve end} in ns (globaltimer)
-__device__ unsigned long long *mg_trace;
-__device__ __forceinline__ unsigned long long gtimer() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
-#define MG_TR(tile, slot) do { if (mg_trace) mg_trace[(size_t)(tile) * 8 + (slot)] = gtimer(); } while (0)
-#define MG_TRMAX(tile, slot) do { if (mg_trace) atomicMax(&mg_trace[(size_t)(tile) * 8 + (slot)], gtimer()); } while (0)
-#define MG_TROR(tile, slot, v) do { if (mg_trace) atomicOr(&mg_trace[(size_t)(tile) * 8 + (slot)], (unsigned long long)(v)); } while (0)
-#else
-#define MG_TROR(tile, slot, v) do { } while (0)
-#define MG_TR(tile, slot) do { } while (0)
-#define MG_TRMAX(tile, slot) do { } while (0)
-#endif
 
-// A pending query's three words: w0 = code << 24 | row meta; code = hits (0, 1, ... 254; 255 = "255 or
-// more": the count is in w2).  One hit: w0 also holds the row's {qcid, strand byte}, w1/w2 its
-// {start, end}.  Several hits: w1 = first candidate block, w2 = candidates (= hits).
 constexpr int MG_SMALL = 16;   // candidates up to which a multi-hit query is expanded by its own thread
 constexpr int MG_XS = 128;     // per-warp sort scratch in shared memory (entries)
 constexpr int MG_GXS = 2048;   // per-warp sort scratch in global memory (entries)
-#ifndef MG_CTAS_OVR
-#define MG_CTAS_OVR 6
-#endif
-constexpr int MG_CTAS = MG_CTAS_OVR;  // resident CTAs per SM the register budget is set for
-#ifndef MG_DEPTH_OVR
-#define MG_DEPTH_OVR 2
-#endif
-constexpr int MG_DEPTH = MG_DEPTH_OVR;  // a tile is stored MG_DEPTH iterations after it was searched and published
-constexpr int MG_RING = MG_DEPTH + 1;
-static_assert(MG_DEPTH >= 1, "ring depth");
-constexpr int MG_QPW = 32 * LI_IPT;  // queries per warp and tile
-#ifndef MG_NW_OVR
-#define MG_NW_OVR 4
-#endif
-constexpr int MG_NW = MG_NW_OVR;        // warps per CTA
+constexpr int MG_QPW = 32 * LI_IPT;  // queries per warp pass ("tile")
+constexpr int MG_NW = 8;             // warps per CTA
 constexpr int MG_TPB = MG_NW * 32;
-constexpr int MG_TILE = MG_NW * MG_QPW;  // queries per tile
-
-struct MergeSmem {
-    int4 q[2][3][MG_TPB];                  // the queries of the tile in work / the one after the next: {tcid}, {start}, {end}
-    int4 carry[MG_RING][3][MG_TPB];        // a thread's four pending queries per tile in flight: {w0}, {w1}, {w2}
-    uint32_t poff[MG_RING][MG_TPB];        //   and the tile-local offset of its first row
-    int4 cmeta[LI_CM_CAP];                 // per-contig {first block, end block, sample offset, samples}
-    int32_t smp[ChainTable::EY_CAP];       // group maxima of pmaxKey in SORTED order (per contig)
-    unsigned long long xscr[MG_NW][MG_XS]; // sort scratch of a warp's cooperative expansion
-    unsigned long long gbase[2];           // exclusive prefix of the tile being stored (alternating)
-    uint64_t qbar[2];                      // mbarriers of the two query stages
-    uint32_t wtot[2][MG_NW];               // rows of each warp's 128 queries (alternating)
-    unsigned arrive;                       // warps that have finished their searches (running count)
-};
+#ifndef MG_WRITE_CTAS
+#define MG_WRITE_CTAS 3
+#endif
+constexpr int MG_SCAN_ITEMS = 16, MG_SCAN_TILE = 256 * MG_SCAN_ITEMS;  // scan_tiles_kernel1: tiles per CTA
 
 // Multi-hit queries left for expand_wide_kernel: {query, first candidate block, candidates, row position}
 struct WideList {
     unsigned *count;  // appended so far (may run past cap: those were expanded on the spot)
     uint4 *ent;
     unsigned cap;
+};
+// per warp tile, between the passes
+struct MergeTiles {
+    uint32_t *total;          // [ntw] rows of the tile; after the scan: exclusive prefix inside its scan tile
+    int32_t *window;          // [ntw] first block of the tile's window, -1: per-query search
+    unsigned long long *sum;  // [ntw / MG_SCAN_TILE + 1] rows per scan tile; after the scan: exclusive prefix
+};
+
+struct MergeSmem {
+    int4 cmeta[LI_CM_CAP];                 // per-contig {first block, end block, sample offset, samples}
+    int32_t smp[ChainTable::EY_CAP];       // group maxima of pmaxKey in SORTED order (per contig)
+    unsigned long long xscr[MG_NW][MG_XS]; // sort scratch of a warp's cooperative expansion (write pass)
 };
 
 // first i in [lo, hi] with key[i] > x, where hi is either a position known to hold a key > x or
@@ -323,287 +289,315 @@ __device__ __forceinline__ void expand_wide(const LiftArgs &A, const RowSink &si
     else expand_query<false>(A, sink, A.T.ey, q, lo, cnt, pos, lane_id(), 32);
 }
 
-template <bool STRAND>
-__global__ void __launch_bounds__(MG_TPB, MG_CTAS) lift_sorted_kernel(const __grid_constant__ LiftArgs A, const __grid_constant__ Lb2 L,
-                                                                      const __grid_constant__ WideList W) {
+// The window merge of one warp: blocks [wb, wb+64) of a contig ending at block `cend` against the
+// lane's four queries (all of the warp's queries on that contig, none starting before smin).
+__device__ __forceinline__ void merge_window(const TableView &T, int wb, int cend, int smin, const int (&st)[LI_IPT],
+                                             const int (&en)[LI_IPT], int (&lo)[LI_IPT], int (&hi)[LI_IPT]) {
+    const int lane = lane_id();
+    const int ja = wb + lane, jb = wb + 32 + lane;
+    const int pmA = ja < cend ? __ldg(T.pmaxKey + ja) : 0x7fffffff, tsA = ja < cend ? __ldg(T.tStartKey + ja) : 0x7fffffff;
+    const int pmB = jb < cend ? __ldg(T.pmaxKey + jb) : 0x7fffffff, tsB = jb < cend ? __ldg(T.tStartKey + jb) : 0x7fffffff;
+    // blocks of the window that end at or before the smallest start lie before every query
+    int jj = __popc(__ballot_sync(FULL, pmA <= smin));
+    if (jj == 32) jj += __popc(__ballot_sync(FULL, pmB <= smin));
+    const int w_end = wb + 64;
+#pragma unroll
+    for (int k = 0; k < LI_IPT; k++) lo[k] = hi[k] = wb + jj;
+#pragma unroll 1
+    for (; jj < 64; jj++) {
+        const int pmj = __shfl_sync(FULL, jj < 32 ? pmA : pmB, jj), tsj = __shfl_sync(FULL, jj < 32 ? tsA : tsB, jj);
+        if (!merge_step(pmj, tsj, st, en, lo, hi)) break;
+    }
+    if (jj == 64) {  // some query runs past the window: its thread finishes it (four searches in lockstep)
+        unsigned act_lo = 0, act_hi = 0;
+#pragma unroll
+        for (int k = 0; k < LI_IPT; k++) {
+            act_hi |= hi[k] == w_end ? 1u << k : 0u;
+            act_lo |= lo[k] == w_end ? 1u << k : 0u;  // implies the same bit of act_hi
+        }
+        if (act_lo) {
+            const Int4x r = gallop4<false>(T.pmaxKey, cend, Int4x{{lo[0], lo[1], lo[2], lo[3]}}, Int4x{{st[0], st[1], st[2], st[3]}}, act_lo);
+#pragma unroll
+            for (int k = 0; k < LI_IPT; k++) lo[k] = r.v[k];
+        }
+        if (act_hi) {
+            Int4x base;
+#pragma unroll
+            for (int k = 0; k < LI_IPT; k++) base.v[k] = lo[k] > w_end ? lo[k] : w_end;
+            const Int4x r = gallop4<true>(T.tStartKey, cend, base, Int4x{{en[0], en[1], en[2], en[3]}}, act_hi);
+#pragma unroll
+            for (int k = 0; k < LI_IPT; k++)
+                if ((act_hi >> k) & 1u) hi[k] = r.v[k];
+        }
+        __syncwarp();
+    }
+}
+
+// the lane's four queries of tile `tile` (tcid -1 / empty interval behind the end of the batch)
+__device__ __forceinline__ void load_queries(const LiftArgs &A, uint32_t q0, bool full, int (&tc)[LI_IPT], int (&st)[LI_IPT],
+                                             int (&en)[LI_IPT]) {
+    if (full) {
+        const int4 a = ld_stream_v4(A.tcid + q0), b = ld_stream_v4(A.start + q0), c = ld_stream_v4(A.end + q0);
+        tc[0] = a.x, tc[1] = a.y, tc[2] = a.z, tc[3] = a.w;
+        st[0] = b.x, st[1] = b.y, st[2] = b.z, st[3] = b.w;
+        en[0] = c.x, en[1] = c.y, en[2] = c.z, en[3] = c.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < LI_IPT; k++) {
+            const bool ok = q0 + k < A.n;
+            tc[k] = ok ? A.tcid[q0 + k] : -1;
+            st[k] = ok ? A.start[q0 + k] : 0;
+            en[k] = ok ? A.end[q0 + k] : 0;
+        }
+    }
+}
+
+// the warp's next tile (known: tiles are dealt round-robin) into L2
+__device__ __forceinline__ void prefetch_queries(const LiftArgs &A, long long tile) {
+    const int lane = lane_id();
+    if (lane < 12 && (tile + 1) * MG_QPW <= (long long)A.n) {
+        const int32_t *base = lane < 4 ? A.tcid : lane < 8 ? A.start : A.end;
+        prefetch_l2(base + tile * MG_QPW + (lane & 3) * 32);
+    }
+}
+
+__device__ __forceinline__ void merge_tables(const TableView &T, MergeSmem &S, bool samples) {
+    const int tid = threadIdx.x, lane = lane_id(), w = warp_id();
+    if (T.ntc <= LI_CM_CAP)
+        for (int i = tid; i < T.ntc; i += MG_TPB) S.cmeta[i] = __ldg(T.cmeta + i);
+    // group maxima in sorted order: sample i of contig c is the last key of its i-th full group
+    if (samples)
+        for (int c = w; c < T.ntc; c += MG_NW) {
+            const int4 cm = __ldg(T.cmeta + c);
+            for (int i = lane; i < cm.w; i += 32) S.smp[cm.z + i] = __ldg(T.pmaxKey + cm.x + ((i + 1) << T.ey_shift) - 1);
+        }
+    __syncthreads();
+}
+
+// Pass 1: rows and window position of every warp tile; unmatched count.
+__global__ void __launch_bounds__(MG_TPB, 4) merge_count_kernel(const __grid_constant__ LiftArgs A, const __grid_constant__ MergeTiles M) {
     extern __shared__ __align__(16) unsigned char li_smem_raw[];
     MergeSmem &S = *reinterpret_cast<MergeSmem *>(li_smem_raw);
     if (__ldg(A.sorted_flag) == 0u) return;
-
-    const int tid = threadIdx.x, lane = lane_id(), w = warp_id();
-    const int G = (int)gridDim.x;
     const TableView &T = A.T;
+    merge_tables(T, S, true);
+    const int lane = lane_id();
     const bool cm_smem = T.ntc <= LI_CM_CAP;
-    if (cm_smem)
-        for (int i = tid; i < T.ntc; i += MG_TPB) S.cmeta[i] = __ldg(T.cmeta + i);
-    // group maxima in sorted order: sample i of contig c is the last key of its i-th full group
-    for (int c = w; c < T.ntc; c += MG_NW) {
-        const int4 cm = __ldg(T.cmeta + c);
-        for (int i = lane; i < cm.w; i += 32) S.smp[cm.z + i] = __ldg(T.pmaxKey + cm.x + ((i + 1) << T.ey_shift) - 1);
-    }
-    const int last_block = __ldg(&T.cmeta[T.ntc - 1].y) - 1;
-    // a tile's queries come through shared memory when the whole tile exists (not the batch's last, partial tile)
-    const auto tile_staged = [&](long long t) { return (t + 1) * MG_TILE <= (long long)A.n; };
-    const auto stage_tile = [&](int t, int st) {  // one thread: arm the stage's barrier, issue the three copies
-        mbar_expect_tx(&S.qbar[st], 3u * MG_TILE * 4u);
-        bulk_g2s(S.q[st][0], A.tcid + (size_t)t * MG_TILE, MG_TILE * 4u, &S.qbar[st]);
-        bulk_g2s(S.q[st][1], A.start + (size_t)t * MG_TILE, MG_TILE * 4u, &S.qbar[st]);
-        bulk_g2s(S.q[st][2], A.end + (size_t)t * MG_TILE, MG_TILE * 4u, &S.qbar[st]);
-    };
-    if (tid == 0) {
-        S.arrive = 0;
-        mbar_init(&S.qbar[0], 1);
-        mbar_init(&S.qbar[1], 1);
-        mbar_init_fence();
-        const long long t0 = blockIdx.x, t1 = t0 + G;
-        if (t0 < A.ntiles && tile_staged(t0)) stage_tile((int)t0, 0);
-        if (t1 < A.ntiles && tile_staged(t1)) stage_tile((int)t1, 1);
-    }
-    __syncthreads();
-
-    const RowSink sink{A.rows, A.thick, A.rows_cap};
-    unsigned long long *const gxs = A.gscr + ((size_t)blockIdx.x * MG_NW + w) * MG_GXS;
-    const uint32_t cap32 = A.rows_cap > 0xffffffffull ? 0xffffffffu : (uint32_t)A.rows_cap;
-    int slot = 0;  // ring slot of the current tile; the tile stored in this iteration sits in slot+1 (mod MG_RING)
+    const int nwarps = (int)gridDim.x * MG_NW;
     uint32_t unm_acc = 0;
-
-    // iteration k: search tile blockIdx.x + k*G (while there is one) and store the tile of iteration k - MG_DEPTH
-    const int my_tiles = (int)blockIdx.x < A.ntiles ? (A.ntiles - (int)blockIdx.x + G - 1) / G : 0;
-    for (int k = 0; k < my_tiles + MG_DEPTH; k++) {
-        const long long tile_ll = (long long)blockIdx.x + (long long)k * G;
-        const bool live = k < my_tiles;
-        const int tile = live ? (int)tile_ll : A.ntiles;
-        const int par = k & 1;
-        const int o_tile = k >= MG_DEPTH ? (int)(tile_ll - (long long)MG_DEPTH * G) : -1;
+    for (int tile = (int)blockIdx.x * MG_NW + warp_id(); tile < A.ntiles; tile += nwarps) {
+        const uint32_t q0 = (uint32_t)tile * MG_QPW + (uint32_t)lane * LI_IPT;
+        const bool full = (uint32_t)(tile + 1) * MG_QPW <= A.n;
+        int tc[LI_IPT], st[LI_IPT], en[LI_IPT], lo[LI_IPT], hi[LI_IPT];
+        load_queries(A, q0, full, tc, st, en);
+        prefetch_queries(A, (long long)tile + nwarps);
+        const int tc0 = __shfl_sync(FULL, tc[0], 0);
+        const bool same = __all_sync(FULL, tc[0] == tc0 && tc[1] == tc0 && tc[2] == tc0 && tc[3] == tc0) && tc0 >= 0 && tc0 < T.ntc;
+        int wb = -1;
+        if (same) {
+            const int4 cm = cm_smem ? S.cmeta[tc0] : load_cmeta(T, tc0);
+            const int m01 = st[0] < st[1] ? st[0] : st[1], m23 = st[2] < st[3] ? st[2] : st[3];
+            const int smin = __reduce_min_sync(FULL, m01 < m23 ? m01 : m23);
+            // The warp's window: 64 consecutive blocks that contain the lower bound of its smallest start.
+            // Groups of 32 blocks (every table up to 65,536 blocks): the group found in the shared-memory
+            // samples and the one behind it, no probe of the key array in between; larger groups: the
+            // window starts at the lower bound itself (one more search round trip).
+            const int gi = coop_lower_gt(S.smp + cm.z, 0, cm.w, smin);
+            const int g_lo = cm.x + (gi << T.ey_shift);
+            wb = g_lo;
+            if (T.ey_shift != 5) wb = coop_lower_gt(T.pmaxKey, g_lo, gi < cm.w ? g_lo + (1 << T.ey_shift) - 1 : cm.y, smin);
+            merge_window(T, wb, cm.y, smin, st, en, lo, hi);
+        } else {
+            const LoHi4 r = search_each(A, q0);  // several contigs in the warp (or the batch tail)
+#pragma unroll
+            for (int k = 0; k < LI_IPT; k++) lo[k] = r.lo[k], hi[k] = r.hi[k];
+            converge(A);
+        }
         uint32_t tsum = 0;
-        if (live) {
-            if (tid == 0) MG_TR(tile, 0);
-            const uint32_t q0 = (uint32_t)tile * MG_TILE + (uint32_t)tid * LI_IPT;
-            int tc[LI_IPT], st[LI_IPT], en[LI_IPT];
-            const bool staged = tile_staged(tile_ll);
-            const bool warp_full = staged;
-            if (staged) {
-                mbar_wait(&S.qbar[par], (k >> 1) & 1);  // this stage's (k/2)-th use
-                const int4 a = S.q[par][0][tid], b = S.q[par][1][tid], c = S.q[par][2][tid];
-                tc[0] = a.x, tc[1] = a.y, tc[2] = a.z, tc[3] = a.w;
-                st[0] = b.x, st[1] = b.y, st[2] = b.z, st[3] = b.w;
-                en[0] = c.x, en[1] = c.y, en[2] = c.z, en[3] = c.w;
-            } else {
 #pragma unroll
-                for (int k = 0; k < LI_IPT; k++) {
-                    const bool ok = q0 + k < A.n;
-                    tc[k] = ok ? A.tcid[q0 + k] : -1;
-                    st[k] = ok ? A.start[q0 + k] : 0;
-                    en[k] = ok ? A.end[q0 + k] : 0;
-                    unm_acc -= ok ? 0u : 1u;  // counted as "no hit" below
-                }
-            }
-            const int tc0 = __shfl_sync(FULL, tc[0], 0);
-            const bool same = __all_sync(FULL, tc[0] == tc0 && tc[1] == tc0 && tc[2] == tc0 && tc[3] == tc0) &&
-                              tc0 >= 0 && tc0 < T.ntc;
-            int lo[LI_IPT], hi[LI_IPT];
-            if (lane == 0) MG_TRMAX(tile, 5);  // queries have arrived
-            if (lane == 0 && !same) MG_TROR(tile, 4, 1);
-            if (same) {
-                const int4 cm = cm_smem ? S.cmeta[tc0] : load_cmeta(T, tc0);
-                const int m01 = st[0] < st[1] ? st[0] : st[1], m23 = st[2] < st[3] ? st[2] : st[3];
-                const int smin = __reduce_min_sync(FULL, m01 < m23 ? m01 : m23);
-                // The warp's window: 64 consecutive blocks that contain the lower bound lo_w of its smallest
-                // start.  Groups of 32 blocks (every table up to 65,536 blocks): the group found in the
-                // shared-memory samples and the one behind it, no probe of the key array in between;
-                // larger groups: the window starts at lo_w itself (one more search round trip).
-                const int gi = coop_lower_gt(S.smp + cm.z, 0, cm.w, smin);
-                const int g_lo = cm.x + (gi << T.ey_shift);
-                int wb = g_lo;
-                if (T.ey_shift != 5) wb = coop_lower_gt(T.pmaxKey, g_lo, gi < cm.w ? g_lo + (1 << T.ey_shift) - 1 : cm.y, smin);
-                const int ja = wb + lane, jb = wb + 32 + lane;
-                const int pmA = ja < cm.y ? __ldg(T.pmaxKey + ja) : 0x7fffffff, tsA = ja < cm.y ? __ldg(T.tStartKey + ja) : 0x7fffffff;
-                const int pmB = jb < cm.y ? __ldg(T.pmaxKey + jb) : 0x7fffffff, tsB = jb < cm.y ? __ldg(T.tStartKey + jb) : 0x7fffffff;
-                // blocks of the window that end at or before the smallest start lie before every query
-                int jj = __popc(__ballot_sync(FULL, pmA <= smin));
-                if (jj == 32) jj += __popc(__ballot_sync(FULL, pmB <= smin));
-                const int w_end = wb + 64;
-#pragma unroll
-                for (int k = 0; k < LI_IPT; k++) lo[k] = hi[k] = wb + jj;
-#pragma unroll 1
-                for (; jj < 64; jj++) {
-                    const int pmj = __shfl_sync(FULL, jj < 32 ? pmA : pmB, jj), tsj = __shfl_sync(FULL, jj < 32 ? tsA : tsB, jj);
-                    if (!merge_step(pmj, tsj, st, en, lo, hi)) break;
-                }
-                if (lane == 0) MG_TRMAX(tile, 6);  // window merged
-                if (jj == 64) {  // some query runs past the window: its thread finishes it (four searches in lockstep)
-                    if (lane == 0) MG_TROR(tile, 4, 2);
-                    unsigned act_lo = 0, act_hi = 0;
-#pragma unroll
-                    for (int k = 0; k < LI_IPT; k++) {
-                        act_hi |= hi[k] == w_end ? 1u << k : 0u;
-                        act_lo |= lo[k] == w_end ? 1u << k : 0u;  // implies the same bit of act_hi
-                    }
-                    if (act_lo) {
-                        const Int4x r = gallop4<false>(T.pmaxKey, cm.y, Int4x{{lo[0], lo[1], lo[2], lo[3]}},
-                                                       Int4x{{st[0], st[1], st[2], st[3]}}, act_lo);
-#pragma unroll
-                        for (int k = 0; k < LI_IPT; k++) lo[k] = r.v[k];
-                    }
-                    if (act_hi) {
-                        Int4x base;
-#pragma unroll
-                        for (int k = 0; k < LI_IPT; k++) base.v[k] = lo[k] > w_end ? lo[k] : w_end;
-                        const Int4x r = gallop4<true>(T.tStartKey, cm.y, base, Int4x{{en[0], en[1], en[2], en[3]}}, act_hi);
-#pragma unroll
-                        for (int k = 0; k < LI_IPT; k++)
-                            if ((act_hi >> k) & 1u) hi[k] = r.v[k];
-                    }
-                    __syncwarp();
-                }
-            } else {
-                // several contigs in the warp (or the batch tail): one search per query
-                const LoHi4 r = search_each(A, q0);
-#pragma unroll
-                for (int k = 0; k < LI_IPT; k++) lo[k] = r.lo[k], hi[k] = r.hi[k];
-                converge(A);
-            }
-            // Hits, and the row of the first candidate — computed without branches for every query (four
-            // independent block loads in flight); it is only kept for single-hit queries.
-            uchar4 sb4 = make_uchar4(0, 0, 0, 0);
-            if (STRAND) {
-                if (warp_full) sb4 = __ldg(reinterpret_cast<const uchar4 *>(A.strand + q0));
-                else {
-                    sb4.x = q0 + 0 < A.n ? A.strand[q0 + 0] : 0;
-                    sb4.y = q0 + 1 < A.n ? A.strand[q0 + 1] : 0;
-                    sb4.z = q0 + 2 < A.n ? A.strand[q0 + 2] : 0;
-                    sb4.w = q0 + 3 < A.n ? A.strand[q0 + 3] : 0;
-                }
-            }
-            const unsigned char sbk[LI_IPT] = {sb4.x, sb4.y, sb4.z, sb4.w};
-            Block bk[LI_IPT];
-#pragma unroll
-            for (int k = 0; k < LI_IPT; k++) bk[k] = load_block(T, lo[k] < last_block ? lo[k] : last_block);
-            int w0[LI_IPT], w1[LI_IPT], w2[LI_IPT];
-#pragma unroll
-            for (int k = 0; k < LI_IPT; k++) {
-                const int cnt = hi[k] > lo[k] ? hi[k] - lo[k] : 0;
-                const RowCore r = make_row(bk[k], st[k], en[k]);
-                const int meta = STRAND ? (r.qcid | ((int)strand_flip(sbk[k], r.inv) << 16)) : r.qcid;
-                const bool one = cnt == 1;
-                w0[k] = one ? ((1 << 24) | meta) : ((cnt < 255 ? cnt : 255) << 24);
-                w1[k] = one ? r.s : lo[k];
-                w2[k] = one ? r.e : cnt;
-                tsum += (uint32_t)cnt;
-                unm_acc += cnt == 0 ? 1u : 0u;
-            }
-            if (lane == 0) MG_TRMAX(tile, 7);  // rows computed
-            // the thread's results wait in its ring slot until the tile is stored
-            S.carry[slot][0][tid] = make_int4(w0[0], w0[1], w0[2], w0[3]);
-            S.carry[slot][1][tid] = make_int4(w1[0], w1[1], w1[2], w1[3]);
-            S.carry[slot][2][tid] = make_int4(w2[0], w2[1], w2[2], w2[3]);
+        for (int k = 0; k < LI_IPT; k++) {
+            const int cnt = hi[k] > lo[k] ? hi[k] - lo[k] : 0;
+            tsum += (uint32_t)cnt;
+            unm_acc += (cnt == 0 && (full || q0 + k < A.n)) ? 1u : 0u;
         }
-        // the warp's rows: published at once (no tile waits for this CTA any more); hand-over at the barrier
-        const uint32_t inc = warp_inclusive_scan(tsum);
-        if (lane == 31) {
-            S.wtot[par][w] = inc;
-            if (live) lookback2_add(L, tile, (uint64_t)inc);
-            if (live) MG_TRMAX(tile, 1);
+        const uint32_t total = __reduce_add_sync(FULL, tsum);
+        if (lane == 0) {
+            M.total[tile] = total;
+            M.window[tile] = wb;
         }
-        // the first warp to get here resolves the old tile's prefix while the others finish their searches
-        int resolver = 0;
-        if (o_tile >= 0) {
-            if (lane == 0) resolver = (atomicAdd(&S.arrive, 1u) & (MG_NW - 1)) == 0u;
-            resolver = __shfl_sync(FULL, resolver, 0);
-        }
-        if (resolver) {
-            if (lane == 0) MG_TR(o_tile, 2);
-            const uint64_t gb = lookback2_resolve<MG_NW>(L, o_tile);
-            if (lane == 0) MG_TR(o_tile, 3);
-            if (lane == 0) S.gbase[par] = gb;
-        }
-        __syncthreads();  // the only barrier of an iteration
-        // every thread has its queries of this stage in registers: the tile after the next goes in
-        if (tid == 0) {
-            const long long t2 = tile_ll + 2ll * G;
-            if (t2 < A.ntiles && tile_staged(t2)) {
-                fence_proxy_async();
-                stage_tile((int)t2, par);
-            }
-        }
-        uint32_t wbase = 0;
-#pragma unroll
-        for (int i = 0; i < MG_NW; i++) wbase += i < w ? S.wtot[par][i] : 0u;
-        const int oslot = slot + 1 == MG_RING ? 0 : slot + 1;  // the tile searched MG_DEPTH iterations ago
-
-        // store that tile: row offsets, single-hit rows, multi-hit queries
-        if (o_tile >= 0) {
-            const uint64_t gb = S.gbase[par];
-            const uint32_t p_q0 = (uint32_t)o_tile * MG_TILE + (uint32_t)tid * LI_IPT;
-            const int4 c0 = S.carry[oslot][0][tid], c1 = S.carry[oslot][1][tid], c2 = S.carry[oslot][2][tid];
-            const int p0[LI_IPT] = {c0.x, c0.y, c0.z, c0.w}, p1[LI_IPT] = {c1.x, c1.y, c1.z, c1.w},
-                      p2[LI_IPT] = {c2.x, c2.y, c2.z, c2.w};
-            // row indices are 32-bit (the host rejects batches with 2^32 rows or more)
-            uint32_t pos[LI_IPT + 1];
-            pos[0] = (uint32_t)gb + S.poff[oslot][tid];
-            unsigned multi = 0;
-#pragma unroll
-            for (int k2 = 0; k2 < LI_IPT; k2++) {
-                const uint32_t code = (uint32_t)p0[k2] >> 24;
-                pos[k2 + 1] = pos[k2] + (code == 255u ? (uint32_t)p2[k2] : code);
-                multi |= code >= 2u ? 1u << k2 : 0u;
-                if (code == 1u && pos[k2] < cap32)
-                    st_stream_v4(A.rows + pos[k2], make_int4(p0[k2] & 0xffffff, p1[k2], p2[k2], (int)(p_q0 + k2)));
-            }
-            if (p_q0 + LI_IPT <= A.n) {
-                st_stream_v4(A.row_offset + p_q0, make_int4((int)pos[0], (int)pos[1], (int)pos[2], (int)pos[3]));
-            } else {
-#pragma unroll
-                for (int k2 = 0; k2 < LI_IPT; k2++)
-                    if (p_q0 + k2 < A.n) A.row_offset[p_q0 + k2] = pos[k2];
-            }
-            if (o_tile == A.ntiles - 1 && tid == MG_TPB - 1) {  // the batch's last thread: its last position is the total
-                const uint64_t all = gb + (uint64_t)(uint32_t)(pos[LI_IPT] - (uint32_t)gb);
-                A.row_offset[A.n] = (uint32_t)all;
-                A.totals[0] = all;
-            }
-            if (__any_sync(FULL, multi != 0u)) {
-                unsigned wide = 0;  // list full: queries for the whole warp
-#pragma unroll
-                for (int k2 = 0; k2 < LI_IPT; k2++) {
-                    if ((multi >> k2) & 1u) {
-                        if (p2[k2] <= MG_SMALL) {
-                            expand_small(A, p_q0 + k2, p1[k2], p2[k2], gb + (uint64_t)(uint32_t)(pos[k2] - (uint32_t)gb));
-                        } else {
-                            const unsigned e = atomicAdd(W.count, 1u);
-                            if (e < W.cap) W.ent[e] = make_uint4(p_q0 + k2, (unsigned)p1[k2], (unsigned)p2[k2], pos[k2]);
-                            else wide |= 1u << k2;
-                        }
-                    }
-                }
-                converge(A);
-                if (__any_sync(FULL, wide != 0u)) {
-#pragma unroll 1
-                    for (int k2 = 0; k2 < LI_IPT; k2++) {
-                        unsigned m = __ballot_sync(FULL, (wide >> k2) & 1u);
-                        while (m) {
-                            const int src = __ffs(m) - 1;
-                            m &= m - 1;
-                            const uint32_t q = __shfl_sync(FULL, p_q0, src) + (uint32_t)k2;
-                            const int qlo = __shfl_sync(FULL, p1[k2], src), qcnt = __shfl_sync(FULL, p2[k2], src);
-                            const uint64_t qpos = gb + (uint64_t)(uint32_t)(__shfl_sync(FULL, pos[k2], src) - (uint32_t)gb);
-                            expand_wide(A, sink, q, qlo, qcnt, qpos, S.xscr[w], gxs);
-                            converge(A);
-                        }
-                    }
-                }
-            }
-        }
-        // the current tile enters the ring
-        S.poff[slot][tid] = wbase + inc - tsum;
-        __syncwarp();
-        slot = oslot;
     }
     const uint32_t unm = warp_sum(unm_acc);
     if (lane == 0 && unm) atomicAdd((unsigned long long *)(A.totals + 1), (unsigned long long)unm);
 }
 
-// The queries lift_sorted_kernel left on the list: a warp per query.  Row positions are 32-bit
+// Scan, step 1: every CTA turns MG_SCAN_TILE tile totals into exclusive prefixes (in place) and stores their sum.
+__global__ void __launch_bounds__(256) scan_tiles_kernel1(const uint32_t *flag, MergeTiles M, int ntw) {
+    __shared__ uint32_t scr[9];
+    if (__ldg(flag) == 0u) return;
+    const int base = (int)blockIdx.x * MG_SCAN_TILE + (int)threadIdx.x * MG_SCAN_ITEMS;
+    uint32_t v[MG_SCAN_ITEMS], run = 0;
+#pragma unroll
+    for (int i = 0; i < MG_SCAN_ITEMS; i += 4) {
+        int4 x = make_int4(0, 0, 0, 0);
+        if (base + i + 3 < ntw) x = *reinterpret_cast<const int4 *>(M.total + base + i);
+        else {
+            x.x = base + i < ntw ? (int)M.total[base + i] : 0;
+            x.y = base + i + 1 < ntw ? (int)M.total[base + i + 1] : 0;
+            x.z = base + i + 2 < ntw ? (int)M.total[base + i + 2] : 0;
+        }
+        v[i] = (uint32_t)x.x, v[i + 1] = (uint32_t)x.y, v[i + 2] = (uint32_t)x.z, v[i + 3] = (uint32_t)x.w;
+    }
+#pragma unroll
+    for (int i = 0; i < MG_SCAN_ITEMS; i++) {
+        const uint32_t t = v[i];
+        v[i] = run;
+        run += t;
+    }
+    uint32_t tot;
+    const uint32_t ex = block_exclusive_scan<uint32_t, 8>(run, scr, &tot);
+#pragma unroll
+    for (int i = 0; i < MG_SCAN_ITEMS; i++)
+        if (base + i < ntw) M.total[base + i] = ex + v[i];
+    if (threadIdx.x == 0) M.sum[blockIdx.x] = tot;  // a scan tile holds < 2^32 rows (the host rejects larger batches)
+}
+// Scan, step 2: one CTA scans the per-scan-tile sums; the grand total goes to totals[0] and row_offset[n].
+__global__ void __launch_bounds__(1024) scan_tiles_kernel2(const uint32_t *flag, MergeTiles M, int nsum, uint64_t *totals,
+                                                            uint32_t *row_offset_n) {
+    __shared__ unsigned long long scr[33];
+    if (__ldg(flag) == 0u) return;
+    unsigned long long carry = 0;
+    for (int b = 0; b < nsum; b += 1024) {
+        const int i = b + (int)threadIdx.x;
+        const unsigned long long v = i < nsum ? M.sum[i] : 0ull;
+        unsigned long long tot;
+        const unsigned long long ex = block_exclusive_scan<unsigned long long, 32>(v, scr, &tot);
+        if (i < nsum) M.sum[i] = carry + ex;
+        carry += tot;
+    }
+    if (threadIdx.x == 0) {
+        totals[0] = carry;
+        *row_offset_n = (uint32_t)carry;
+    }
+}
+
+// Pass 2: the merge again, from the stored window; row offsets and rows to their final places.
+template <bool STRAND>
+__global__ void __launch_bounds__(MG_TPB, MG_WRITE_CTAS) merge_write_kernel(const __grid_constant__ LiftArgs A, const __grid_constant__ MergeTiles M,
+                                                                const __grid_constant__ WideList W) {
+    extern __shared__ __align__(16) unsigned char li_smem_raw[];
+    MergeSmem &S = *reinterpret_cast<MergeSmem *>(li_smem_raw);
+    if (__ldg(A.sorted_flag) == 0u) return;
+    const TableView &T = A.T;
+    merge_tables(T, S, false);
+    const int lane = lane_id(), w = warp_id();
+    const bool cm_smem = T.ntc <= LI_CM_CAP;
+    const int nwarps = (int)gridDim.x * MG_NW;
+    const int last_block = __ldg(&T.cmeta[T.ntc - 1].y) - 1;
+    const RowSink sink{A.rows, A.thick, A.rows_cap};
+    unsigned long long *const gxs = A.gscr + ((size_t)blockIdx.x * MG_NW + w) * MG_GXS;
+    for (int tile = (int)blockIdx.x * MG_NW + w; tile < A.ntiles; tile += nwarps) {
+        const uint32_t q0 = (uint32_t)tile * MG_QPW + (uint32_t)lane * LI_IPT;
+        const bool full = (uint32_t)(tile + 1) * MG_QPW <= A.n;
+        int tc[LI_IPT], st[LI_IPT], en[LI_IPT], lo[LI_IPT], hi[LI_IPT];
+        load_queries(A, q0, full, tc, st, en);
+        prefetch_queries(A, (long long)tile + nwarps);
+        const int wb = __ldg(M.window + tile);
+        const uint64_t tbase = M.sum[tile / MG_SCAN_TILE] + (uint64_t)M.total[tile];
+        uchar4 sb4 = make_uchar4(0, 0, 0, 0);
+        if (STRAND) {
+            if (full) sb4 = __ldg(reinterpret_cast<const uchar4 *>(A.strand + q0));
+            else {
+                sb4.x = q0 + 0 < A.n ? A.strand[q0 + 0] : 0;
+                sb4.y = q0 + 1 < A.n ? A.strand[q0 + 1] : 0;
+                sb4.z = q0 + 2 < A.n ? A.strand[q0 + 2] : 0;
+                sb4.w = q0 + 3 < A.n ? A.strand[q0 + 3] : 0;
+            }
+        }
+        if (wb >= 0) {  // warp-uniform: one contig
+            const int tc0 = __shfl_sync(FULL, tc[0], 0);
+            const int4 cm = cm_smem ? S.cmeta[tc0] : load_cmeta(T, tc0);
+            const int m01 = st[0] < st[1] ? st[0] : st[1], m23 = st[2] < st[3] ? st[2] : st[3];
+            const int smin = __reduce_min_sync(FULL, m01 < m23 ? m01 : m23);
+            merge_window(T, wb, cm.y, smin, st, en, lo, hi);
+        } else {
+            const LoHi4 r = search_each(A, q0);
+#pragma unroll
+            for (int k = 0; k < LI_IPT; k++) lo[k] = r.lo[k], hi[k] = r.hi[k];
+            converge(A);
+        }
+        // Hits, and the row of the first candidate — computed without branches for every query (four
+        // independent block loads in flight); it is only stored for single-hit queries.
+        Block bk[LI_IPT];
+#pragma unroll
+        for (int k = 0; k < LI_IPT; k++) bk[k] = load_block(T, lo[k] < last_block ? lo[k] : last_block);
+        const unsigned char sbk[LI_IPT] = {sb4.x, sb4.y, sb4.z, sb4.w};
+        int cnt[LI_IPT];
+        uint32_t tsum = 0;
+#pragma unroll
+        for (int k = 0; k < LI_IPT; k++) {
+            cnt[k] = hi[k] > lo[k] ? hi[k] - lo[k] : 0;
+            tsum += (uint32_t)cnt[k];
+        }
+        const uint32_t inc = warp_inclusive_scan(tsum);
+        uint64_t pos = tbase + (inc - tsum);
+        const uint32_t o0 = (uint32_t)pos;  // row offsets are 32-bit (the host rejects batches with 2^32 rows or more)
+        const uint32_t o1 = o0 + (uint32_t)cnt[0], o2 = o1 + (uint32_t)cnt[1], o3 = o2 + (uint32_t)cnt[2];
+        if (full) {
+            st_stream_v4(A.row_offset + q0, make_int4((int)o0, (int)o1, (int)o2, (int)o3));
+        } else {
+            const uint32_t o[LI_IPT] = {o0, o1, o2, o3};
+#pragma unroll
+            for (int k = 0; k < LI_IPT; k++)
+                if (q0 + k < A.n) A.row_offset[q0 + k] = o[k];
+        }
+        unsigned multi = 0;
+#pragma unroll
+        for (int k = 0; k < LI_IPT; k++) {
+            const RowCore r = make_row(bk[k], st[k], en[k]);
+            const int meta = STRAND ? (r.qcid | ((int)strand_flip(sbk[k], r.inv) << 16)) : r.qcid;
+            if (cnt[k] == 1 && pos < A.rows_cap) st_stream_v4(A.rows + pos, make_int4(meta, r.s, r.e, (int)(q0 + k)));
+            multi |= cnt[k] >= 2 ? 1u << k : 0u;
+            pos += (uint64_t)cnt[k];
+        }
+        if (__any_sync(FULL, multi != 0u)) {
+            unsigned wide = 0;  // list full: queries for the whole warp
+            uint64_t p = tbase + (inc - tsum);
+#pragma unroll
+            for (int k = 0; k < LI_IPT; k++) {
+                if ((multi >> k) & 1u) {
+                    if (cnt[k] <= MG_SMALL) {
+                        expand_small(A, q0 + k, lo[k], cnt[k], p);
+                    } else {
+                        const unsigned e = atomicAdd(W.count, 1u);
+                        if (e < W.cap) W.ent[e] = make_uint4(q0 + k, (unsigned)lo[k], (unsigned)cnt[k], (uint32_t)p);
+                        else wide |= 1u << k;
+                    }
+                }
+                p += (uint64_t)cnt[k];
+            }
+            converge(A);
+            if (__any_sync(FULL, wide != 0u)) {
+                p = tbase + (inc - tsum);
+#pragma unroll 1
+                for (int k = 0; k < LI_IPT; k++) {
+                    unsigned m = __ballot_sync(FULL, (wide >> k) & 1u);
+                    while (m) {
+                        const int src = __ffs(m) - 1;
+                        m &= m - 1;
+                        const uint32_t q = __shfl_sync(FULL, q0, src) + (uint32_t)k;
+                        const int qlo = __shfl_sync(FULL, lo[k], src), qcnt = __shfl_sync(FULL, cnt[k], src);
+                        const uint64_t qpos = __shfl_sync(FULL, p, src);
+                        expand_wide(A, sink, q, qlo, qcnt, qpos, S.xscr[w], gxs);
+                        converge(A);
+                    }
+                    p += (uint64_t)cnt[k];
+                }
+            }
+        }
+    }
+}
+
+// The queries merge_write_kernel left on the list: a warp per query.  Row positions are 32-bit
 // (the host rejects batches with 2^32 rows or more).
 __global__ void __launch_bounds__(256) expand_wide_kernel(const __grid_constant__ LiftArgs A, const __grid_constant__ WideList W) {
     __shared__ unsigned long long xs[8][MG_XS];

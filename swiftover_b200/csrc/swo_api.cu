@@ -106,7 +106,7 @@ struct Device {
     PinBuf h_sizes;  // N_SLOTS * 6 u64
     // per-shard host output arenas (multi-shard runs)
     PinBuf a_lifted, a_unm;
-    int text_grid = 0, bin_grid[4] = {0, 0, 0, 0};
+    int text_grid = 0, bin_grid[5] = {0, 0, 0, 0, 0};
 };
 
 }  // namespace
@@ -262,14 +262,15 @@ int launch_lift_intervals(swo_ctx *c, Device &d, size_t n, const int32_t *tcid, 
                           uint32_t *row_offset, swo_row *rows, swo_thick *thick, size_t rows_cap, uint64_t *totals,
                           cudaStream_t st) {
     const int ntiles = (int)((n + LI_TILE - 1) / LI_TILE);
-    // scratch: [ticket, -, sorted flag, -] [ntiles tile descriptors (per-query-search variants)]
-    // sorted variant (tiles of MG_TILE queries, two-level look-back): [nts tile words] [nts/32+1 acc] [nts/32+1 inc]
-    const int nts = (int)((n + MG_TILE - 1) / MG_TILE);
-    const size_t w_desc = (16 + (size_t)ntiles * 8 + 15) & ~(size_t)15;
-    const size_t w_acc = w_desc + (size_t)nts * 8, w_inc = w_acc + ((size_t)nts / LBG_TILES + 1) * 8;
-    const size_t scratch_bytes = w_inc + ((size_t)nts / LBG_TILES + 1) * 8;
+    // scratch: [ticket, wide-list count, sorted flag, -] [ntiles tile descriptors (per-query-search variants)]
+    // sorted variant (count / scan / write over warp tiles of MG_QPW queries): [ntw totals] [ntw windows] [nsum sums]
+    const int ntw = (int)((n + MG_QPW - 1) / MG_QPW), nsum = (ntw + MG_SCAN_TILE - 1) / MG_SCAN_TILE;
+    const size_t w_total = (16 + (size_t)ntiles * 8 + 15) & ~(size_t)15;
+    const size_t w_window = (w_total + (size_t)ntw * 4 + 15) & ~(size_t)15, w_sum = (w_window + (size_t)ntw * 4 + 15) & ~(size_t)15;
+    const size_t scratch_bytes = w_sum + (size_t)(nsum + 1) * 8;
+    const size_t zero_bytes = w_total;  // header + tile descriptors; the sorted variant's arrays are written before they are read
     CK(c, d.scratch.reserve((scratch_bytes + 3) & ~(size_t)3));
-    if (int rc = zero_async(c, d.scratch.p, scratch_bytes, totals, 16, st)) return rc;
+    if (int rc = zero_async(c, d.scratch.p, zero_bytes, totals, 16, st)) return rc;
     if (n == 0) {
         if (int rc = zero_async(c, row_offset, 4, nullptr, 0, st)) return rc;
         return SWO_OK;
@@ -290,10 +291,10 @@ int launch_lift_intervals(swo_ctx *c, Device &d, size_t n, const int32_t *tcid, 
     A.rows_cap = rows_cap;
     A.ticket = d.scratch.as<unsigned>();
     A.desc = reinterpret_cast<uint64_t *>(d.scratch.as<char>() + 16);
-    Lb2 L;
-    L.desc = reinterpret_cast<unsigned long long *>(d.scratch.as<char>() + w_desc);
-    L.acc = reinterpret_cast<unsigned long long *>(d.scratch.as<char>() + w_acc);
-    L.inc = reinterpret_cast<uint64_t *>(d.scratch.as<char>() + w_inc);
+    MergeTiles M;
+    M.total = reinterpret_cast<uint32_t *>(d.scratch.as<char>() + w_total);
+    M.window = reinterpret_cast<int32_t *>(d.scratch.as<char>() + w_window);
+    M.sum = reinterpret_cast<unsigned long long *>(d.scratch.as<char>() + w_sum);
     A.gscr = nullptr;
     A.totals = totals;
     // sortedness sample -> flag word in the scratch header; both variants of the kernel
@@ -307,69 +308,60 @@ int launch_lift_intervals(swo_ctx *c, Device &d, size_t n, const int32_t *tcid, 
     const bool th = ths != nullptr;
     const bool merge_ok = d.T.disjoint != 0;  // the merge kernel assumes candidates == hits
     if (!th) {
-        sample_sorted_kernel<<<1, 256, 0, st>>>(tcid, start, (uint32_t)n, flag, merge_ok ? 1u : 0u);
+        sample_sorted_kernel<<<1, 1024, 0, st>>>(tcid, start, (uint32_t)n, flag, merge_ok ? 1u : 0u);
         c->launches++;
     }
     for (int v = th ? 2 : 0; v < (th ? 3 : 2); v++) {
-        const void *fn = v == 0   ? (const void *)lift_intervals_kernel<false, false>
-                         : v == 1 ? (strand ? (const void *)lift_sorted_kernel<true> : (const void *)lift_sorted_kernel<false>)
-                                  : (const void *)lift_intervals_kernel<true, false>;
-        const size_t smem = v == 0   ? sizeof(LiftSmem<false, false>)
-                            : v == 1 ? sizeof(MergeSmem)
-                                     : sizeof(LiftSmem<true, false>);
-        if (v == 1 && !merge_ok) continue;
-        const int gi = v == 1 && strand ? 3 : v;
-        if (!d.bin_grid[gi]) {
-            int per = 0;
-            CK(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, fn, v == 1 ? MG_TPB : LI_TPB, smem));
-            d.bin_grid[gi] = std::max(1, per) * d.sms;
-        }
-        LiftArgs Aw = A;
-        int grid = std::min(ntiles, d.bin_grid[gi]);
         if (v == 1) {
-            // Sorted variant: its own tile size, tiles dealt round-robin => every CTA must be resident
-            // (cooperative launch); per-warp sort scratch and the wide-query list in global memory;
-            // expand_wide_kernel works the list off afterwards.
-            Aw.ntiles = nts;
-            grid = std::min(nts, d.bin_grid[gi]);
-            CK(c, d.gscr.reserve((size_t)d.bin_grid[gi] * MG_NW * MG_GXS * sizeof(unsigned long long)));
+            // Sorted batches (flag set on the device; otherwise each of these returns at once): count pass, scan of the
+            // warp tiles' totals, write pass, and the wide multi-hit queries the write pass left on its list.
+            if (!merge_ok) continue;
+            const void *fw = strand ? (const void *)merge_write_kernel<true> : (const void *)merge_write_kernel<false>;
+            const size_t smem = sizeof(MergeSmem);
+            if (!d.bin_grid[1]) {
+                int per = 0;
+                CK(c, cudaFuncSetAttribute((const void *)merge_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, (const void *)merge_count_kernel, MG_TPB, smem));
+                d.bin_grid[1] = std::max(1, per) * d.sms;
+            }
+            const int gw = strand ? 4 : 3;
+            if (!d.bin_grid[gw]) {
+                int per = 0;
+                CK(c, cudaFuncSetAttribute(fw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, fw, MG_TPB, smem));
+                d.bin_grid[gw] = std::max(1, per) * d.sms;
+            }
+            LiftArgs Aw = A;
+            Aw.ntiles = ntw;
+            const int need = (ntw + MG_NW - 1) / MG_NW;
+            const int grid_c = std::min(need, d.bin_grid[1]), grid_w = std::min(need, d.bin_grid[gw]);
+            CK(c, d.gscr.reserve((size_t)std::max(grid_w * MG_NW, 8) * MG_GXS * sizeof(unsigned long long)));
             Aw.gscr = d.gscr.as<unsigned long long>();
             WideList W;
             W.cap = (unsigned)std::min<size_t>(n / 128 + 65536, 0x7fffffffu);
             CK(c, d.wide.reserve((size_t)W.cap * sizeof(uint4)));
             W.ent = d.wide.as<uint4>();
             W.count = reinterpret_cast<unsigned *>(d.scratch.as<char>() + 4);
-            void *cargs[] = {(void *)&Aw, (void *)&L, (void *)&W};
-#ifdef MG_TRACE
-            unsigned long long *trbuf = nullptr;
-            if (v == 1 && getenv("SWO_MG_TRACE")) {
-                cudaMalloc(&trbuf, (size_t)nts * 64);
-                cudaMemset(trbuf, 0, (size_t)nts * 64);
-                cudaMemcpyToSymbol(mg_trace, &trbuf, sizeof trbuf);
-            }
-#endif
-            CK(c, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(MG_TPB), cargs, smem, st));
-            c->launches++;
-#ifdef MG_TRACE
-            if (trbuf) {
-                cudaStreamSynchronize(st);
-                std::vector<unsigned long long> h((size_t)nts * 8);
-                cudaMemcpy(h.data(), trbuf, h.size() * 8, cudaMemcpyDeviceToHost);
-                FILE *f = fopen(getenv("SWO_MG_TRACE"), "wb");
-                if (f) { fwrite(h.data(), 8, h.size(), f); fclose(f); }
-                unsigned long long *z = nullptr;
-                cudaMemcpyToSymbol(mg_trace, &z, sizeof z);
-                cudaFree(trbuf);
-            }
-#endif
-            const int wgrid = std::max(1, grid * MG_NW / 8);
-            expand_wide_kernel<<<wgrid, 256, 0, st>>>(Aw, W);
-            c->launches++;
+            merge_count_kernel<<<grid_c, MG_TPB, smem, st>>>(Aw, M);
+            scan_tiles_kernel1<<<nsum, 256, 0, st>>>(flag, M, ntw);
+            scan_tiles_kernel2<<<1, 1024, 0, st>>>(flag, M, nsum, totals, row_offset + n);
+            void *wargs[] = {(void *)&Aw, (void *)&M, (void *)&W};
+            CK(c, cudaLaunchKernel(fw, dim3(grid_w), dim3(MG_TPB), wargs, smem, st));
+            expand_wide_kernel<<<std::max(1, grid_w * MG_NW / 8), 256, 0, st>>>(Aw, W);
+            c->launches += 5;
             continue;
         }
-        void *args[] = {(void *)&Aw, (void *)&L};
-        CK(c, cudaLaunchKernel(fn, dim3(grid), dim3(v == 1 ? MG_TPB : LI_TPB), args, smem, st));
+        const void *fn = v == 0 ? (const void *)lift_intervals_kernel<false, false> : (const void *)lift_intervals_kernel<true, false>;
+        const size_t smem = v == 0 ? sizeof(LiftSmem<false, false>) : sizeof(LiftSmem<true, false>);
+        if (!d.bin_grid[v]) {
+            int per = 0;
+            CK(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, fn, LI_TPB, smem));
+            d.bin_grid[v] = std::max(1, per) * d.sms;
+        }
+        const int grid = std::min(ntiles, d.bin_grid[v]);
+        void *args[] = {(void *)&A};
+        CK(c, cudaLaunchKernel(fn, dim3(grid), dim3(LI_TPB), args, smem, st));
         c->launches++;
     }
     CK(c, cudaGetLastError());
