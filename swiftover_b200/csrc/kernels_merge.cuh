@@ -70,6 +70,8 @@ struct MergeTiles {
 };
 
 struct MergeSmem {
+    int4 q[MG_NW][2][3][32];               // per warp, two stages: the queries {tcid}, {start}, {end} of a tile (TMA-filled)
+    uint64_t qbar[MG_NW][2];               //   and their mbarriers
     int4 cmeta[LI_CM_CAP];                 // per-contig {first block, end block, sample offset, samples}
     int32_t smp[ChainTable::EY_CAP];       // group maxima of pmaxKey in SORTED order (per contig)
     unsigned long long xscr[MG_NW][MG_XS]; // sort scratch of a warp's cooperative expansion (write pass)
@@ -227,9 +229,8 @@ __device__ __noinline__ LoHi4 search_each(const LiftArgs &A, uint32_t q0) {
 // ascending ('+' chains) or strictly descending ('-' chains) and the rows are written in one
 // sequential pass, forwards or backwards, with the running strand flip (bed.d:173); any other
 // order takes the rank-by-comparison form.
-__device__ __noinline__ void expand_small(const LiftArgs &A, uint32_t q, int lo, int cnt, uint64_t pos) {
+__device__ __noinline__ bool expand_small(const LiftArgs &A, uint32_t q, int lo, int cnt, uint64_t pos) {
     const TableView &T = A.T;
-    const RowSink sink{A.rows, A.thick, A.rows_cap};
     const int start = __ldg(A.start + q), end = __ldg(A.end + q);
     if (cnt == 2 && T.disjoint) {  // the usual case: an interval across one gap
         const RowCore a = make_row(load_block(T, lo), start, end), b = make_row(load_block(T, lo + 1), start, end);
@@ -242,7 +243,7 @@ __device__ __noinline__ void expand_small(const LiftArgs &A, uint32_t q, int lo,
         }
         if (pos < A.rows_cap) st_stream_v4(A.rows + pos, make_int4(r0.qcid | ((int)s0 << 16), r0.s, r0.e, (int)q));
         if (pos + 1 < A.rows_cap) st_stream_v4(A.rows + pos + 1, make_int4(r1.qcid | ((int)s1 << 16), r1.s, r1.e, (int)q));
-        return;
+        return true;
     }
     bool asc = true, desc = true, first = true;
     int prev = 0, nhit = 0;
@@ -258,10 +259,7 @@ __device__ __noinline__ void expand_small(const LiftArgs &A, uint32_t q, int lo,
         prev = key;
         nhit++;
     }
-    if (!asc && !desc) {
-        expand_query<false>(A, sink, T.ey, q, lo, cnt, pos, 0, 1);
-        return;
-    }
+    if (!asc && !desc) return false;
     const unsigned char orig = A.strand ? __ldg(A.strand + q) : 0;
     int rank = 0, negs = 0, inv_first = 1;
     for (int i = 0; i < cnt; i++) {
@@ -278,6 +276,7 @@ __device__ __noinline__ void expand_small(const LiftArgs &A, uint32_t q, int lo,
         }
         rank++;
     }
+    return true;
 }
 
 // one multi-hit query by a whole warp: sort keys in shared memory, in the warp's global scratch, or
@@ -333,33 +332,55 @@ __device__ __forceinline__ void merge_window(const TableView &T, int wb, int cen
     }
 }
 
-// the lane's four queries of tile `tile` (tcid -1 / empty interval behind the end of the batch)
-__device__ __forceinline__ void load_queries(const LiftArgs &A, uint32_t q0, bool full, int (&tc)[LI_IPT], int (&st)[LI_IPT],
-                                             int (&en)[LI_IPT]) {
-    if (full) {
-        const int4 a = ld_stream_v4(A.tcid + q0), b = ld_stream_v4(A.start + q0), c = ld_stream_v4(A.end + q0);
-        tc[0] = a.x, tc[1] = a.y, tc[2] = a.z, tc[3] = a.w;
-        st[0] = b.x, st[1] = b.y, st[2] = b.z, st[3] = b.w;
-        en[0] = c.x, en[1] = c.y, en[2] = c.z, en[3] = c.w;
-    } else {
-#pragma unroll
-        for (int k = 0; k < LI_IPT; k++) {
-            const bool ok = q0 + k < A.n;
-            tc[k] = ok ? A.tcid[q0 + k] : -1;
-            st[k] = ok ? A.start[q0 + k] : 0;
-            en[k] = ok ? A.end[q0 + k] : 0;
+// A warp's queries come through shared memory: lane 0 arms the stage's mbarrier and issues three
+// 1-D bulk copies (TMA; UBLKCP in the SASS) for the warp's NEXT tile — tiles are dealt round-robin,
+// so it is known — while the current one is merged; the load latency is off the critical path.
+// The batch's last, partial tile is read directly (tcid -1 / empty interval behind its end).
+struct QueryStager {
+    MergeSmem &S;
+    const LiftArgs &A;
+    int w, lane;
+    unsigned uses[2];  // how often each stage has been waited for (mbarrier phase parity)
+    __device__ QueryStager(MergeSmem &S_, const LiftArgs &A_) : S(S_), A(A_), w(warp_id()), lane(lane_id()) {
+        uses[0] = uses[1] = 0;
+        if (lane == 0) {
+            mbar_init(&S.qbar[w][0], 1);
+            mbar_init(&S.qbar[w][1], 1);
+            mbar_init_fence();
+        }
+        __syncwarp();
+    }
+    __device__ bool whole(long long tile) const { return tile >= 0 && (tile + 1) * MG_QPW <= (long long)A.n; }
+    // lane 0 issues; every lane of the warp has finished reading stage `st` (the caller's __syncwarp)
+    __device__ void issue(long long tile, int st) {
+        if (lane == 0 && whole(tile)) {
+            fence_proxy_async();
+            mbar_expect_tx(&S.qbar[w][st], 3u * MG_QPW * 4u);
+            bulk_g2s(S.q[w][st][0], A.tcid + tile * MG_QPW, MG_QPW * 4u, &S.qbar[w][st]);
+            bulk_g2s(S.q[w][st][1], A.start + tile * MG_QPW, MG_QPW * 4u, &S.qbar[w][st]);
+            bulk_g2s(S.q[w][st][2], A.end + tile * MG_QPW, MG_QPW * 4u, &S.qbar[w][st]);
         }
     }
-}
-
-// the warp's next tile (known: tiles are dealt round-robin) into L2
-__device__ __forceinline__ void prefetch_queries(const LiftArgs &A, long long tile) {
-    const int lane = lane_id();
-    if (lane < 12 && (tile + 1) * MG_QPW <= (long long)A.n) {
-        const int32_t *base = lane < 4 ? A.tcid : lane < 8 ? A.start : A.end;
-        prefetch_l2(base + tile * MG_QPW + (lane & 3) * 32);
+    __device__ void fetch(long long tile, int st, int (&tc)[LI_IPT], int (&sta)[LI_IPT], int (&en)[LI_IPT]) {
+        if (whole(tile)) {
+            mbar_wait(&S.qbar[w][st], uses[st] & 1u);
+            uses[st]++;
+            const int4 a = S.q[w][st][0][lane], b = S.q[w][st][1][lane], c = S.q[w][st][2][lane];
+            tc[0] = a.x, tc[1] = a.y, tc[2] = a.z, tc[3] = a.w;
+            sta[0] = b.x, sta[1] = b.y, sta[2] = b.z, sta[3] = b.w;
+            en[0] = c.x, en[1] = c.y, en[2] = c.z, en[3] = c.w;
+        } else {
+            const uint32_t q0 = (uint32_t)tile * MG_QPW + (uint32_t)lane * LI_IPT;
+#pragma unroll
+            for (int k = 0; k < LI_IPT; k++) {
+                const bool ok = q0 + k < A.n;
+                tc[k] = ok ? A.tcid[q0 + k] : -1;
+                sta[k] = ok ? A.start[q0 + k] : 0;
+                en[k] = ok ? A.end[q0 + k] : 0;
+            }
+        }
     }
-}
+};
 
 __device__ __forceinline__ void merge_tables(const TableView &T, MergeSmem &S, bool samples) {
     const int tid = threadIdx.x, lane = lane_id(), w = warp_id();
@@ -385,12 +406,16 @@ __global__ void __launch_bounds__(MG_TPB, 4) merge_count_kernel(const __grid_con
     const bool cm_smem = T.ntc <= LI_CM_CAP;
     const int nwarps = (int)gridDim.x * MG_NW;
     uint32_t unm_acc = 0;
-    for (int tile = (int)blockIdx.x * MG_NW + warp_id(); tile < A.ntiles; tile += nwarps) {
+    QueryStager Q(S, A);
+    Q.issue((long long)blockIdx.x * MG_NW + warp_id(), 0);
+    int stage = 0;
+    for (int tile = (int)blockIdx.x * MG_NW + warp_id(); tile < A.ntiles; tile += nwarps, stage ^= 1) {
         const uint32_t q0 = (uint32_t)tile * MG_QPW + (uint32_t)lane * LI_IPT;
         const bool full = (uint32_t)(tile + 1) * MG_QPW <= A.n;
         int tc[LI_IPT], st[LI_IPT], en[LI_IPT], lo[LI_IPT], hi[LI_IPT];
-        load_queries(A, q0, full, tc, st, en);
-        prefetch_queries(A, (long long)tile + nwarps);
+        __syncwarp();
+        if ((long long)tile + nwarps < A.ntiles) Q.issue((long long)tile + nwarps, stage ^ 1);
+        Q.fetch(tile, stage, tc, st, en);
         const int tc0 = __shfl_sync(FULL, tc[0], 0);
         const bool same = __all_sync(FULL, tc[0] == tc0 && tc[1] == tc0 && tc[2] == tc0 && tc[3] == tc0) && tc0 >= 0 && tc0 < T.ntc;
         int wb = -1;
@@ -494,13 +519,18 @@ __global__ void __launch_bounds__(MG_TPB, MG_WRITE_CTAS) merge_write_kernel(cons
     const int nwarps = (int)gridDim.x * MG_NW;
     const int last_block = __ldg(&T.cmeta[T.ntc - 1].y) - 1;
     const RowSink sink{A.rows, A.thick, A.rows_cap};
+    const uint32_t cap32 = A.rows_cap > 0xffffffffull ? 0xffffffffu : (uint32_t)A.rows_cap;
     unsigned long long *const gxs = A.gscr + ((size_t)blockIdx.x * MG_NW + w) * MG_GXS;
-    for (int tile = (int)blockIdx.x * MG_NW + w; tile < A.ntiles; tile += nwarps) {
+    QueryStager Q(S, A);
+    Q.issue((long long)blockIdx.x * MG_NW + w, 0);
+    int stage = 0;
+    for (int tile = (int)blockIdx.x * MG_NW + w; tile < A.ntiles; tile += nwarps, stage ^= 1) {
         const uint32_t q0 = (uint32_t)tile * MG_QPW + (uint32_t)lane * LI_IPT;
         const bool full = (uint32_t)(tile + 1) * MG_QPW <= A.n;
         int tc[LI_IPT], st[LI_IPT], en[LI_IPT], lo[LI_IPT], hi[LI_IPT];
-        load_queries(A, q0, full, tc, st, en);
-        prefetch_queries(A, (long long)tile + nwarps);
+        __syncwarp();
+        if ((long long)tile + nwarps < A.ntiles) Q.issue((long long)tile + nwarps, stage ^ 1);
+        Q.fetch(tile, stage, tc, st, en);
         const int wb = __ldg(M.window + tile);
         const uint64_t tbase = M.sum[tile / MG_SCAN_TILE] + (uint64_t)M.total[tile];
         uchar4 sb4 = make_uchar4(0, 0, 0, 0);
@@ -539,8 +569,9 @@ __global__ void __launch_bounds__(MG_TPB, MG_WRITE_CTAS) merge_write_kernel(cons
             tsum += (uint32_t)cnt[k];
         }
         const uint32_t inc = warp_inclusive_scan(tsum);
-        uint64_t pos = tbase + (inc - tsum);
-        const uint32_t o0 = (uint32_t)pos;  // row offsets are 32-bit (the host rejects batches with 2^32 rows or more)
+        const uint64_t pos64 = tbase + (inc - tsum);
+        uint32_t pos = (uint32_t)pos64;  // row indices are 32-bit (the host rejects batches with 2^32 rows or more)
+        const uint32_t o0 = pos;
         const uint32_t o1 = o0 + (uint32_t)cnt[0], o2 = o1 + (uint32_t)cnt[1], o3 = o2 + (uint32_t)cnt[2];
         if (full) {
             st_stream_v4(A.row_offset + q0, make_int4((int)o0, (int)o1, (int)o2, (int)o3));
@@ -553,21 +584,27 @@ __global__ void __launch_bounds__(MG_TPB, MG_WRITE_CTAS) merge_write_kernel(cons
         unsigned multi = 0;
 #pragma unroll
         for (int k = 0; k < LI_IPT; k++) {
-            const RowCore r = make_row(bk[k], st[k], en[k]);
-            const int meta = STRAND ? (r.qcid | ((int)strand_flip(sbk[k], r.inv) << 16)) : r.qcid;
-            if (cnt[k] == 1 && pos < A.rows_cap) st_stream_v4(A.rows + pos, make_int4(meta, r.s, r.e, (int)(q0 + k)));
+            // intersect + qEnd + orderStartEnd (chain.d:728-743, 128-134, 787-793) for a +/-1 invert
+            const Block &b = bk[k];
+            const int ts = max(b.tStart, st[k]), te = min(b.tEnd, en[k]);
+            const bool neg = b.meta & 1;
+            const int key = neg ? b.qStart - (ts - b.tStart) : b.qStart + (ts - b.tStart);
+            const int len = te - ts;
+            const int rs = neg ? key - len : key, re = neg ? key : key + len;  // cnt == 1: len > 0
+            const int meta = STRAND ? ((b.meta >> 1) | ((int)strand_flip(sbk[k], neg ? -1 : 1) << 16)) : (b.meta >> 1);
+            if (cnt[k] == 1 && pos < cap32) st_stream_v4(A.rows + pos, make_int4(meta, rs, re, (int)(q0 + k)));
             multi |= cnt[k] >= 2 ? 1u << k : 0u;
-            pos += (uint64_t)cnt[k];
+            pos += (uint32_t)cnt[k];
         }
         if (__any_sync(FULL, multi != 0u)) {
             unsigned wide = 0;  // list full: queries for the whole warp
-            uint64_t p = tbase + (inc - tsum);
+            uint64_t p = pos64;
 #pragma unroll
             for (int k = 0; k < LI_IPT; k++) {
                 if ((multi >> k) & 1u) {
-                    if (cnt[k] <= MG_SMALL) {
-                        expand_small(A, q0 + k, lo[k], cnt[k], p);
-                    } else {
+                    // up to MG_SMALL candidates: by the thread, unless their rows are neither in ascending
+                    // nor in descending qStart order — those need a sort and go with the large ones
+                    if (!(cnt[k] <= MG_SMALL && expand_small(A, q0 + k, lo[k], cnt[k], p))) {
                         const unsigned e = atomicAdd(W.count, 1u);
                         if (e < W.cap) W.ent[e] = make_uint4(q0 + k, (unsigned)lo[k], (unsigned)cnt[k], (uint32_t)p);
                         else wide |= 1u << k;
@@ -577,7 +614,7 @@ __global__ void __launch_bounds__(MG_TPB, MG_WRITE_CTAS) merge_write_kernel(cons
             }
             converge(A);
             if (__any_sync(FULL, wide != 0u)) {
-                p = tbase + (inc - tsum);
+                p = pos64;
 #pragma unroll 1
                 for (int k = 0; k < LI_IPT; k++) {
                     unsigned m = __ballot_sync(FULL, (wide >> k) & 1u);
