@@ -275,18 +275,18 @@ __device__ __forceinline__ void flush_pending(const LiftArgs &A, LiftSmem<THICK,
     if (tid == 0) S.p_tile = -1;
 }
 
-// Is the batch (mostly) sorted by position?  1024 threads look at 2048 adjacent pairs spread over
+// Is the batch (mostly) sorted by position?  512 threads look at 1024 adjacent pairs spread over
 // the batch; a pair counts when both queries name the same contig and the start does not move
 // back.  *flag = 1 when at least 7 of 8 pairs do (and the caller allows the sorted variant at all).
 // Decides which kernel variant does the work.
-__global__ void __launch_bounds__(1024) sample_sorted_kernel(const int32_t *__restrict__ tcid, const int32_t *__restrict__ start,
+__global__ void __launch_bounds__(512) sample_sorted_kernel(const int32_t *__restrict__ tcid, const int32_t *__restrict__ start,
                                                              uint32_t n, uint32_t *flag, uint32_t allow) {
     __shared__ unsigned s_cnt;
     if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
-    const uint32_t pairs = n > 1 ? n - 1 : 0, want = pairs < 2048u ? pairs : 2048u;
+    const uint32_t pairs = n > 1 ? n - 1 : 0, want = pairs < 1024u ? pairs : 1024u;
     unsigned ok = 0;
-    const uint32_t j0 = threadIdx.x, j1 = threadIdx.x + 1024u;
+    const uint32_t j0 = threadIdx.x, j1 = threadIdx.x + 512u;
     const uint32_t i0 = j0 < want ? (uint32_t)(((unsigned long long)j0 * pairs) / want) : 0u;
     const uint32_t i1 = j1 < want ? (uint32_t)(((unsigned long long)j1 * pairs) / want) : 0u;
     int a0 = 0, a1 = 0, b0 = 0, b1 = 0, c0 = 0, c1 = 0, d0 = 0, d1 = 0;

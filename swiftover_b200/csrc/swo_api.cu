@@ -308,7 +308,7 @@ int launch_lift_intervals(swo_ctx *c, Device &d, size_t n, const int32_t *tcid, 
     const bool th = ths != nullptr;
     const bool merge_ok = d.T.disjoint != 0;  // the merge kernel assumes candidates == hits
     if (!th) {
-        sample_sorted_kernel<<<1, 1024, 0, st>>>(tcid, start, (uint32_t)n, flag, merge_ok ? 1u : 0u);
+        sample_sorted_kernel<<<1, 512, 0, st>>>(tcid, start, (uint32_t)n, flag, merge_ok ? 1u : 0u);
         c->launches++;
     }
     for (int v = th ? 2 : 0; v < (th ? 3 : 2); v++) {
