@@ -192,53 +192,9 @@ def test_cfg4_vcf_points(hg):
 
 
 def fragmented_chain(seed=20245005, target_blocks=540_000):
-    """cfg 5 stand-in: a target-disjoint chain file with ~10x the blocks of hg19ToHg38 — short
-    blocks separated by 1..50 bp gaps on both sides, 30 % of the chains on the '-' strand, 10 %
-    re-targeted to another destination contig."""
-    rng = np.random.default_rng(seed)
-    src = gzip.open(os.path.join(os.path.dirname(__file__), "golden", "resources", "hg19ToHg38.over.chain.gz"), "rb").read()
-    sizes = {}
-    for ln in src.split(b"\n"):
-        if ln.startswith(b"chain"):
-            f = ln.split(b" ")
-            sizes[f[2]] = int(f[3])
-    names = list(sizes)
-    total = float(sum(sizes.values()))
-    out = []
-    cid = 0
-    qsize = 400_000_000
-    for t in names:
-        nb_t = max(4, int(target_blocks * sizes[t] / total))
-        per_chain = 400
-        pos_t = int(rng.integers(0, 2000))
-        done = 0
-        while done < nb_t:
-            nb = min(per_chain, nb_t - done)
-            avg = max(20, int(0.9 * sizes[t] / nb_t) - 25)
-            bs = rng.integers(max(1, avg // 2), avg * 3 // 2 + 2, nb)
-            dt = rng.integers(1, 51, nb - 1) if nb > 1 else np.zeros(0, np.int64)
-            dq = rng.integers(1, 51, nb - 1) if nb > 1 else np.zeros(0, np.int64)
-            span_t = int(bs.sum() + dt.sum())
-            span_q = int(bs.sum() + dq.sum())
-            if pos_t + span_t >= sizes[t]:
-                break
-            cid += 1
-            q = t if rng.random() >= 0.10 else names[int(rng.integers(0, len(names)))]
-            strand = b"-" if rng.random() < 0.30 else b"+"
-            qs = int(rng.integers(0, qsize - span_q - 1))
-            out.append(b"chain %d %s %d + %d %d %s %d %s %d %d %d" % (
-                1_000_000 - cid, t, sizes[t], pos_t, pos_t + span_t, q, qsize, strand, qs, qs + span_q, cid))
-            body = np.empty((nb, 3), np.int64)
-            body[:, 0] = bs
-            body[:-1, 1] = dt
-            body[:-1, 2] = dq
-            lines = [b"%d\t%d\t%d" % (r[0], r[1], r[2]) for r in body[:-1]]
-            lines.append(b"%d" % body[-1, 0])
-            out.extend(lines)
-            out.append(b"")
-            pos_t += span_t + int(rng.integers(1, 200))
-            done += nb
-    return b"\n".join(out) + b"\n"
+    from swiftover_b200.synth import fragmented_chain as fc
+    return fc(gzip.open(os.path.join(os.path.dirname(__file__), "golden", "resources", "hg19ToHg38.over.chain.gz"), "rb").read(),
+              seed, target_blocks)
 
 
 def test_cfg5_fragmented_chain(oracle):
