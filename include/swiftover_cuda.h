@@ -156,8 +156,23 @@ typedef struct swo_text_out {
     uint64_t n_unmatched;     /* records without any block */
 } swo_text_out;
 
-/* `in` = the whole BED file (any host memory; pinned is faster). */
+/* `in` = the whole BED file (any host memory; pinned is faster).  With several devices the
+ * input is cut into byte-range shards (one per device, a shard owns the lines that start
+ * inside it), every shard streams through its own device, and the outputs come back in
+ * shard order = single-device order (the reference is one sequential loop,
+ * bed.d:113).  A malformed line (fewer than 3 fields, non-integer coordinate; the reference
+ * dies there with a range violation / ConvException, bed.d:125-126) gives SWO_E_PARSE, and
+ * `out` then holds what the reference had written by that point: the outputs of every line in
+ * front of it. */
 int swo_lift_bed_text(swo_ctx *ctx, const char *in, size_t in_len, swo_text_out *out);
+
+/* The result of the last swo_lift_bed_text as per-shard pieces in output order (which: 0 =
+ * lifted, 1 = unmatched): the concatenation of the pieces is the output.  With
+ * swo_set_option(ctx, "concat", 0) the pieces are all there is (out->lifted / out->unmatched
+ * are NULL, the lengths are the totals): a caller that writes to a file, like liftBED does
+ * (bed.d:151,199), writes the pieces in order and no concatenation copy is made. */
+int swo_text_num_segments(const swo_ctx *ctx);
+int swo_text_segment(const swo_ctx *ctx, int which, int i, const char **ptr, size_t *len);
 
 /* Same kernels on device-resident text (kernel-only measurement).  d_in must be
  * 16-byte aligned.  d_sizes[0]=lifted bytes, [1]=unmatched bytes, [2]=records,

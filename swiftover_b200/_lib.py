@@ -75,6 +75,8 @@ def lib():
         "swo_lift_intervals_dev": (i32, [vp, sz, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp, vp]),
         "swo_lift_points": (i32, [vp, sz, vp, vp, vp, vp, vp]),
         "swo_lift_bed_text": (i32, [vp, vp, sz, C.POINTER(SwoTextOut)]),
+        "swo_text_num_segments": (i32, [vp]),
+        "swo_text_segment": (i32, [vp, i32, i32, C.POINTER(vp), C.POINTER(sz)]),
         "swo_lift_bed_text_dev": (i32, [vp, vp, sz, vp, sz, vp, sz, vp, vp]),
         "swo_load_genome_2bit": (i32, [vp, vp, sz, vp, vp, i32]),
         "swo_lift_vcf_points_dev": (i32, [vp, sz, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),

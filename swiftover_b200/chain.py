@@ -170,6 +170,16 @@ class ChainFile:
         self._ck(self._lib.swo_lift_bed_text(self._h, ptr, nbytes, C.byref(out)))
         return out
 
+    def text_segments(self, which):
+        """The last lift_bed_text result as per-shard (address, length) pieces in output order
+        (which: 0 = lifted, 1 = unmatched) — see swo_text_segment."""
+        out = []
+        for i in range(self._lib.swo_text_num_segments(self._h)):
+            p, n = C.c_void_p(), C.c_size_t()
+            self._ck(self._lib.swo_text_segment(self._h, which, i, C.byref(p), C.byref(n)))
+            out.append((p.value or 0, n.value))
+        return out
+
     def load_genome_2bit(self, packed, contig_off, contig_len):
         packed = np.ascontiguousarray(packed, np.uint8)
         contig_off = np.ascontiguousarray(contig_off, np.int64)

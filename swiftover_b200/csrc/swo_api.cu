@@ -14,7 +14,9 @@
 #include <cstring>
 #include <ctime>
 #include <fstream>
+#include <condition_variable>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -127,6 +129,10 @@ struct swo_ctx {
     // copy when nothing else uses the link, but slower than staging once D2H copies of the output overlap
     bool zero_copy_input = false;
     int d2h_streams = 1;  // 2: alternate the chunks' D2H copies over two streams
+    // multi-device runs: 1 = hand back ONE contiguous buffer per output (the shards' arenas are copied into it, all
+    // shards at once); 0 = no copy: the caller walks the shards' arenas in order with swo_text_segment
+    bool concat = true;
+    std::vector<std::pair<const char *, size_t>> seg_l, seg_u;
     // text tile size: TX_TILE, or 8192 / 4096 for inputs with large fan-out (a tile's lifted text should fit
     // its 20 KiB stage); 0 = choose per chunk from the previous chunk's output/input ratio
     uint32_t tile_bytes = TX_TILE;
@@ -704,6 +710,10 @@ int swo_set_option(swo_ctx *c, const char *key, int64_t value) {
         c->tile_auto = false;
         return SWO_OK;
     }
+    if (!strcmp(key, "concat")) {
+        c->concat = value != 0;
+        return SWO_OK;
+    }
     if (!strcmp(key, "d2h_streams")) {
         c->d2h_streams = value >= 2 ? 2 : 1;
         return SWO_OK;
@@ -927,10 +937,17 @@ int swo_lift_bed_text(swo_ctx *c, const char *in, size_t in_len, swo_text_out *o
         int rc = run_shard(c, c->dev[0], in, 0, in_len, &c->r_lifted, 0, &c->r_unm, 0, res[0]);
         if (rc) return rc;
     } else {
-        // one host thread per shard; each streams into its own pinned arena, then the
-        // arenas are concatenated in shard order (== single-device output order)
+        // One host thread per shard.  Shard 0 streams straight into the result arenas; the others into
+        // their own pinned arenas.  A shard's place in the result is known once every shard before it
+        // has finished, so when a thread is done it waits for its predecessors' sizes and copies its
+        // arena to its place itself: the copies of all shards run at the same time (the first version
+        // of this did them one after the other on the calling thread: 19 GB at 8 x 2.4 GB).
         std::vector<std::thread> th;
         std::vector<std::string> emsg(nd);
+        std::vector<int> fin(nd, 0);
+        std::mutex mu;
+        std::condition_variable cv;
+        const bool concat = c->concat;
         for (int k = 0; k < nd; k++) {
             th.emplace_back([&, k]() {
                 swo_ctx local;  // private error sink; run_shard only touches err/launches/chunk_bytes
@@ -940,32 +957,81 @@ int swo_lift_bed_text(swo_ctx *c, const char *in, size_t in_len, swo_text_out *o
                 local.tile_bytes = c->tile_bytes;
                 local.tile_auto = c->tile_auto;
                 Device &d = c->dev[k];
-                res[k].rc = run_shard(&local, d, in, cut[k], cut[k + 1], &d.a_lifted, 0, &d.a_unm, 0, res[k]);
+                PinBuf *pl = k == 0 ? &c->r_lifted : &d.a_lifted, *pu = k == 0 ? &c->r_unm : &d.a_unm;
+                res[k].rc = run_shard(&local, d, in, cut[k], cut[k + 1], pl, 0, pu, 0, res[k]);
                 emsg[k] = local.err;
                 __atomic_fetch_add(&c->launches, local.launches, __ATOMIC_RELAXED);
+                size_t ol = 0, ou = 0;
+                bool ok = res[k].rc == SWO_OK;
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    fin[k] = 1;
+                    cv.notify_all();
+                    if (k > 0 && concat) {
+                        cv.wait(lk, [&] {
+                            for (int j = 0; j < k; j++)
+                                if (!fin[j]) return false;
+                            return true;
+                        });
+                        for (int j = 0; j < k; j++) {
+                            ok = ok && res[j].rc == SWO_OK;
+                            ol += res[j].lifted;
+                            ou += res[j].unm;
+                        }
+                    }
+                }
+                if (k > 0 && concat && ok) {
+                    if (ol + res[k].lifted <= c->r_lifted.cap && ou + res[k].unm <= c->r_unm.cap) {
+                        memcpy(c->r_lifted.as<char>() + ol, d.a_lifted.p, res[k].lifted);
+                        memcpy(c->r_unm.as<char>() + ou, d.a_unm.p, res[k].unm);
+                    } else {
+                        res[k].rc = SWO_E_CAPACITY;  // redone below, single-threaded, after growing the result
+                    }
+                }
             });
         }
         for (auto &t : th) t.join();
         size_t tl = 0, tu = 0;
+        bool redo = false;
         for (int k = 0; k < nd; k++) {
-            if (res[k].rc) return fail(c, res[k].rc, "%s", emsg[k].c_str());
+            if (res[k].rc == SWO_E_CAPACITY) redo = true;
+            else if (res[k].rc) return fail(c, res[k].rc, "%s", emsg[k].c_str());
             tl += res[k].lifted;
             tu += res[k].unm;
         }
-        CK(c, c->r_lifted.reserve(tl + 1));
-        CK(c, c->r_unm.reserve(tu + 1));
-        size_t ol = 0, ou = 0;
+        c->seg_l.clear();
+        c->seg_u.clear();
         for (int k = 0; k < nd; k++) {
-            memcpy(c->r_lifted.as<char>() + ol, c->dev[k].a_lifted.p, res[k].lifted);
-            memcpy(c->r_unm.as<char>() + ou, c->dev[k].a_unm.p, res[k].unm);
-            ol += res[k].lifted;
-            ou += res[k].unm;
+            c->seg_l.emplace_back(k == 0 ? c->r_lifted.as<char>() : c->dev[k].a_lifted.as<char>(), res[k].lifted);
+            c->seg_u.emplace_back(k == 0 ? c->r_unm.as<char>() : c->dev[k].a_unm.as<char>(), res[k].unm);
+        }
+        if (redo) {  // fan-out beyond the reserve: grow (keeps shard 0's bytes) and copy again
+            CK(c, c->r_lifted.reserve(tl + 1, true, res[0].lifted));
+            CK(c, c->r_unm.reserve(tu + 1, true, res[0].unm));
+            c->seg_l[0].first = c->r_lifted.as<char>();
+            c->seg_u[0].first = c->r_unm.as<char>();
+            size_t ol = res[0].lifted, ou = res[0].unm;
+            for (int k = 1; k < nd; k++) {
+                memcpy(c->r_lifted.as<char>() + ol, c->dev[k].a_lifted.p, res[k].lifted);
+                memcpy(c->r_unm.as<char>() + ou, c->dev[k].a_unm.p, res[k].unm);
+                ol += res[k].lifted;
+                ou += res[k].unm;
+            }
         }
     }
     for (int k = 0; k < nd; k++) {
-        if (res[k].has_err)
+        if (res[k].has_err) {
+            // The reference streams (bed.d:113-199): every record in front of the malformed line has been
+            // written when it dies.  Same here: lift the input up to that line once more (it parses) and
+            // hand those outputs back together with the error.
+            const uint64_t off = res[k].err_off;
+            if (off > 0 && off <= in_len) {
+                const int rc2 = swo_lift_bed_text(c, in, (size_t)off, out);
+                if (rc2 != SWO_OK) memset(out, 0, sizeof *out);
+            }
             return fail(c, SWO_E_PARSE, "BED line at byte %llu has fewer than 3 fields or a non-integer coordinate",
-                        (unsigned long long)res[k].err_off);
+                        (unsigned long long)off);
+        }
         out->lifted_len += res[k].lifted;
         out->unmatched_len += res[k].unm;
         out->n_records += res[k].rec;
@@ -974,6 +1040,21 @@ int swo_lift_bed_text(swo_ctx *c, const char *in, size_t in_len, swo_text_out *o
     }
     out->lifted = c->r_lifted.as<char>();
     out->unmatched = c->r_unm.as<char>();
+    if (nd == 1) {
+        c->seg_l.assign(1, {out->lifted, out->lifted_len});
+        c->seg_u.assign(1, {out->unmatched, out->unmatched_len});
+    } else if (!c->concat) {
+        out->lifted = out->unmatched = nullptr;  // the lengths are the totals; the bytes are in the segments
+    }
+    return SWO_OK;
+}
+
+int swo_text_num_segments(const swo_ctx *c) { return c ? (int)c->seg_l.size() : 0; }
+int swo_text_segment(const swo_ctx *c, int which, int i, const char **ptr, size_t *len) {
+    if (!c || !ptr || !len || i < 0 || i >= (int)c->seg_l.size() || (which != 0 && which != 1)) return SWO_E_ARG;
+    const auto &sg = which == 0 ? c->seg_l[i] : c->seg_u[i];
+    *ptr = sg.first;
+    *len = sg.second;
     return SWO_OK;
 }
 

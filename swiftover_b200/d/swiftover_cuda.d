@@ -60,6 +60,8 @@ int swo_lift_intervals_dev(swo_ctx* ctx, size_t n, const(int)* d_tcid, const(int
 int swo_lift_points(swo_ctx* ctx, size_t n, const(int)* tcid, const(int)* pos, int* out_qcid, int* out_pos,
                     ubyte* hit);
 int swo_lift_bed_text(swo_ctx* ctx, const(char)* inbuf, size_t in_len, swo_text_out* o);
+int swo_text_num_segments(const(swo_ctx)* ctx);
+int swo_text_segment(const(swo_ctx)* ctx, int which, int i, const(char)** ptr, size_t* len);
 int swo_lift_bed_text_dev(swo_ctx* ctx, const(char)* d_in, size_t in_len, char* d_lifted, size_t lifted_cap,
                           char* d_unmatched, size_t unmatched_cap, ulong* d_sizes, void* stream);
 int swo_load_genome_2bit(swo_ctx* ctx, const(ubyte)* packed, size_t packed_bytes, const(long)* contig_off,

@@ -69,3 +69,16 @@ def test_cli_bed_liftover(exe, oracle, tmp_path):
     r = subprocess.run([exe, "-t", "bed", "-c", str(tmp_path / "c.chain"), "-u", str(tmp_path / "un2.bed")], input=data,
                        capture_output=True)
     assert r.returncode == 0 and r.stdout == oc.lift_bed(data)[0]
+    # a malformed line: the records in front of it are written (the reference streams, bed.d:113-199), exit status 1
+    good = resource_bytes("chr1_hg19.bed")[:50_000]
+    good = good[: good.rfind(b"\n") + 1]
+    (tmp_path / "bad.bed").write_bytes(good + b"chr1\t12\n" + resource_bytes("test.bed"))
+    r = run(exe, "-t", "bed", "-c", str(tmp_path / "c.chain"), "-i", str(tmp_path / "bad.bed"), "-o", str(tmp_path / "o3.bed"),
+            "-u", str(tmp_path / "u3.bed"))
+    assert r.returncode == 1 and b"fewer than 3 fields" in r.stderr
+    o_l, o_u, _ = oc.lift_bed(good)
+    assert (tmp_path / "o3.bed").read_bytes() == o_l and (tmp_path / "u3.bed").read_bytes() == o_u
+    # an output path that cannot be written: non-zero exit, not a silently truncated file
+    r = run(exe, "-t", "bed", "-c", str(tmp_path / "c.chain"), "-i", str(tmp_path / "in.bed"), "-o", "/dev/full",
+            "-u", str(tmp_path / "u4.bed"))
+    assert r.returncode != 0

@@ -233,6 +233,24 @@ def test_text_errors(oracle):
     cf.close()
 
 
+def test_text_error_keeps_the_records_in_front(hg):
+    """The reference streams (bed.d:113-199): everything in front of a malformed line is written
+    before it dies.  swo_lift_bed_text returns SWO_E_PARSE with exactly those outputs."""
+    import ctypes as C
+    from oracle_ffi import _bytes_at
+    from swiftover_b200 import _lib as L
+    cf, oc = hg
+    good = resource_bytes("hg19_col123.bed")[:200_000]
+    good = good[: good.rfind(b"\n") + 1]
+    data = good + b"chr1 oops 10\n" + resource_bytes("test.bed")
+    out = L.SwoTextOut()
+    rc = L.lib().swo_lift_bed_text(cf.handle, data, len(data), C.byref(out))
+    assert rc == L.SWO_E_PARSE
+    o_l, o_u, st = oc.lift_bed(good)
+    assert _bytes_at(out.lifted, out.lifted_len) == o_l and _bytes_at(out.unmatched, out.unmatched_len) == o_u
+    assert out.n_records == st["n_records"]
+
+
 @pytest.mark.parametrize("seed", range(10))
 def test_text_random(oracle, seed):
     rng = np.random.default_rng(700 + seed)
@@ -341,6 +359,58 @@ def test_text_logical_shards(oracle, nshards):
         o_l, o_u, _ = oc.lift_bed(data)
         assert lifted == o_l and unm == o_u
     cf.close()
+
+
+def test_text_shards_as_segments(oracle):
+    """concat = 0: no concatenation copy, the shards' pieces in order are the output (swo_text_segment)."""
+    from oracle_ffi import _bytes_at
+    cf, oc = pair(oracle, resource_bytes("hg19ToHg38.over.chain"), devices=[0] * 3)
+    cf.set_option("concat", 0)
+    data = resource_bytes("hg19_col123.bed")
+    out = cf.lift_bed_text_ptr(data, len(data))
+    o_l, o_u, _ = oc.lift_bed(data)
+    assert not out.lifted and not out.unmatched and out.lifted_len == len(o_l) and out.unmatched_len == len(o_u)
+    segs_l, segs_u = cf.text_segments(0), cf.text_segments(1)
+    assert len(segs_l) == 3 and len(segs_u) == 3
+    assert b"".join(_bytes_at(p, n) for p, n in segs_l) == o_l
+    assert b"".join(_bytes_at(p, n) for p, n in segs_u) == o_u
+    cf.close()
+
+
+def test_text_physical_devices(oracle):
+    """The in-process sharder on every GPU of the box: a single input cut into one
+    byte-range shard per device must give the 1-device output byte for byte.  SWO_MULTI_BYTES sets the
+    input size (default 64 MB; the multi-GPU run of this round used 4 GB, see profiles/)."""
+    import hashlib
+    import torch
+    from swiftover_b200 import ChainFile
+    from swiftover_b200 import synth as S
+    ndev = torch.cuda.device_count()
+    if ndev < 2:
+        pytest.skip("one GPU: the sharder runs with logical shards in test_text_logical_shards")
+    chain = resource_bytes("hg19ToHg38.over.chain")
+    want = int(os.environ.get("SWO_MULTI_BYTES", 64 << 20))
+    one = ChainFile(text=chain, devices=[0])
+    iv = S.gen_intervals(one, want // 24, 20240002, device="cuda:0", sort=True)
+    host = S.bed_text(one, iv, ncols=3).cpu().pin_memory()
+    del iv
+    ref = one.lift_bed_text_ptr(host.data_ptr(), host.numel())
+    ref_l = hashlib.sha256(_view(ref.lifted, ref.lifted_len)).hexdigest()
+    ref_u = hashlib.sha256(_view(ref.unmatched, ref.unmatched_len)).hexdigest()
+    ref_n = (ref.lifted_len, ref.unmatched_len, ref.n_records, ref.n_rows, ref.n_unmatched)
+    one.close()
+    for devs in ([0, 1], list(range(ndev))):
+        cf = ChainFile(text=chain, devices=devs)
+        out = cf.lift_bed_text_ptr(host.data_ptr(), host.numel())
+        assert (out.lifted_len, out.unmatched_len, out.n_records, out.n_rows, out.n_unmatched) == ref_n
+        assert hashlib.sha256(_view(out.lifted, out.lifted_len)).hexdigest() == ref_l
+        assert hashlib.sha256(_view(out.unmatched, out.unmatched_len)).hexdigest() == ref_u
+        cf.close()
+
+
+def _view(ptr, n):
+    import ctypes
+    return (ctypes.c_char * n).from_address(ptr) if n else b""
 
 
 def test_text_heavy_and_long_lines(hg):
