@@ -165,6 +165,9 @@ def run_cuda(args):
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         out = cf.lift_bed_text_ptr(host_in.data_ptr(), in_bytes)
+        # ordered concat across ranks = one exchange of piece lengths per step: a rank's piece goes to its
+        # offset of the output (shard.piece_offsets); the bytes stay where the D2H copies put them
+        my_off, totals = shard.piece_offsets([out.lifted_len, out.unmatched_len], device=dev)
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
     barrier()
@@ -204,6 +207,8 @@ def run_cuda(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes,
                     "d2h_bytes_per_step": out_bytes + 48 * max(1, e2e_launches // e2e_steps), "steps": e2e_steps,
                     "ms_per_step": e2e_ms_total / e2e_steps, "api": "swo_lift_bed_text (pinned host in/out)",
+                    "concat": "pieces stay in each rank's pinned arena; their offsets in the ordered output come from one "
+                              "all_gather of the piece lengths per step (inside the timed region)",
                     "link_ceiling": {"ms_per_step": link_ms, "value": world * n / (link_ms * 1e-3), "unit": UNIT,
                                      "what": "cudaMemcpyAsync H2D of the input bytes and D2H of the output bytes at the "
                                              "same time on two streams, pinned memory, all ranks at once (max over ranks)"},

@@ -65,3 +65,21 @@ def gather_in_rank_order(obj):
     out = [None] * dist.get_world_size()
     dist.all_gather_object(out, obj)
     return out
+
+
+def piece_offsets(lengths, device="cpu"):
+    """Ordered concatenation without a copy: every rank contributes the byte lengths of its output
+    pieces (e.g. [lifted, unmatched]); returned are this rank's offsets in the concatenated outputs
+    (the sum of the lower ranks' lengths) and the totals.  One small all_gather: a rank then writes
+    its piece at its offset (pwrite / its slot of a shared segment) and the result is the
+    single-process output, byte for byte (outputs in shard order)."""
+    import torch
+    import torch.distributed as dist
+    mine = torch.tensor(list(lengths), dtype=torch.int64, device=device)
+    if not (dist.is_available() and dist.is_initialized()):
+        return [0] * len(lengths), mine.tolist()
+    world, rank = dist.get_world_size(), dist.get_rank()
+    every = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(every, mine)
+    stack = torch.stack(every)
+    return stack[:rank].sum(0).tolist(), stack.sum(0).tolist()

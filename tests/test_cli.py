@@ -79,6 +79,7 @@ def test_cli_bed_liftover(exe, oracle, tmp_path):
     o_l, o_u, _ = oc.lift_bed(good)
     assert (tmp_path / "o3.bed").read_bytes() == o_l and (tmp_path / "u3.bed").read_bytes() == o_u
     # an output path that cannot be written: non-zero exit, not a silently truncated file
+    (tmp_path / "in.bed").write_bytes(resource_bytes("chr1_hg19.bed"))
     r = run(exe, "-t", "bed", "-c", str(tmp_path / "c.chain"), "-i", str(tmp_path / "in.bed"), "-o", "/dev/full",
             "-u", str(tmp_path / "u4.bed"))
     assert r.returncode != 0

@@ -35,7 +35,8 @@ def _worker(rank, world, port, bed_name, q):
     a, b = shard.shard_bounds(data, rank, world)
     lifted, unm, st = oc.lift_bed(data[a:b])
     shard.barrier()
-    parts = shard.gather_in_rank_order((a, b, lifted, unm, st["n_records"]))
+    off, tot = shard.piece_offsets([len(lifted), len(unm)])
+    parts = shard.gather_in_rank_order((a, b, lifted, unm, st["n_records"], off, tot))
     mx = shard.max_over_ranks([float(rank + 1), 10.0 - rank])
     if rank == 0:
         q.put((parts, mx))
@@ -56,6 +57,12 @@ def test_rank_sharding_matches_single_process(oracle, world, bed):
         p.join(timeout=60)
         assert p.exitcode == 0
     data = resource_bytes(bed)
+    # piece offsets (one all_gather of lengths): every rank's piece lands at the sum of the lower ranks' lengths
+    run_l = run_u = 0
+    for p in parts:
+        assert p[5] == [run_l, run_u]
+        run_l, run_u = run_l + len(p[2]), run_u + len(p[3])
+        assert p[6] == [sum(len(x[2]) for x in parts), sum(len(x[3]) for x in parts)]
     # shards tile the input exactly, on line boundaries
     assert parts[0][0] == 0 and parts[-1][1] == len(data)
     for (a0, b0, *_), (a1, b1, *_) in zip(parts[:-1], parts[1:]):
