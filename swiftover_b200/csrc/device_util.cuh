@@ -67,16 +67,28 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- warp reconvergence ---------------------------------------------------
-// Reconverge the warp behind long divergent per-thread work, before a block barrier (bar.sync
-// counts arrivals per WARP, so a split warp arriving twice breaks the barrier) or a warp
-// collective.  Out of line and with the mask as a run-time value on purpose: ptxas 12.9 (sm_100a)
-// drops a __syncwarp() — also one with a mask it cannot see through — wherever it takes the warp
-// for converged (behind a BSYNC.RECONVERGENT), and it is not always right: on tiles whose lanes
-// mix the hinted and the full search one lane was seen (progress markers in host-mapped memory)
-// still behind the search loop while the other 31 had passed the scan's barriers; the block
-// scan came out short or the kernel died with "illegal instruction".  Inside a function that is
-// not inlined nothing is known about the callers' convergence, so the WARPSYNC stays.
+// Behind long divergent per-thread work (the per-query searches) a warp can reach the next warp
+// collective or block barrier SPLIT although the code is straight-line there: ptxas 12.9 (sm_100a)
+// takes the warp for converged behind its BSYNC.RECONVERGENT and
+//   * drops a __syncwarp() placed there — also this out-of-line form with a run-time mask: in
+//     merge_count_kernel the whole function became "LDC; NOP; RET"
+//     (profiles/r02_converge_sass_merge_count.txt);
+//   * emits REDUX (redux.sync: __reduce_add_sync / __reduce_min_sync) with no convergence check,
+//     so a split warp reduces only the lanes that are there: tools/fuzz_parity.py seed 771 lost one
+//     lane's rows from a tile total.  SHFL / VOTE are compiled with an out-of-line
+//     WARPSYNC.COLLECTIVE path for exactly that case and stay correct.
+// Rules this code follows: reductions and scans behind divergent work use shuffles (warp_sum,
+// warp_min, warp_inclusive_scan), never redux.sync; converge_warp is kept in front of block
+// barriers (bar.sync counts arrivals per warp) — where ptxas keeps its WARPSYNC it costs 1-5 %,
+// where ptxas elides it nothing.  Experiments: profiles/r02_converge_experiments.md
+// (compute-sanitizer is closed on this pool, so there is no synccheck log).
+#if defined(SWO_CONVERGE_NONE)  // experiments (profiles/r02_converge_*): nothing at all ...
+__device__ __forceinline__ void converge_warp(unsigned) {}
+#elif defined(SWO_CONVERGE_PLAIN)  // ... or the plain intrinsic, inlined
+__device__ __forceinline__ void converge_warp(unsigned) { __syncwarp(); }
+#else
 __device__ __noinline__ void converge_warp(unsigned mask) { __syncwarp(mask); }
+#endif
 
 // ---- warp / block scans ----------------------------------------------------
 template <typename T>
@@ -86,6 +98,12 @@ __device__ __forceinline__ T warp_inclusive_scan(T v) {
         T o = __shfl_up_sync(FULL, v, d);
         if (lane_id() >= d) v += o;
     }
+    return v;
+}
+// (shuffle-based on purpose, not redux.sync: see the note at converge_warp)
+__device__ __forceinline__ int warp_min(int v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v = min(v, __shfl_xor_sync(FULL, v, d));
     return v;
 }
 template <typename T>

@@ -67,6 +67,16 @@ struct LiftArgs {
 
 // see converge_warp (device_util.cuh)
 __device__ __forceinline__ void converge(const LiftArgs &A) { converge_warp(A.full_mask); }
+// the same per call site, so that experiments can swap single sites for the plain intrinsic
+// (-DSWO_PLAIN_SITES=<bit mask>; profiles/r02_converge_experiments.md)
+#ifndef SWO_PLAIN_SITES
+#define SWO_PLAIN_SITES 0
+#endif
+template <int SITE>
+__device__ __forceinline__ void converge_at(const LiftArgs &A) {
+    if ((SWO_PLAIN_SITES >> SITE) & 1) __syncwarp();
+    else converge_warp(A.full_mask);
+}
 
 // Where a tile's rows go: global memory (positions are global row indices) or the tile's
 // shared-memory stage (positions are offsets inside the tile).
@@ -152,7 +162,7 @@ __device__ __noinline__ void expand_query_coop(const LiftArgs &A, const RowSink 
         }
         scr[c] = key;
     }
-    converge(A);
+    converge_at<0>(A);
     if (BLOCK) __syncthreads();
     bool mine = true;
     for (int c = first; c < P; c += stride)
@@ -175,7 +185,7 @@ __device__ __noinline__ void expand_query_coop(const LiftArgs &A, const RowSink 
                 // then race on the keys: test_binary_* fail); block form: uniform trip counts behind
                 // the reconvergence above, the block barrier alone is enough
                 if (BLOCK) __syncthreads();
-                else converge(A);
+                else converge_at<1>(A);
             }
         }
     }
@@ -270,7 +280,7 @@ __device__ __forceinline__ void flush_pending(const LiftArgs &A, LiftSmem<THICK,
         A.row_offset[A.n] = (uint32_t)(gb + total);
         A.totals[0] = gb + total;
     }
-    converge(A);
+    converge_at<2>(A);
     __syncthreads();  // the stage is free again
     if (tid == 0) S.p_tile = -1;
 }
@@ -385,7 +395,7 @@ __global__ void __launch_bounds__(LI_TPB, 4) lift_intervals_kernel(const __grid_
                 r_e[k] = r.e;
             }
         }
-        converge(A);
+        converge_at<3>(A);
         // Block scan of the per-thread fan-out (the warp was reconverged just above: the scan's
         // shuffles and barriers need every lane there); the unmatched count goes through a
         // shared-memory atomic.
@@ -464,7 +474,7 @@ __global__ void __launch_bounds__(LI_TPB, 4) lift_intervals_kernel(const __grid_
         }
         // multi-hit queries: rounds of (fill the work list, expand it cooperatively) until none is
         // pending — batches where most queries have many hits need more than one round
-        converge(A);
+        converge_at<4>(A);
         if (__syncthreads_or(pending != 0)) {
             for (;;) {
                 {
@@ -485,7 +495,7 @@ __global__ void __launch_bounds__(LI_TPB, 4) lift_intervals_kernel(const __grid_
                         rb += (uint64_t)nh[k];
                     }
                 }
-                converge(A);
+                converge_at<5>(A);
                 __syncthreads();
                 const int nwl = min(S.wl_n, LI_WL_CAP);
                 const bool heavy = S.wl_heavy != 0;
@@ -507,7 +517,7 @@ __global__ void __launch_bounds__(LI_TPB, 4) lift_intervals_kernel(const __grid_
                             expand_query<THICK>(A, sink, ey, S.wl_q[e], S.wl_lo[e], S.wl_cnt[e], gbase + S.wl_off[e], tid, LI_TPB);
                     }
                 }
-                converge(A);
+                converge_at<6>(A);
                 if (!__syncthreads_or(pending != 0)) break;
                 if (tid == 0) {
                     S.wl_n = 0;

@@ -437,7 +437,7 @@ __global__ void __launch_bounds__(MG_TPB, 4) merge_count_kernel(const __grid_con
         if (same) {
             const int4 cm = cm_smem ? S.cmeta[tc0] : load_cmeta(T, tc0);
             const int m01 = st[0] < st[1] ? st[0] : st[1], m23 = st[2] < st[3] ? st[2] : st[3];
-            const int smin = __reduce_min_sync(FULL, m01 < m23 ? m01 : m23);
+            const int smin = warp_min(m01 < m23 ? m01 : m23);
             // The warp's window: 64 consecutive blocks that contain the lower bound of its smallest start.
             // Groups of 32 blocks (every table up to 65,536 blocks): the group found in the shared-memory
             // samples and the one behind it, no probe of the key array in between; larger groups: the
@@ -460,7 +460,12 @@ __global__ void __launch_bounds__(MG_TPB, 4) merge_count_kernel(const __grid_con
             tsum += (uint32_t)cnt;
             unm_acc += (cnt == 0 && (full || q0 + k < A.n)) ? 1u : 0u;
         }
-        const uint32_t total = __reduce_add_sync(FULL, tsum);
+        // Shuffles, not redux.sync: behind the divergent per-thread search the warp can still be split here
+        // (ptxas 12.9 takes it for converged and even turns converge_warp into a NOP in this kernel), a
+        // SHFL then takes its out-of-line WARPSYNC.COLLECTIVE path, whereas REDUX.SUM silently sums the
+        // lanes that happen to be there (found by tools/fuzz_parity.py seed 771: one lane's rows missing
+        // from the tile total; profiles/r02_converge_experiments.md).
+        const uint32_t total = warp_sum(tsum);
         if (lane == 0) {
             M.total[tile] = total;
             M.window[tile] = wb;
@@ -562,7 +567,7 @@ __global__ void __launch_bounds__(MG_TPB, MG_WRITE_CTAS) merge_write_kernel(cons
             const int tc0 = __shfl_sync(FULL, tc[0], 0);
             const int4 cm = cm_smem ? S.cmeta[tc0] : load_cmeta(T, tc0);
             const int m01 = st[0] < st[1] ? st[0] : st[1], m23 = st[2] < st[3] ? st[2] : st[3];
-            const int smin = __reduce_min_sync(FULL, m01 < m23 ? m01 : m23);
+            const int smin = warp_min(m01 < m23 ? m01 : m23);
             merge_window(T, wb, cm.y, smin, st, en, lo, hi);
         } else {
             const LoHi4 r = search_each(A, q0);
