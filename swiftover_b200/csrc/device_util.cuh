@@ -67,21 +67,18 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- warp reconvergence ---------------------------------------------------
-// Behind long divergent per-thread work (the per-query searches) a warp can reach the next warp
-// collective or block barrier SPLIT although the code is straight-line there: ptxas 12.9 (sm_100a)
-// takes the warp for converged behind its BSYNC.RECONVERGENT and
-//   * drops a __syncwarp() placed there — also this out-of-line form with a run-time mask: in
-//     merge_count_kernel the whole function became "LDC; NOP; RET"
-//     (profiles/r02_converge_sass_merge_count.txt);
-//   * emits REDUX (redux.sync: __reduce_add_sync / __reduce_min_sync) with no convergence check,
-//     so a split warp reduces only the lanes that are there: tools/fuzz_parity.py seed 771 lost one
-//     lane's rows from a tile total.  SHFL / VOTE are compiled with an out-of-line
-//     WARPSYNC.COLLECTIVE path for exactly that case and stay correct.
-// Rules this code follows: reductions and scans behind divergent work use shuffles (warp_sum,
-// warp_min, warp_inclusive_scan), never redux.sync; converge_warp is kept in front of block
-// barriers (bar.sync counts arrivals per warp) — where ptxas keeps its WARPSYNC it costs 1-5 %,
-// where ptxas elides it nothing.  Experiments: profiles/r02_converge_experiments.md
-// (compute-sanitizer is closed on this pool, so there is no synccheck log).
+// Behind long divergent per-thread work (per-query searches: loops with a per-lane trip count) a
+// warp can reach the next warp collective or block barrier SPLIT although the code is straight-line
+// there: ptxas 12.9 (sm_100a) takes the warp for converged behind its BSYNC.RECONVERGENT, emits
+// the collective without the BRA.DIV / WARPSYNC.COLLECTIVE guard and drops a __syncwarp() placed
+// there — in merge_count_kernel even this out-of-line form with a run-time mask became
+// "LDC; NOP; RET" — and on the GPU a lane was occasionally not part of the collective (a short
+// block scan, "illegal instruction" at a bar.sync, a tile total without one lane's rows).
+// Experiments and SASS: profiles/r02_converge_experiments.md (compute-sanitizer is closed on this
+// pool, so there is no synccheck log).  The kernels of kernels_binary.cuh and kernels_text.cuh call
+// this in front of every barrier / collective behind their searches (ptxas keeps the WARPSYNC in
+// those kernels; cost 1-5 %); the merge kernels (kernels_merge.cuh) avoid the situation instead:
+// every loop there has a warp-uniform trip count.
 #if defined(SWO_CONVERGE_NONE)  // experiments (profiles/r02_converge_*): nothing at all ...
 __device__ __forceinline__ void converge_warp(unsigned) {}
 #elif defined(SWO_CONVERGE_PLAIN)  // ... or the plain intrinsic, inlined

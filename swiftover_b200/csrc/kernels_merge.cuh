@@ -32,11 +32,11 @@
 //     starts a convoy, and the per-tile chain ticket -> load -> search -> publish -> resolve ->
 //     store leaves the SMs idle; here no warp ever waits for another.
 //   * The first candidate's row is computed without branches for every query (four block loads in
-//     flight per lane) and kept for single-hit queries.  Queries with 2..MG_SMALL candidate blocks
-//     are expanded by their own thread (sequentially when their rows are already in qStart order,
-//     forwards or backwards).  Larger ones are appended to a list {query, first block, candidates,
-//     row position} and expanded by expand_wide_kernel, a warp per query (list full: by their
-//     warp, on the spot).
+//     flight per lane) and kept for single-hit queries.  A query with two candidate blocks (an
+//     interval across one gap) is expanded by its own thread, straight-line.  Larger ones are
+//     appended to a list {query, first block, candidates, row position} and expanded by
+//     expand_wide_kernel, a warp per query (list full: by their warp, on the spot).
+//   * Every loop of the merge kernels has a warp-uniform trip count (see merge_window for why).
 // Only for target-disjoint tables (every UCSC over.chain; the host sends other tables to the
 // per-query-search variant): candidates == hits, and pmaxKey[j] == tEnd[j].
 #pragma once
@@ -45,7 +45,6 @@
 namespace swo {
 
 
-constexpr int MG_SMALL = 16;   // candidates up to which a multi-hit query is expanded by its own thread
 constexpr int MG_XS = 128;     // per-warp sort scratch in shared memory (entries)
 constexpr int MG_GXS = 2048;   // per-warp sort scratch in global memory (entries)
 constexpr int MG_QPW = 32 * LI_IPT;  // queries per warp pass ("tile")
@@ -67,6 +66,9 @@ struct MergeTiles {
     uint32_t *total;          // [ntw] rows of the tile; after the scan: exclusive prefix inside its scan tile
     int32_t *window;          // [ntw] first block of the tile's window, -1: per-query search
     unsigned long long *sum;  // [ntw / MG_SCAN_TILE + 1] rows per scan tile; after the scan: exclusive prefix
+#ifdef MG_DEBUG_COUNTS
+    int32_t *dbg;             // [4 * n]: per query {lo, hi, path, -} as the count pass saw them
+#endif
 };
 
 struct MergeSmem {
@@ -135,148 +137,22 @@ __device__ __forceinline__ bool merge_step(int pmj, int tsj, const int (&st)[LI_
     return any != 0u;
 }
 
-// first j in [base, end) with key[j] > x (GE: >= x), else end — for up to four searches of one
-// thread at once (bit k of `act`): an exponential probe from base, then bisection, with the loads
-// of the four searches issued together in every round (one dependent-load chain instead of four).
-struct Int4x {
-    int v[LI_IPT];
-};
-template <bool GE>
-__device__ __noinline__ Int4x gallop4(const int32_t *__restrict__ key, int end, Int4x base, Int4x x, unsigned act) {
-    int a[LI_IPT], b[LI_IPT];
-    unsigned need = 0;
-#pragma unroll
-    for (int k = 0; k < LI_IPT; k++) {
-        a[k] = base.v[k];
-        b[k] = end;
-        if (((act >> k) & 1u) && a[k] < end) need |= 1u << k;
-    }
-    for (int step = 8; need; step <<= 1) {
-        int p[LI_IPT], v[LI_IPT];
-#pragma unroll
-        for (int k = 0; k < LI_IPT; k++) {
-            p[k] = a[k] + step - 1 < end ? a[k] + step - 1 : end - 1;
-            v[k] = ((need >> k) & 1u) ? __ldg(key + p[k]) : 0;
-        }
-#pragma unroll
-        for (int k = 0; k < LI_IPT; k++) {
-            if ((need >> k) & 1u) {
-                if (GE ? v[k] >= x.v[k] : v[k] > x.v[k]) {
-                    b[k] = p[k];
-                    need &= ~(1u << k);
-                } else {
-                    a[k] = p[k] + 1;
-                    if (a[k] >= end) need &= ~(1u << k);
-                }
-            }
-        }
-    }
-    for (;;) {
-        unsigned open = 0;
-        int m[LI_IPT], v[LI_IPT];
-#pragma unroll
-        for (int k = 0; k < LI_IPT; k++) {
-            const bool o = ((act >> k) & 1u) && a[k] < b[k];
-            m[k] = (int)(((unsigned)a[k] + (unsigned)b[k]) >> 1);
-            v[k] = o ? __ldg(key + m[k]) : 0;
-            open |= o ? 1u << k : 0u;
-        }
-        if (!open) break;
-#pragma unroll
-        for (int k = 0; k < LI_IPT; k++) {
-            if ((open >> k) & 1u) {
-                if (GE ? v[k] >= x.v[k] : v[k] > x.v[k]) b[k] = m[k];
-                else a[k] = m[k] + 1;
-            }
-        }
-    }
-    Int4x r;
-#pragma unroll
-    for (int k = 0; k < LI_IPT; k++) r.v[k] = a[k];
-    return r;
-}
-
-// The per-query search of kernels_binary.cuh for a thread's four queries (re-read from global
-// memory: this is the rare path — warps that straddle a contig boundary and the batch tail).
-struct LoHi4 {
-    int lo[LI_IPT], hi[LI_IPT];
-};
-__device__ __noinline__ LoHi4 search_each(const LiftArgs &A, uint32_t q0) {
+// A query across exactly one gap (two candidate blocks, the usual multi-hit case): both rows, in
+// (qStart, block) order, with the running strand flip (bed.d:156-173).  Straight-line code on purpose:
+// see the note on divergent loops at merge_window.
+__device__ __forceinline__ void expand_pair(const LiftArgs &A, uint32_t q, int lo, int start, int end, unsigned char strand_byte,
+                                            uint64_t pos) {
     const TableView &T = A.T;
-    LoHi4 r;
-    int ptc = -1, pst = 0;
-#pragma unroll
-    for (int k = 0; k < LI_IPT; k++) {
-        const bool ok = q0 + k < A.n;
-        const int tc = ok ? __ldg(A.tcid + q0 + k) : -1;
-        const int st = ok ? __ldg(A.start + q0 + k) : 0, en = ok ? __ldg(A.end + q0 + k) : 0;
-        Block b0;
-        Cand cd{0, 0};
-        if (tc >= 0 && tc < T.ntc) {
-            const int4 cm = load_cmeta(T, tc);
-            if (k > 0 && tc == ptc && st >= pst) cd = find_candidates_from(T, cm.y, r.lo[k - 1], st, en, b0);
-            else cd = find_candidates_cm(T, T.ey, cm, st, en, b0);
-        }
-        r.lo[k] = cd.lo;
-        r.hi[k] = cd.hi;
-        ptc = tc;
-        pst = st;
+    const RowCore a = make_row(load_block(T, lo), start, end), b = make_row(load_block(T, lo + 1), start, end);
+    const bool swap = b.key < a.key;
+    const RowCore &r0 = swap ? b : a, &r1 = swap ? a : b;
+    unsigned char s0 = 0, s1 = 0;
+    if (A.strand) {
+        s0 = strand_flip(strand_byte, r0.inv);
+        s1 = strand_flip(s0, r1.inv);  // bed.d:173: the flips accumulate
     }
-    return r;
-}
-// A multi-hit query with few candidates, expanded by its own thread.  The candidates of a query are
-// consecutive blocks, nearly always of one chain: their sort keys (raw qStart, bed.d:156) then run
-// ascending ('+' chains) or strictly descending ('-' chains) and the rows are written in one
-// sequential pass, forwards or backwards, with the running strand flip (bed.d:173); any other
-// order takes the rank-by-comparison form.
-__device__ __noinline__ bool expand_small(const LiftArgs &A, uint32_t q, int lo, int cnt, uint64_t pos) {
-    const TableView &T = A.T;
-    const int start = __ldg(A.start + q), end = __ldg(A.end + q);
-    if (cnt == 2 && T.disjoint) {  // the usual case: an interval across one gap
-        const RowCore a = make_row(load_block(T, lo), start, end), b = make_row(load_block(T, lo + 1), start, end);
-        const bool swap = b.key < a.key;
-        const RowCore &r0 = swap ? b : a, &r1 = swap ? a : b;
-        unsigned char s0 = 0, s1 = 0;
-        if (A.strand) {
-            s0 = strand_flip(__ldg(A.strand + q), r0.inv);
-            s1 = strand_flip(s0, r1.inv);  // bed.d:173: the flips accumulate
-        }
-        if (pos < A.rows_cap) st_stream_v4(A.rows + pos, make_int4(r0.qcid | ((int)s0 << 16), r0.s, r0.e, (int)q));
-        if (pos + 1 < A.rows_cap) st_stream_v4(A.rows + pos + 1, make_int4(r1.qcid | ((int)s1 << 16), r1.s, r1.e, (int)q));
-        return true;
-    }
-    bool asc = true, desc = true, first = true;
-    int prev = 0, nhit = 0;
-    for (int c = 0; c < cnt; c++) {
-        const Block b = load_block(T, lo + c);
-        if (!T.disjoint && !block_hits(b, start)) continue;
-        const int key = make_row(b, start, end).key;
-        if (!first) {
-            asc &= key >= prev;
-            desc &= key < prev;
-        }
-        first = false;
-        prev = key;
-        nhit++;
-    }
-    if (!asc && !desc) return false;
-    const unsigned char orig = A.strand ? __ldg(A.strand + q) : 0;
-    int rank = 0, negs = 0, inv_first = 1;
-    for (int i = 0; i < cnt; i++) {
-        const int c = asc ? i : cnt - 1 - i;
-        const Block b = load_block(T, lo + c);
-        if (!T.disjoint && !block_hits(b, start)) continue;
-        const RowCore r = make_row(b, start, end);
-        if (rank == 0) inv_first = r.inv;
-        negs += r.inv < 0 ? 1 : 0;
-        const uint64_t p = pos + (uint64_t)rank;
-        if (p < A.rows_cap) {
-            const unsigned char sb = A.strand ? strand_at_rank(orig, inv_first, rank, negs) : 0;
-            st_stream_v4(A.rows + p, make_int4(r.qcid | ((int)sb << 16), r.s, r.e, (int)q));
-        }
-        rank++;
-    }
-    return true;
+    if (pos < A.rows_cap) st_stream_v4(A.rows + pos, make_int4(r0.qcid | ((int)s0 << 16), r0.s, r0.e, (int)q));
+    if (pos + 1 < A.rows_cap) st_stream_v4(A.rows + pos + 1, make_int4(r1.qcid | ((int)s1 << 16), r1.s, r1.e, (int)q));
 }
 
 // one multi-hit query by a whole warp: sort keys in shared memory, in the warp's global scratch, or
@@ -288,48 +164,124 @@ __device__ __forceinline__ void expand_wide(const LiftArgs &A, const RowSink &si
     else expand_query<false>(A, sink, A.T.ey, q, lo, cnt, pos, lane_id(), 32);
 }
 
-// The window merge of one warp: blocks [wb, wb+64) of a contig ending at block `cend` against the
-// lane's four queries (all of the warp's queries on that contig, none starting before smin).
-__device__ __forceinline__ void merge_window(const TableView &T, int wb, int cend, int smin, const int (&st)[LI_IPT],
+// The window merge of one warp: blocks [wb, wb+64) of a contig ending at block `cend` against those of
+// the lane's four queries that are on that contig (bit k of `act`), none of which starts before smin.
+//
+// EVERY LOOP IN THE MERGE KERNELS HAS A WARP-UNIFORM TRIP COUNT.  An earlier version finished queries
+// that ran past the window, and warps with several contigs, with per-thread searches (data-dependent
+// loops per lane).  Behind such loops ptxas 12.9 (sm_100a) takes the warp for converged: it emits the
+// following SHFL / REDUX without their BRA.DIV + WARPSYNC.COLLECTIVE guard and reduces __syncwarp()
+// — also an out-of-line one with a run-time mask — to a NOP; on the GPU a lane was occasionally
+// not there (tools/fuzz_parity.py seed 771: one lane's rows missing from a tile total, in one build
+// and not in another with a printf added).  profiles/r02_converge_experiments.md has the SASS.
+// With uniform loops there is nothing to reconverge.
+__device__ __forceinline__ void merge_window(const TableView &T, int wb, int cend, int smin, unsigned act, const int (&st)[LI_IPT],
                                              const int (&en)[LI_IPT], int (&lo)[LI_IPT], int (&hi)[LI_IPT]) {
     const int lane = lane_id();
     const int ja = wb + lane, jb = wb + 32 + lane;
     const int pmA = ja < cend ? __ldg(T.pmaxKey + ja) : 0x7fffffff, tsA = ja < cend ? __ldg(T.tStartKey + ja) : 0x7fffffff;
     const int pmB = jb < cend ? __ldg(T.pmaxKey + jb) : 0x7fffffff, tsB = jb < cend ? __ldg(T.tStartKey + jb) : 0x7fffffff;
+    // queries of other contigs take no part: no block ends at or before INT_MIN, none starts before it
+    int s2[LI_IPT], e2[LI_IPT], l2[LI_IPT], h2[LI_IPT];
+#pragma unroll
+    for (int k = 0; k < LI_IPT; k++) {
+        const bool on = (act >> k) & 1u;
+        s2[k] = on ? st[k] : (int)0x80000000;
+        e2[k] = on ? en[k] : (int)0x80000000;
+    }
     // blocks of the window that end at or before the smallest start lie before every query
     int jj = __popc(__ballot_sync(FULL, pmA <= smin));
     if (jj == 32) jj += __popc(__ballot_sync(FULL, pmB <= smin));
     const int w_end = wb + 64;
 #pragma unroll
-    for (int k = 0; k < LI_IPT; k++) lo[k] = hi[k] = wb + jj;
+    for (int k = 0; k < LI_IPT; k++) l2[k] = h2[k] = wb + jj;
 #pragma unroll 1
     for (; jj < 64; jj++) {
         const int pmj = __shfl_sync(FULL, jj < 32 ? pmA : pmB, jj), tsj = __shfl_sync(FULL, jj < 32 ? tsA : tsB, jj);
-        if (!merge_step(pmj, tsj, st, en, lo, hi)) break;
+        if (!merge_step(pmj, tsj, s2, e2, l2, h2)) break;
     }
-    if (jj == 64) {  // some query runs past the window: its thread finishes it (four searches in lockstep)
-        unsigned act_lo = 0, act_hi = 0;
+    // Queries that run past the window (all 64 blocks start before their end): one at a time, the
+    // whole warp searches for it — 32-ary rounds over the key arrays.
+    if (jj == 64) {
 #pragma unroll
         for (int k = 0; k < LI_IPT; k++) {
-            act_hi |= hi[k] == w_end ? 1u << k : 0u;
-            act_lo |= lo[k] == w_end ? 1u << k : 0u;  // implies the same bit of act_hi
+            unsigned m = __ballot_sync(FULL, ((act >> k) & 1u) && h2[k] == w_end);
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const int x_st = __shfl_sync(FULL, s2[k], src), x_en = __shfl_sync(FULL, e2[k], src), x_lo = __shfl_sync(FULL, l2[k], src);
+                int nlo = x_lo;
+                if (x_lo == w_end) nlo = coop_lower_gt(T.pmaxKey, w_end, cend, x_st);  // its lower bound lies behind the window too
+                const int from = nlo > w_end ? nlo : w_end;
+                const int nhi = x_en == (int)0x80000000 ? from : coop_lower_gt(T.tStartKey, from, cend, x_en - 1);  // first tStart >= end
+                if (lane == src) {
+                    l2[k] = nlo;
+                    h2[k] = nhi;
+                }
+            }
         }
-        if (act_lo) {
-            const Int4x r = gallop4<false>(T.pmaxKey, cend, Int4x{{lo[0], lo[1], lo[2], lo[3]}}, Int4x{{st[0], st[1], st[2], st[3]}}, act_lo);
-#pragma unroll
-            for (int k = 0; k < LI_IPT; k++) lo[k] = r.v[k];
-        }
-        if (act_hi) {
-            Int4x base;
-#pragma unroll
-            for (int k = 0; k < LI_IPT; k++) base.v[k] = lo[k] > w_end ? lo[k] : w_end;
-            const Int4x r = gallop4<true>(T.tStartKey, cend, base, Int4x{{en[0], en[1], en[2], en[3]}}, act_hi);
-#pragma unroll
-            for (int k = 0; k < LI_IPT; k++)
-                if ((act_hi >> k) & 1u) hi[k] = r.v[k];
-        }
-        __syncwarp();
     }
+#pragma unroll
+    for (int k = 0; k < LI_IPT; k++)
+        if ((act >> k) & 1u) lo[k] = l2[k], hi[k] = h2[k];
+}
+
+// The first block of the 64-block window of a contig {first block, end block, sample offset, samples} for
+// a smallest start smin: groups of 32 blocks (every table up to 65,536 blocks): the group found in the
+// shared-memory samples (the next group follows it in the window), no probe of the key array; larger
+// groups: the window starts at the lower bound itself (one more search round trip).
+__device__ __forceinline__ int find_window(const TableView &T, const MergeSmem &S, const int4 cm, int smin) {
+    const int gi = coop_lower_gt(S.smp + cm.z, 0, cm.w, smin);
+    const int g_lo = cm.x + (gi << T.ey_shift);
+    if (T.ey_shift == 5) return g_lo;
+    return coop_lower_gt(T.pmaxKey, g_lo, gi < cm.w ? g_lo + (1 << T.ey_shift) - 1 : cm.y, smin);
+}
+
+// Candidate block ranges [lo, hi) of the lane's four queries.  hint >= 0: the tile is on one contig and
+// its window starts at block `hint` (write pass, from the count pass); hint == -1: several contigs (or
+// invalid ones); hint == -2: not known yet (count pass).  Returns the window's first block / -1.
+__device__ __forceinline__ int warp_search(const TableView &T, const MergeSmem &S, bool cm_smem, int hint, const int (&tc)[LI_IPT],
+                                           const int (&st)[LI_IPT], const int (&en)[LI_IPT], int (&lo)[LI_IPT], int (&hi)[LI_IPT]) {
+    const int tc0 = __shfl_sync(FULL, tc[0], 0);
+    bool same = hint >= 0;
+    if (hint == -2)
+        same = __all_sync(FULL, tc[0] == tc0 && tc[1] == tc0 && tc[2] == tc0 && tc[3] == tc0) && tc0 >= 0 && tc0 < T.ntc;
+    if (same) {
+        const int4 cm = cm_smem ? S.cmeta[tc0] : load_cmeta(T, tc0);
+        const int m01 = st[0] < st[1] ? st[0] : st[1], m23 = st[2] < st[3] ? st[2] : st[3];
+        const int smin = warp_min(m01 < m23 ? m01 : m23);
+        const int wb = hint >= 0 ? hint : find_window(T, S, cm, smin);
+        merge_window(T, wb, cm.y, smin, 0xFu, st, en, lo, hi);
+        return wb;
+    }
+    // Several contigs in the tile (contig boundaries, the batch tail, unsorted stretches): one round of
+    // the same merge per distinct contig, smallest id first; queries of other contigs sit the round out.
+    unsigned done = 0;
+#pragma unroll
+    for (int k = 0; k < LI_IPT; k++) lo[k] = hi[k] = 0;
+    for (;;) {
+        int mine = 0x7fffffff;
+#pragma unroll
+        for (int k = 0; k < LI_IPT; k++)
+            if (!((done >> k) & 1u) && tc[k] < mine) mine = tc[k];
+        const int c = warp_min(mine);
+        if (c == 0x7fffffff) break;  // warp-uniform
+        unsigned act = 0;
+        int smine = 0x7fffffff;
+#pragma unroll
+        for (int k = 0; k < LI_IPT; k++) {
+            if (!((done >> k) & 1u) && tc[k] == c) {
+                act |= 1u << k;
+                smine = st[k] < smine ? st[k] : smine;
+            }
+        }
+        done |= act;
+        if (c < 0 || c >= T.ntc) continue;  // unknown contig: no candidates (lo = hi = 0)
+        const int4 cm = cm_smem ? S.cmeta[c] : load_cmeta(T, c);
+        const int smin = warp_min(smine);
+        merge_window(T, find_window(T, S, cm, smin), cm.y, smin, act, st, en, lo, hi);
+    }
+    return -1;
 }
 
 // A warp's queries come through shared memory: lane 0 arms the stage's mbarrier and issues three
@@ -431,35 +383,28 @@ __global__ void __launch_bounds__(MG_TPB, 4) merge_count_kernel(const __grid_con
             if (lane < 12 && (pt + 1) * MG_QPW <= (long long)A.n)
                 prefetch_l2((lane < 4 ? A.tcid : lane < 8 ? A.start : A.end) + pt * MG_QPW + (lane & 3) * 32);
         }
-        const int tc0 = __shfl_sync(FULL, tc[0], 0);
-        const bool same = __all_sync(FULL, tc[0] == tc0 && tc[1] == tc0 && tc[2] == tc0 && tc[3] == tc0) && tc0 >= 0 && tc0 < T.ntc;
-        int wb = -1;
-        if (same) {
-            const int4 cm = cm_smem ? S.cmeta[tc0] : load_cmeta(T, tc0);
-            const int m01 = st[0] < st[1] ? st[0] : st[1], m23 = st[2] < st[3] ? st[2] : st[3];
-            const int smin = warp_min(m01 < m23 ? m01 : m23);
-            // The warp's window: 64 consecutive blocks that contain the lower bound of its smallest start.
-            // Groups of 32 blocks (every table up to 65,536 blocks): the group found in the shared-memory
-            // samples and the one behind it, no probe of the key array in between; larger groups: the
-            // window starts at the lower bound itself (one more search round trip).
-            const int gi = coop_lower_gt(S.smp + cm.z, 0, cm.w, smin);
-            const int g_lo = cm.x + (gi << T.ey_shift);
-            wb = g_lo;
-            if (T.ey_shift != 5) wb = coop_lower_gt(T.pmaxKey, g_lo, gi < cm.w ? g_lo + (1 << T.ey_shift) - 1 : cm.y, smin);
-            merge_window(T, wb, cm.y, smin, st, en, lo, hi);
-        } else {
-            const LoHi4 r = search_each(A, q0);  // several contigs in the warp (or the batch tail)
-#pragma unroll
-            for (int k = 0; k < LI_IPT; k++) lo[k] = r.lo[k], hi[k] = r.hi[k];
-            converge(A);
-        }
+        const int wb = warp_search(T, S, cm_smem, -2, tc, st, en, lo, hi);
         uint32_t tsum = 0;
 #pragma unroll
         for (int k = 0; k < LI_IPT; k++) {
             const int cnt = hi[k] > lo[k] ? hi[k] - lo[k] : 0;
             tsum += (uint32_t)cnt;
             unm_acc += (cnt == 0 && (full || q0 + k < A.n)) ? 1u : 0u;
+#ifdef MG_DEBUG_COUNTS
+            if (M.dbg && q0 + k < A.n) {
+                M.dbg[4 * (size_t)(q0 + k)] = lo[k];
+                M.dbg[4 * (size_t)(q0 + k) + 1] = hi[k];
+                M.dbg[4 * (size_t)(q0 + k) + 2] = wb;
+                M.dbg[4 * (size_t)(q0 + k) + 3] = (int)tsum;
+            }
+#endif
         }
+#ifdef MG_DEBUG_COUNTS
+        {
+            const unsigned am = __activemask();
+            if (M.dbg && am != FULL) printf("tile %d lane %d: active mask %08x in front of the tile total\n", tile, lane, am);
+        }
+#endif
         // Shuffles, not redux.sync: behind the divergent per-thread search the warp can still be split here
         // (ptxas 12.9 takes it for converged and even turns converge_warp into a NOP in this kernel), a
         // SHFL then takes its out-of-line WARPSYNC.COLLECTIVE path, whereas REDUX.SUM silently sums the
@@ -533,7 +478,7 @@ __global__ void __launch_bounds__(MG_TPB, MG_WRITE_CTAS) merge_write_kernel(cons
     MergeSmem &S = *reinterpret_cast<MergeSmem *>(li_smem_raw);
     if (__ldg(A.sorted_flag) == 0u) return;
     const TableView &T = A.T;
-    merge_tables(T, S, false);
+    merge_tables(T, S, true);
     const int lane = lane_id(), w = warp_id();
     const bool cm_smem = T.ntc <= LI_CM_CAP;
     const int nwarps = (int)gridDim.x * MG_NW;
@@ -563,18 +508,7 @@ __global__ void __launch_bounds__(MG_TPB, MG_WRITE_CTAS) merge_write_kernel(cons
                 sb4.w = q0 + 3 < A.n ? A.strand[q0 + 3] : 0;
             }
         }
-        if (wb >= 0) {  // warp-uniform: one contig
-            const int tc0 = __shfl_sync(FULL, tc[0], 0);
-            const int4 cm = cm_smem ? S.cmeta[tc0] : load_cmeta(T, tc0);
-            const int m01 = st[0] < st[1] ? st[0] : st[1], m23 = st[2] < st[3] ? st[2] : st[3];
-            const int smin = warp_min(m01 < m23 ? m01 : m23);
-            merge_window(T, wb, cm.y, smin, st, en, lo, hi);
-        } else {
-            const LoHi4 r = search_each(A, q0);
-#pragma unroll
-            for (int k = 0; k < LI_IPT; k++) lo[k] = r.lo[k], hi[k] = r.hi[k];
-            converge(A);
-        }
+        warp_search(T, S, cm_smem, wb < 0 ? -1 : wb, tc, st, en, lo, hi);
         // Hits, and the row of the first candidate — computed without branches for every query (four
         // independent block loads in flight); it is only stored for single-hit queries.
         Block bk[LI_IPT];
@@ -617,14 +551,17 @@ __global__ void __launch_bounds__(MG_TPB, MG_WRITE_CTAS) merge_write_kernel(cons
             pos += (uint32_t)cnt[k];
         }
         if (__any_sync(FULL, multi != 0u)) {
-            unsigned wide = 0;  // list full: queries for the whole warp
+            // Two candidates (an interval across one gap): by the thread, straight-line.  More: onto the list for
+            // expand_wide_kernel — or, list full, by the whole warp one query at a time.  (No per-thread loops
+            // in here: see merge_window.)
+            unsigned wide = 0;
             uint64_t p = pos64;
 #pragma unroll
             for (int k = 0; k < LI_IPT; k++) {
                 if ((multi >> k) & 1u) {
-                    // up to MG_SMALL candidates: by the thread, unless their rows are neither in ascending
-                    // nor in descending qStart order — those need a sort and go with the large ones
-                    if (!(cnt[k] <= MG_SMALL && expand_small(A, q0 + k, lo[k], cnt[k], p))) {
+                    if (cnt[k] == 2) {
+                        expand_pair(A, q0 + k, lo[k], st[k], en[k], sbk[k], p);
+                    } else {
                         const unsigned e = atomicAdd(W.count, 1u);
                         if (e < W.cap) W.ent[e] = make_uint4(q0 + k, (unsigned)lo[k], (unsigned)cnt[k], (uint32_t)p);
                         else wide |= 1u << k;
@@ -632,10 +569,9 @@ __global__ void __launch_bounds__(MG_TPB, MG_WRITE_CTAS) merge_write_kernel(cons
                 }
                 p += (uint64_t)cnt[k];
             }
-            converge(A);
             if (__any_sync(FULL, wide != 0u)) {
                 p = pos64;
-#pragma unroll 1
+#pragma unroll
                 for (int k = 0; k < LI_IPT; k++) {
                     unsigned m = __ballot_sync(FULL, (wide >> k) & 1u);
                     while (m) {
@@ -645,7 +581,6 @@ __global__ void __launch_bounds__(MG_TPB, MG_WRITE_CTAS) merge_write_kernel(cons
                         const int qlo = __shfl_sync(FULL, lo[k], src), qcnt = __shfl_sync(FULL, cnt[k], src);
                         const uint64_t qpos = __shfl_sync(FULL, p, src);
                         expand_wide(A, sink, q, qlo, qcnt, qpos, S.xscr[w], gxs);
-                        converge(A);
                     }
                     p += (uint64_t)cnt[k];
                 }

@@ -348,7 +348,24 @@ int launch_lift_intervals(swo_ctx *c, Device &d, size_t n, const int32_t *tcid, 
             CK(c, d.wide.reserve((size_t)W.cap * sizeof(uint4)));
             W.ent = d.wide.as<uint4>();
             W.count = reinterpret_cast<unsigned *>(d.scratch.as<char>() + 4);
+#ifdef MG_DEBUG_COUNTS
+            M.dbg = nullptr;
+            if (getenv("SWO_DUMP_COUNTS")) cudaMalloc(&M.dbg, n * 16);
+#endif
             merge_count_kernel<<<grid_c, MG_TPB, smem, st>>>(Aw, M);
+#ifdef MG_DEBUG_COUNTS
+            if (M.dbg) {
+                cudaStreamSynchronize(st);
+                std::vector<int32_t> h(n * 4);
+                std::vector<uint32_t> tot(ntw);
+                cudaMemcpy(h.data(), M.dbg, n * 16, cudaMemcpyDeviceToHost);
+                cudaMemcpy(tot.data(), M.total, (size_t)ntw * 4, cudaMemcpyDeviceToHost);
+                FILE *f = fopen(getenv("SWO_DUMP_COUNTS"), "wb");
+                if (f) { fwrite(h.data(), 4, h.size(), f); fwrite(tot.data(), 4, tot.size(), f); fclose(f); }
+                cudaFree(M.dbg);
+                M.dbg = nullptr;
+            }
+#endif
             scan_tiles_kernel1<<<nsum, 256, 0, st>>>(flag, M, ntw);
             scan_tiles_kernel2<<<1, 1024, 0, st>>>(flag, M, nsum, totals, row_offset + n);
             void *wargs[] = {(void *)&Aw, (void *)&M, (void *)&W};

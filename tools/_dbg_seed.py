@@ -44,3 +44,12 @@ if t:
     i0 = cf.tcid(names[tc[q][0]]) if tc[q][0] >= 0 else -1
     ts, te, qs, qc, inv = cf.blocks(int(tc[q][0]))
     print("contig blocks", len(ts), "tStart", ts[:70].tolist(), "tEnd", te[:70].tolist())
+if os.environ.get("SWO_DUMP_COUNTS") and os.path.exists(os.environ["SWO_DUMP_COUNTS"]):
+    raw = np.fromfile(os.environ["SWO_DUMP_COUNTS"], dtype=np.int32)
+    dbg, tot = raw[:4 * n].reshape(n, 4), raw[4 * n:].view(np.uint32)
+    cnt = np.maximum(dbg[:, 1] - dbg[:, 0], 0)
+    per_tile_ref = np.add.reduceat(fr, np.arange(0, n, 128))
+    per_tile_cnt = np.add.reduceat(cnt, np.arange(0, n, 128))
+    print("tiles where stored total != ref:", [(t, int(tot[t]), int(per_tile_ref[t]), int(per_tile_cnt[t])) for t in range(len(tot)) if tot[t] != per_tile_ref[t]])
+    badq = np.flatnonzero(cnt != fr)
+    print("queries where count-pass cnt != ref:", [(int(i), dbg[i].tolist(), int(fr[i])) for i in badq[:10]])
