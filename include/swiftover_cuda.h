@@ -174,7 +174,9 @@ int swo_lift_bed_text(swo_ctx *ctx, const char *in, size_t in_len, swo_text_out 
 int swo_text_num_segments(const swo_ctx *ctx);
 int swo_text_segment(const swo_ctx *ctx, int which, int i, const char **ptr, size_t *len);
 
-/* Same kernels on device-resident text (kernel-only measurement).  d_in must be
+/* Same kernels on device-resident text (kernel-only measurement; launches of one ctx that use
+ * different streams are ordered one after the other on the device: they share per-device scratch).
+ * d_in must be
  * 16-byte aligned.  d_sizes[0]=lifted bytes, [1]=unmatched bytes, [2]=records,
  * [3]=rows, [4]=unmatched records, [5]=error (0 = every line parsed, else
  * UINT64_MAX - byte offset of the first malformed line) — a DEVICE array of 6

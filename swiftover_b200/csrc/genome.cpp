@@ -55,7 +55,7 @@ struct Packer {
             const unsigned char c = (unsigned char)s[i];
             if (c == ' ' || (c >= 9 && c <= 13)) continue;
             if (cur_len >= cap) {
-                err = "FASTA sequence " + cur_name + " is longer than the chain's size for it";
+                err = "FASTA sequence " + cur_name + " changed between the two passes over the file";
                 return false;
             }
             const int64_t p = g.off[cur] + cur_len++;
@@ -126,11 +126,10 @@ void sort_runs(GenomeStore &g) {
 
 }  // namespace
 
-bool genome_from_fasta_text(std::string_view text, const std::vector<std::string> &qnames,
-                            const std::vector<int64_t> &qsizes, GenomeStore &out, std::string &err) {
-    layout(qnames, qsizes, out);
-    Packer pk{qnames, out, {}, -1, {}, 0, 0, -1, 0, 0};
-    for (size_t i = 0; i < qnames.size(); i++) pk.qid.emplace(qnames[i], (int)i);
+namespace {
+
+// stream the FASTA text through a packer (header lines start records, everything else is bases)
+bool feed_text(std::string_view text, Packer &pk, std::string &err) {
     size_t i = 0;
     while (i < text.size()) {
         size_t e = text.find('\n', i);
@@ -145,20 +144,15 @@ bool genome_from_fasta_text(std::string_view text, const std::vector<std::string
         i = e + 1;
     }
     pk.end_record();
-    sort_runs(out);
     return true;
 }
 
-bool genome_from_fasta(const char *path, const std::vector<std::string> &qnames, const std::vector<int64_t> &qsizes,
-                       GenomeStore &out, std::string &err) {
+bool feed_file(const char *path, Packer &pk, std::string &err) {
     FILE *f = fopen(path, "rb");
     if (!f) {
         err = std::string("Genome FASTA does not exist: ") + path;
         return false;
     }
-    layout(qnames, qsizes, out);
-    Packer pk{qnames, out, {}, -1, {}, 0, 0, -1, 0, 0};
-    for (size_t i = 0; i < qnames.size(); i++) pk.qid.emplace(qnames[i], (int)i);
     std::vector<char> buf(1 << 22);
     std::string header;  // a '>' line may straddle two reads
     bool in_header = false, at_line_start = true, ok = true;
@@ -202,8 +196,41 @@ bool genome_from_fasta(const char *path, const std::vector<std::string> &qnames,
         pk.begin_record(std::string_view(header).substr(0, b));
     }
     pk.end_record();
+    return true;
+}
+
+// Two passes over the source: the first only measures every record (all records "ignored"), so that
+// each destination contig's slot is sized from the FASTA itself — the reference fetches by FASTA
+// coordinates whatever the chain header says about the contig's size, and only warns (and leaves the
+// ##contig line out) when the two lengths differ (vcf.d:83-86); the second packs.
+template <typename Feed>
+bool build(Feed feed, const std::vector<std::string> &qnames, GenomeStore &out, std::string &err) {
+    GenomeStore probe;
+    Packer measure{qnames, probe, {}, -1, {}, 0, 0, -1, 0, 0};
+    if (!feed(measure, err)) return false;
+    std::vector<int64_t> sizes(qnames.size(), 0);
+    for (size_t i = 0; i < qnames.size(); i++) {
+        auto it = probe.fasta_len.find(qnames[i]);
+        if (it != probe.fasta_len.end()) sizes[i] = it->second;
+    }
+    layout(qnames, sizes, out);
+    Packer pk{qnames, out, {}, -1, {}, 0, 0, -1, 0, 0};
+    for (size_t i = 0; i < qnames.size(); i++) pk.qid.emplace(qnames[i], (int)i);
+    if (!feed(pk, err)) return false;
     sort_runs(out);
     return true;
+}
+
+}  // namespace
+
+bool genome_from_fasta_text(std::string_view text, const std::vector<std::string> &qnames, const std::vector<int64_t> &,
+                            GenomeStore &out, std::string &err) {
+    return build([&](Packer &pk, std::string &e) { return feed_text(text, pk, e); }, qnames, out, err);
+}
+
+bool genome_from_fasta(const char *path, const std::vector<std::string> &qnames, const std::vector<int64_t> &,
+                       GenomeStore &out, std::string &err) {
+    return build([&](Packer &pk, std::string &e) { return feed_file(path, pk, e); }, qnames, out, err);
 }
 
 }  // namespace swo

@@ -35,8 +35,9 @@ struct GenomeStore {
     }
 };
 
-// qnames/qsizes: destination contigs of the chain (id order) and their chain sizes (used to
-// reserve the layout before the FASTA is scanned; a FASTA sequence longer than that is an error).
+// qnames: destination contigs of the chain (id order).  The FASTA is read twice: once to measure its
+// records, once to pack them — a contig's slot is as long as its FASTA record, whatever size the chain
+// header states (the reference only warns on a mismatch, vcf.d:83-86).  qsizes is not used any more.
 bool genome_from_fasta(const char *path, const std::vector<std::string> &qnames, const std::vector<int64_t> &qsizes,
                        GenomeStore &out, std::string &err);
 bool genome_from_fasta_text(std::string_view text, const std::vector<std::string> &qnames,

@@ -100,6 +100,11 @@ struct Device {
     int g_n = 0;
     // scratch for the look-back chains
     DevBuf scratch, gscr, wide;
+    // The scratch (ticket, look-back descriptors, tile totals, sorted flag) is per device, not per call: a launch
+    // that uses it first waits for the previous one on ANY stream to be done with it (callers of the *_dev entry
+    // points may use streams of their own).
+    cudaEvent_t ev_scratch = nullptr;
+    bool scratch_used = false;
     // binary path buffers
     DevBuf b_in, b_off, b_rows, b_thick, b_tot;
     // text path: per-slot chunk buffers
@@ -275,6 +280,7 @@ int launch_lift_intervals(swo_ctx *c, Device &d, size_t n, const int32_t *tcid, 
     const size_t w_window = (w_total + (size_t)ntw * 4 + 15) & ~(size_t)15, w_sum = (w_window + (size_t)ntw * 4 + 15) & ~(size_t)15;
     const size_t scratch_bytes = w_sum + (size_t)(nsum + 1) * 8;
     const size_t zero_bytes = w_total;  // header + tile descriptors; the sorted variant's arrays are written before they are read
+    if (d.scratch_used) CK(c, cudaStreamWaitEvent(st, d.ev_scratch, 0));
     CK(c, d.scratch.reserve((scratch_bytes + 3) & ~(size_t)3));
     if (int rc = zero_async(c, d.scratch.p, zero_bytes, totals, 16, st)) return rc;
     if (n == 0) {
@@ -388,6 +394,8 @@ int launch_lift_intervals(swo_ctx *c, Device &d, size_t n, const int32_t *tcid, 
         c->launches++;
     }
     CK(c, cudaGetLastError());
+    CK(c, cudaEventRecord(d.ev_scratch, st));
+    d.scratch_used = true;
     return SWO_OK;
 }
 
@@ -399,6 +407,7 @@ int launch_lift_text(swo_ctx *c, Device &d, const char *d_in, size_t in_len, cha
     if (!tile_bytes) tile_bytes = c->tile_bytes;
     const int ntiles = (int)((in_len + tile_bytes - 1) / tile_bytes);
     const size_t scratch_bytes = 16 + (size_t)ntiles * 16;
+    if (d.scratch_used) CK(c, cudaStreamWaitEvent(st, d.ev_scratch, 0));
     CK(c, d.scratch.reserve((scratch_bytes + 3) & ~(size_t)3));
     if (int rc = zero_async(c, d.scratch.p, scratch_bytes, d_sizes, 48, st)) return rc;
     if (in_len == 0) return SWO_OK;
@@ -438,6 +447,8 @@ int launch_lift_text(swo_ctx *c, Device &d, const char *d_in, size_t in_len, cha
     lift_bed_text_kernel<<<grid, TX_TPB, smem, st>>>(A);
     c->launches++;
     CK(c, cudaGetLastError());
+    CK(c, cudaEventRecord(d.ev_scratch, st));
+    d.scratch_used = true;
     return SWO_OK;
 }
 
@@ -651,6 +662,7 @@ int swo_create(swo_ctx **out, const int *devices, int ndev) {
             cudaStreamCreateWithFlags(&d.s_d2h2, cudaStreamNonBlocking) != cudaSuccess)
             return SWO_E_CUDA;
         for (int s = 0; s < N_SLOTS; s++) {
+            if (!d.ev_scratch) cudaEventCreateWithFlags(&d.ev_scratch, cudaEventDisableTiming);
             cudaEventCreateWithFlags(&d.ev_h2d[s], cudaEventDisableTiming);
             cudaEventCreateWithFlags(&d.ev_comp[s], cudaEventDisableTiming);
             cudaEventCreateWithFlags(&d.ev_d2h[s], cudaEventDisableTiming);
@@ -675,6 +687,7 @@ void swo_destroy(swo_ctx *c) {
         for (DevBuf *b : {&d.blk, &d.tkey, &d.pkey, &d.toff, &d.cmeta, &d.ey, &d.thash, &d.tchars, &d.tnoff, &d.qoff, &d.qchars, &d.g_packed,
                           &d.g_off, &d.g_len, &d.g_lower, &d.g_chunk, &d.g_estart, &d.g_elen, &d.g_ebyte, &d.scratch, &d.gscr, &d.wide, &d.b_in, &d.b_off, &d.b_rows, &d.b_thick, &d.b_tot})
             b->release();
+        if (d.ev_scratch) cudaEventDestroy(d.ev_scratch);
         for (int s = 0; s < N_SLOTS; s++) {
             d.t_in[s].release();
             d.t_out[s].release();
