@@ -57,12 +57,37 @@ __device__ __forceinline__ char genome_base(const GenomeView &A, int64_t g) {
     return base;
 }
 
-__global__ void __launch_bounds__(256) lift_vcf_points_kernel(const VcfArgs A) {
+// liftDirectly for one position with the upper search levels and the per-contig table in shared
+// memory (point_hit of lift_core.cuh walks the global copies: ~10 dependent L2 round trips per record,
+// which made this kernel L2-throughput bound).  Returns the block index or -1.
+__device__ __forceinline__ int point_hit_smem(const TableView &T, const int2 *ey, const int4 *cm_s, int tcid, int c) {
+    if (tcid < 0 || tcid >= T.ntc) return -1;
+    const int4 cm = cm_s ? cm_s[tcid] : load_cmeta(T, tcid);
+    int j = lower_gt_ey(T, ey, cm, c);
+    for (; j < cm.y; j++) {
+        if (__ldg(T.tStartKey + j) > c) return -1;
+        if (T.disjoint || __ldg(&T.blk[j].tEnd) > c) return j;
+    }
+    return -1;
+}
+
+constexpr int VCF_CM_CAP = 128;
+
+__global__ void __launch_bounds__(256) lift_vcf_points_kernel(const __grid_constant__ VcfArgs A) {
+    __shared__ int2 s_ey[ChainTable::EY_CAP];
+    __shared__ int4 s_cm[VCF_CM_CAP];
+    for (int i = threadIdx.x; i < A.T.ey_n; i += 256) s_ey[i] = __ldg(A.T.ey + i);
+    const bool cm_smem = A.T.ntc <= VCF_CM_CAP;
+    if (cm_smem)
+        for (int i = threadIdx.x; i < A.T.ntc; i += 256) s_cm[i] = __ldg(A.T.cmeta + i);
+    __syncthreads();
+    const bool plain = !A.G.lower && !A.G.exc_n;  // an ACGT-only, upper-case genome: 16 bases per 32-bit word
+    const uint32_t *const gw = reinterpret_cast<const uint32_t *>(A.G.packed);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < A.n; i += gridDim.x * blockDim.x) {
         const int c0 = A.pos[i];
         const int rl = A.reflen[i];
         const uint64_t ro = A.ref_off[i];
-        const int j = point_hit(A.T, A.T.ey, A.tcid[i], c0);
+        const int j = point_hit_smem(A.T, s_ey, cm_smem ? s_cm : nullptr, A.tcid[i], c0);
         if (j < 0) {  // vcf.d:134-137: record goes to the unmatched file unchanged
             A.out_qcid[i] = -1;
             A.out_pos[i] = c0;
@@ -79,11 +104,24 @@ __global__ void __launch_bounds__(256) lift_vcf_points_kernel(const VcfArgs A) {
         if (c >= 0 && (int64_t)c < L) m = (int64_t)c + rl > L ? (int)(L - c) : rl;
         bool diff = m != rl;
         const int64_t g0 = q < A.G.g_n ? A.G.g_off[q] + c : 0;
-        for (int k = 0; k < m; k++) {
-            const int64_t g = g0 + k;
-            const char base = genome_base(A.G, g);
-            A.out_ref[ro + k] = base;
-            diff |= base != A.ref[ro + k];  // vcf.d:144 byte-exact compare
+        if (plain) {
+            for (int k0 = 0; k0 < m; k0 += 16) {  // one or two aligned words cover 16 bases from g0 + k0
+                const int64_t g = g0 + k0;
+                const uint32_t w0 = __ldg(gw + (g >> 4)), w1 = (g & 15) ? __ldg(gw + (g >> 4) + 1) : 0u;
+                uint32_t bits = __funnelshift_r(w0, w1, (unsigned)(g & 15) * 2u);
+                const int cnt = m - k0 < 16 ? m - k0 : 16;
+                for (int k = 0; k < cnt; k++, bits >>= 2) {
+                    const char base = (char)(0x54474341u >> ((bits & 3u) * 8u));  // "ACGT"
+                    A.out_ref[ro + k0 + k] = base;
+                    diff |= base != A.ref[ro + k0 + k];  // vcf.d:144 byte-exact compare
+                }
+            }
+        } else {
+            for (int k = 0; k < m; k++) {
+                const char base = genome_base(A.G, g0 + k);
+                A.out_ref[ro + k] = base;
+                diff |= base != A.ref[ro + k];  // vcf.d:144 byte-exact compare
+            }
         }
         A.out_qcid[i] = q;
         A.out_pos[i] = c;
