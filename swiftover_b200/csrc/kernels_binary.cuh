@@ -33,6 +33,12 @@
 
 namespace swo {
 
+#ifndef LI_LOCKSTEP
+#define LI_LOCKSTEP 1  // unsorted quadruples: the four searches of a thread in lockstep (lower_gt_ey_n)
+#endif
+#ifndef LI_MIN_CTAS
+#define LI_MIN_CTAS 4
+#endif
 constexpr int LI_TPB = 256;
 constexpr int LI_IPT = 4;
 constexpr int LI_TILE = LI_TPB * LI_IPT;
@@ -63,6 +69,12 @@ struct LiftArgs {
     const uint32_t *sorted_flag;  // written by sample_sorted_kernel: which kernel variant does the work
     unsigned full_mask;           // 0xffffffff, as a run-time value: see converge()
     unsigned long long *gscr;     // sorted variant: per-warp sort scratch in global memory (kernels_merge.cuh)
+    // multi-hit queries left for expand_wide_kernel (kernels_merge.cuh), two uint4 per entry:
+    // {query, first candidate block, candidates, row position} {start, end, strand byte, tcid}
+    // and a third one in batches with thick columns: {lifted thickStart, thickEnd, has, -}
+    uint4 *wide_ent;              // null: expand inside the kernel
+    unsigned *wide_count;         // appended so far (may run past wide_cap: those were expanded on the spot)
+    unsigned wide_cap;
 };
 
 // see converge_warp (device_util.cuh)
@@ -227,6 +239,288 @@ __device__ __noinline__ void expand_query_coop(const LiftArgs &A, const RowSink 
 }
 
 
+// A multi-hit query on a target-disjoint table, by one warp and without sorting.  Along the candidate
+// blocks (tStart order) the rows of one chain come in qStart order already ('+' chains) or exactly
+// reversed ('-' chains): the candidates form a few monotone RUNS, one per chain piece the interval
+// crosses.  Pass 1 cuts the candidates into runs (run_continues) and leaves {first candidate, first and
+// last destination coordinate, invert} per run in the warp's scratch; lane j then owns run j and adds up
+// the sizes (and inverted rows) of the runs that lie entirely below its own; pass 2 gives every candidate
+// its output position = run offset + place inside the run, the cumulative strand byte (bed.d:173) from
+// the inverted rows in front of it, and stores the row (16 bytes per lane, contiguous inside a run).
+// Runs that overlap or touch in the destination, or more than 32 of them (fragmented regions, many small
+// chains): up to 32 candidates (R == 1) every candidate counts the rows in front of it — smaller
+// qStart, or equal and an earlier candidate: the order of bed.d:156-157 as defined in
+// oracle/swo_oracle.h — with shuffles; otherwise the function returns false, nothing useful written,
+// and the caller does the same count through its scratch (expand_warp_allpairs).
+// Every lane calls it with the same arguments; all loops have warp-uniform trip counts.
+// `runs`: 128 ints of per-warp shared memory.
+// Does candidate c continue the run of candidate c - 1?  Same destination contig and direction (pm == meta), and
+// its piece starts where the previous one ended, give or take a gap of the chain: pv is the previous row's end
+// ('+') or start ('-').  A nested chain inside another chain's gap lands somewhere else and starts a run of its
+// own.  (Only a heuristic for where to cut: whether the cut runs can be placed is checked exactly below.)
+constexpr unsigned RUN_SLACK = 65536;
+__device__ __forceinline__ bool run_continues(int c, int pm, int pv, int meta, const RowCore &row) {
+    const int g = row.inv > 0 ? row.s - pv : pv - row.e;
+    return c > 0 && pm == meta && (unsigned)g <= RUN_SLACK;
+}
+
+// R > 0: the query has at most 32 R candidates and their rows stay in registers between the passes (one
+// round trip to the block table, all loads in flight together); R == 0: any number, blocks loaded in both passes.
+template <bool THICK, int R>
+__device__ __forceinline__ bool expand_warp_runs_t(const LiftArgs &A, const RowSink &K, const Thick &th, uint32_t q, int lo, int cnt,
+                                                   uint64_t rowbase, int start, int end, unsigned char orig, int *runs, const Block &pre) {
+    const TableView &T = A.T;
+    const int lane = lane_id();
+    const unsigned le_mask = 0xffffffffu >> (31 - lane);
+    const int rounds = (cnt + 31) >> 5;
+    RowCore rows[R > 0 ? R : 1];
+    if (R > 0) {
+#pragma unroll
+        for (int i = 0; i < R; i++) {
+            const int c = 32 * i + lane;
+            rows[i] = make_row(i == 0 ? pre : load_block(T, lo + (c < cnt ? c : 0)), start, end);
+        }
+    }
+    auto fetch = [&](int i) -> RowCore {
+        if (R > 0) return rows[R > 0 ? i : 0];
+        const int c = 32 * i + lane;
+        return make_row(i == 0 ? pre : load_block(T, lo + (c < cnt ? c : 0)), start, end);
+    };
+    int nruns = 0, cm = 0, cv = 0;
+#pragma unroll
+    for (int i = 0; i < (R > 0 ? R : rounds); i++) {
+        if (R > 0 && i >= rounds) break;
+        const int c = 32 * i + lane;
+        const bool valid = c < cnt;
+        const RowCore row = fetch(i);
+        const int meta = (row.qcid << 1) | (row.inv < 0 ? 1 : 0), send = row.inv > 0 ? row.e : row.s;
+        int pm = __shfl_up_sync(FULL, meta, 1), pv = __shfl_up_sync(FULL, send, 1);
+        if (lane == 0) pm = cm, pv = cv;
+        const bool brk = valid && !run_continues(c, pm, pv, meta, row);
+        const unsigned bm = __ballot_sync(FULL, brk);
+        const int r = nruns + __popc(bm & le_mask) - 1;  // run of this candidate
+        if (brk && r < 32) {
+            runs[4 * r] = c;
+            runs[4 * r + 1] = row.inv > 0 ? row.s : row.e;
+            runs[4 * r + 3] = row.inv;
+        }
+        if (brk && c > 0 && r <= 32) runs[4 * (r - 1) + 2] = pv;  // the previous run ended just before
+        if (valid && c == cnt - 1 && r < 32) runs[4 * r + 2] = send;
+        nruns += __popc(bm);
+        cm = __shfl_sync(FULL, meta, 31);
+        cv = __shfl_sync(FULL, send, 31);
+    }
+    __syncwarp();
+    // lane j = run j
+    const bool have = lane < nruns && nruns <= 32;
+    const int r_first = have ? runs[4 * lane] : 0, r_k0 = have ? runs[4 * lane + 1] : 0, r_k1 = have ? runs[4 * lane + 2] : 0;
+    const int r_inv = have ? runs[4 * lane + 3] : 1;
+    const int r_size = have ? (lane + 1 < nruns ? runs[4 * (lane + 1)] : cnt) - r_first : 0;
+    int off = 0, negoff = 0;
+    bool sort = nruns > 32;
+    if (nruns > 1 && !sort) {  // warp-uniform
+        const int mn = r_inv > 0 ? r_k0 : r_k1, mx = r_inv > 0 ? r_k1 : r_k0;
+        bool bad = false;
+        for (int i = 0; i < nruns; i++) {
+            const int si = __shfl_sync(FULL, r_size, i), mni = __shfl_sync(FULL, mn, i), mxi = __shfl_sync(FULL, mx, i);
+            const int invi = __shfl_sync(FULL, r_inv, i);
+            if (have && i != lane) {
+                if (mxi < mn) {
+                    off += si;
+                    negoff += invi < 0 ? si : 0;
+                } else if (!(mx < mni)) {
+                    bad = true;
+                }
+            }
+        }
+        sort = __any_sync(FULL, bad);
+    }
+    __syncwarp();  // the scratch may be rewritten by the next call
+    if (sort) {
+        // Interleaved runs (a nested chain inside the gap of another: A A B A A): with the rows in registers every
+        // candidate counts the rows in front of it — smaller qStart, or equal and an earlier candidate.
+        if (R != 1) return false;  // (through the scratch the count costs the same and needs no registers)
+        int rank[R > 0 ? R : 1], negs[R > 0 ? R : 1];
+        unsigned invm[R > 0 ? R : 1];
+#pragma unroll
+        for (int ri = 0; ri < R; ri++) {
+            const bool neg = 32 * ri + lane < cnt && rows[ri].inv < 0;
+            rank[ri] = 0;
+            negs[ri] = neg ? 1 : 0;
+            invm[ri] = __ballot_sync(FULL, neg);
+        }
+#pragma unroll
+        for (int rj = 0; rj < R; rj++) {
+            const int lim = min(32, cnt - 32 * rj);
+            for (int l = 0; l < lim; l++) {  // warp-uniform
+                const int k = __shfl_sync(FULL, rows[rj].key, l), idx = 32 * rj + l, ng = (int)((invm[rj] >> l) & 1u);
+#pragma unroll
+                for (int ri = 0; ri < R; ri++) {
+                    const int before = (k < rows[ri].key || (k == rows[ri].key && idx < 32 * ri + lane)) ? 1 : 0;
+                    rank[ri] += before;
+                    negs[ri] += before & ng;
+                }
+            }
+        }
+        int inv_first = 1;
+#pragma unroll
+        for (int ri = 0; ri < R; ri++) {
+            const unsigned m = __ballot_sync(FULL, 32 * ri + lane < cnt && rank[ri] == 0);
+            const int iv = __shfl_sync(FULL, rows[ri].inv, m ? __ffs(m) - 1 : 0);
+            if (m) inv_first = iv;
+        }
+#pragma unroll
+        for (int ri = 0; ri < R; ri++) {
+            const uint64_t pos = rowbase + (uint64_t)rank[ri];
+            if (32 * ri + lane < cnt && pos < K.cap) {
+                const RowCore &row = rows[ri];
+                const unsigned char sb = A.strand ? strand_at_rank(orig, inv_first, rank[ri], negs[ri]) : 0;
+                *reinterpret_cast<int4 *>(K.rows + pos) = make_int4(row.qcid | ((int)sb << 16), row.s, row.e, (int)q);
+                if (THICK) {
+                    swo_thick tk;
+                    thick_clamp(th, row.s, row.e, tk.thick_start, tk.thick_end);
+                    K.thick[pos] = tk;
+                }
+            }
+        }
+        return true;
+    }
+    const unsigned fm = __ballot_sync(FULL, have && off == 0);
+    const int inv_first = __shfl_sync(FULL, r_inv, __ffs(fm) - 1);
+    auto store = [&](const RowCore &row, int rank, int negs_le) {
+        const uint64_t pos = rowbase + (uint64_t)rank;
+        if (pos < K.cap) {
+            const unsigned char sb = A.strand ? strand_at_rank(orig, inv_first, rank, negs_le) : 0;
+            *reinterpret_cast<int4 *>(K.rows + pos) = make_int4(row.qcid | ((int)sb << 16), row.s, row.e, (int)q);
+            if (THICK) {
+                swo_thick tk;
+                thick_clamp(th, row.s, row.e, tk.thick_start, tk.thick_end);
+                K.thick[pos] = tk;
+            }
+        }
+    };
+    if (nruns == 1) {  // one chain piece (the usual case): candidate order, or exactly reversed
+#pragma unroll
+        for (int i = 0; i < (R > 0 ? R : rounds); i++) {
+            if (R > 0 && i >= rounds) break;
+            const int c = 32 * i + lane;
+            const RowCore row = fetch(i);
+            const int t = inv_first > 0 ? c : cnt - 1 - c;
+            if (c < cnt) store(row, t, inv_first < 0 ? t + 1 : 0);
+        }
+        return true;
+    }
+    nruns = 0;
+#pragma unroll
+    for (int i = 0; i < (R > 0 ? R : rounds); i++) {
+        if (R > 0 && i >= rounds) break;
+        const int c = 32 * i + lane;
+        const bool valid = c < cnt;
+        const RowCore row = fetch(i);
+        const int meta = (row.qcid << 1) | (row.inv < 0 ? 1 : 0), send = row.inv > 0 ? row.e : row.s;
+        int pm = __shfl_up_sync(FULL, meta, 1), pv = __shfl_up_sync(FULL, send, 1);
+        if (lane == 0) pm = cm, pv = cv;
+        const bool brk = valid && !run_continues(c, pm, pv, meta, row);
+        const unsigned bm = __ballot_sync(FULL, brk);
+        const int r = (nruns + __popc(bm & le_mask) - 1) & 31;
+        const int first = __shfl_sync(FULL, r_first, r), sz = __shfl_sync(FULL, r_size, r);
+        const int o = __shfl_sync(FULL, off, r), no = __shfl_sync(FULL, negoff, r);
+        const int t = row.inv > 0 ? c - first : first + sz - 1 - c;
+        if (valid) store(row, o + t, no + (row.inv < 0 ? t + 1 : 0));
+        nruns += __popc(bm);
+        cm = __shfl_sync(FULL, meta, 31);
+        cv = __shfl_sync(FULL, send, 31);
+    }
+    return true;
+}
+// `pre`: the lane's block of the first round, lo + min(lane, cnt - 1), loaded by the caller (expand_wide_kernel
+// loads it while the previous query is expanded, which takes the table's latency out of the chain).
+template <bool THICK>
+__device__ __forceinline__ bool expand_warp_runs(const LiftArgs &A, const RowSink &K, const Thick &th, uint32_t q, int lo, int cnt,
+                                                 uint64_t rowbase, int start, int end, unsigned char orig, int *runs, const Block &pre) {
+    if (cnt <= 32) return expand_warp_runs_t<THICK, 1>(A, K, th, q, lo, cnt, rowbase, start, end, orig, runs, pre);
+    if (cnt <= 64) return expand_warp_runs_t<THICK, 2>(A, K, th, q, lo, cnt, rowbase, start, end, orig, runs, pre);
+    return expand_warp_runs_t<THICK, 0>(A, K, th, q, lo, cnt, rowbase, start, end, orig, runs, pre);
+}
+
+// Any multi-hit query of a target-disjoint table by one warp: one sort key (qStart, candidate, invert) per
+// candidate goes to `scr` (cnt entries of the warp's global scratch; the loads below are warp-uniform, i.e.
+// one L1 transaction each), then every candidate counts the keys in front of its own.  O(cnt^2 / 32) per
+// lane, but with six instructions per pair and no barriers or dependent steps: for the few hundred
+// candidates of a query in a fragmented region this beats a bitonic sort through memory by a wide margin.
+template <bool THICK>
+__device__ __forceinline__ void expand_warp_allpairs(const LiftArgs &A, const RowSink &K, const Thick &th, uint32_t q, int lo, int cnt,
+                                                     uint64_t rowbase, int start, int end, unsigned char orig,
+                                                     unsigned long long *scr) {
+    const TableView &T = A.T;
+    const int lane = lane_id();
+    unsigned long long best = ~0ull;
+    for (int base = 0; base < cnt; base += 32) {
+        const int c = base + lane;
+        if (c < cnt) {
+            const RowCore r = make_row(load_block(T, lo + c), start, end);
+            const unsigned long long key = ((unsigned long long)((uint32_t)r.key ^ 0x80000000u) << 32) | ((uint32_t)c << 1) | (r.inv < 0 ? 1u : 0u);
+            scr[c] = key;
+            best = key < best ? key : best;
+        }
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(FULL, best, d);
+        best = o < best ? o : best;
+    }
+    const int inv_first = (best & 1ull) ? -1 : 1;
+    __syncwarp();
+    for (int base = 0; base < cnt; base += 32) {
+        const int c = base + lane;
+        const bool valid = c < cnt;
+        const unsigned long long my = valid ? scr[c] : 0ull;
+        int rank = 0, negs = (int)(my & 1ull);
+#pragma unroll 4
+        for (int k = 0; k < cnt; k++) {
+            const unsigned long long v = scr[k];
+            const int before = v < my ? 1 : 0;
+            rank += before;
+            negs += before & (int)(v & 1ull);
+        }
+        const uint64_t pos = rowbase + (uint64_t)rank;
+        if (valid && pos < K.cap) {
+            const RowCore row = make_row(load_block(T, lo + c), start, end);
+            const unsigned char sb = A.strand ? strand_at_rank(orig, inv_first, rank, negs) : 0;
+            *reinterpret_cast<int4 *>(K.rows + pos) = make_int4(row.qcid | ((int)sb << 16), row.s, row.e, (int)q);
+            if (THICK) {
+                swo_thick tk;
+                thick_clamp(th, row.s, row.e, tk.thick_start, tk.thick_end);
+                K.thick[pos] = tk;
+            }
+        }
+    }
+    __syncwarp();  // the scratch may be rewritten by the next call
+}
+
+// A query across exactly one gap (two candidate blocks of a target-disjoint table, the usual multi-hit
+// case): both rows, in (qStart, block) order, with the running strand flip (bed.d:156-173).  Straight-line.
+template <bool THICK>
+__device__ __forceinline__ void expand_pair(const LiftArgs &A, const RowSink &K, const Thick &th, uint32_t q, int lo, int start, int end,
+                                            unsigned char strand_byte, uint64_t pos) {
+    const TableView &T = A.T;
+    const RowCore a = make_row(load_block(T, lo), start, end), b = make_row(load_block(T, lo + 1), start, end);
+    const bool swap = b.key < a.key;
+    const RowCore &r0 = swap ? b : a, &r1 = swap ? a : b;
+    unsigned char s0 = 0, s1 = 0;
+    if (A.strand) {
+        s0 = strand_flip(strand_byte, r0.inv);
+        s1 = strand_flip(s0, r1.inv);  // bed.d:173: the flips accumulate
+    }
+    if (pos < K.cap) {
+        *reinterpret_cast<int4 *>(K.rows + pos) = make_int4(r0.qcid | ((int)s0 << 16), r0.s, r0.e, (int)q);
+        if (THICK) thick_clamp(th, r0.s, r0.e, K.thick[pos].thick_start, K.thick[pos].thick_end);
+    }
+    if (pos + 1 < K.cap) {
+        *reinterpret_cast<int4 *>(K.rows + pos + 1) = make_int4(r1.qcid | ((int)s1 << 16), r1.s, r1.e, (int)q);
+        if (THICK) thick_clamp(th, r1.s, r1.e, K.thick[pos + 1].thick_start, K.thick[pos + 1].thick_end);
+    }
+}
+
 // Shared memory of one CTA (dynamic: > 48 KiB with the stage).  The 16-byte aligned arrays come first.
 template <bool THICK, bool DEFER>
 struct LiftSmem {
@@ -315,7 +609,7 @@ __global__ void __launch_bounds__(512) sample_sorted_kernel(const int32_t *__res
 // is resolved one tile later.  The other variant resolves every tile right after its scan and
 // keeps the shared memory for L1 (random probes of the block table).
 template <bool THICK, bool DEFER>
-__global__ void __launch_bounds__(LI_TPB, 4) lift_intervals_kernel(const __grid_constant__ LiftArgs A) {
+__global__ void __launch_bounds__(LI_TPB, LI_MIN_CTAS) lift_intervals_kernel(const __grid_constant__ LiftArgs A) {
     extern __shared__ __align__(16) unsigned char li_smem_raw[];
     LiftSmem<THICK, DEFER> &S = *reinterpret_cast<LiftSmem<THICK, DEFER> *>(li_smem_raw);
     if ((!THICK && __ldg(A.sorted_flag) != 0u) != DEFER) return;
@@ -367,19 +661,42 @@ __global__ void __launch_bounds__(LI_TPB, 4) lift_intervals_kernel(const __grid_
         // row of a single-hit query
         int r_meta[LI_IPT], r_s[LI_IPT], r_e[LI_IPT];
         uint32_t tsum = 0, unm = 0;
+        bool tc_ok[LI_IPT];
+        int4 cm[LI_IPT];
+#pragma unroll
+        for (int k = 0; k < LI_IPT; k++) {
+            tc_ok[k] = tc[k] >= 0 && tc[k] < T.ntc;
+            cm[k] = !tc_ok[k] ? make_int4(0, 0, 0, 0) : cm_smem ? S.cmeta[tc[k]] : load_cmeta(T, tc[k]);
+        }
+        // A thread whose four queries are in order (same contig, starts not moving back: sorted stretches) searches
+        // the first and gallops forward for the others; otherwise the four searches run in lockstep, so that every
+        // round trip to the block table serves all four.
+        bool chained = true;
+#pragma unroll
+        for (int k = 1; k < LI_IPT; k++) chained = chained && tc[k] == tc[k - 1] && st[k] >= st[k - 1];
+        const bool lockstep = LI_LOCKSTEP && !THICK && !chained;  // (with thick columns the lockstep form was not faster)
+        int lo4[LI_IPT];
+        if (lockstep) lower_gt_ey_n<LI_IPT>(T, ey, cm, tc_ok, st, lo4);
 #pragma unroll
         for (int k = 0; k < LI_IPT; k++) {
             Block b0;
-            // sorted batches: same contig and a start that did not move back -> the lower bound only moves
-            // forward from the previous query's (a short gallop instead of a full search)
-            const bool tc_ok = tc[k] >= 0 && tc[k] < T.ntc;
-            const int4 cm = !tc_ok ? make_int4(0, 0, 0, 0) : cm_smem ? S.cmeta[tc[k]] : load_cmeta(T, tc[k]);
-            if (k > 0 && tc[k] == tc[k - 1] && st[k] >= st[k - 1] && tc_ok)
-                cd[k] = find_candidates_from(T, cm.y, cd[k - 1].lo, st[k], en[k], b0);
-            else if (tc_ok)
-                cd[k] = find_candidates_cm(T, ey, cm, st[k], en[k], b0);
-            else
+            if (!tc_ok[k]) {
                 cd[k] = Cand{0, 0};
+            } else if (lockstep) {
+                // (find_candidates_cm behind its search)
+                const int lo = lo4[k];
+                cd[k] = Cand{lo, lo};
+                b0 = Block{0, 0, 0, 0};
+                if (lo < cm[k].y) {
+                    b0 = load_block(T, lo);
+                    const int s1 = lo + 1 < cm[k].y ? __ldg(T.tStartKey + lo + 1) : 0x7fffffff;
+                    if (b0.tStart < en[k]) cd[k].hi = s1 >= en[k] ? lo + 1 : gallop_ge(T.tStartKey, lo + 2, cm[k].y, en[k]);
+                }
+            } else if (k > 0 && tc[k] == tc[k - 1] && st[k] >= st[k - 1]) {
+                cd[k] = find_candidates_from(T, cm[k].y, cd[k - 1].lo, st[k], en[k], b0);
+            } else {
+                cd[k] = find_candidates_cm(T, ey, cm[k], st[k], en[k], b0);
+            }
             nh[k] = count_hits(T, cd[k], st[k]);
             tsum += (uint32_t)nh[k];
             unm += (q0 + k < A.n && nh[k] == 0) ? 1u : 0u;
@@ -467,14 +784,54 @@ __global__ void __launch_bounds__(LI_TPB, 4) lift_intervals_kernel(const __grid_
                         sink.thick[run64] = t;
                     }
                 }
+            } else if (nh[k] == 2 && T.disjoint) {  // an interval across one gap: by its thread, straight-line
+                Thick th{0, 0, 0};
+                if (THICK)
+                    th = lift_thick_from(T, ey, tc[k], __ldg(A.thick_s + q), __ldg(A.thick_e + q), st[k], cd[k].lo,
+                                         (cm_smem ? S.cmeta[tc[k]] : load_cmeta(T, tc[k])).y);
+                expand_pair<THICK>(A, sink, th, q, cd[k].lo, st[k], en[k], A.strand ? __ldg(A.strand + q) : 0, run64);
             } else if (nh[k] >= 2) {
-                pending |= 1u << k;  // queued below, possibly over several rounds of the work list
+                pending |= 1u << k;  // expand_wide_kernel's list, or queued below over several rounds of the work list
             }
             run64 += (uint64_t)nh[k];
         }
-        // multi-hit queries: rounds of (fill the work list, expand it cooperatively) until none is
-        // pending — batches where most queries have many hits need more than one round
         converge_at<4>(A);
+        // Multi-hit queries on a target-disjoint table are appended to the global list (one atomic per
+        // warp) and expanded by expand_wide_kernel, a warp per query with the rows coming straight from
+        // registers: no work-list rounds and no block barriers in here, and the block's other warps do
+        // not wait for the one with the heaviest query.
+        if (!defer && T.disjoint && A.wide_ent) {
+            const uint32_t mine = (uint32_t)__popc(pending);
+            const uint32_t inc = warp_inclusive_scan(mine);
+            const uint32_t wtot = __shfl_sync(FULL, inc, 31);
+            if (wtot) {  // warp-uniform
+                unsigned slot = 0;
+                if (lane_id() == 0) slot = atomicAdd(A.wide_count, wtot);
+                slot = __shfl_sync(FULL, slot, 0) + inc - mine;
+                uint64_t rb = gbase + excl;
+#pragma unroll
+                for (int k = 0; k < LI_IPT; k++) {
+                    if ((pending >> k) & 1u) {
+                        if (slot < A.wide_cap) {
+                            constexpr int STRIDE = THICK ? 3 : 2;
+                            uint4 *const ent = A.wide_ent + STRIDE * (size_t)slot;
+                            ent[0] = make_uint4(q0 + k, (unsigned)cd[k].lo, (unsigned)nh[k], (uint32_t)rb);
+                            ent[1] = make_uint4((unsigned)st[k], (unsigned)en[k], A.strand ? __ldg(A.strand + q0 + k) : 0u, (unsigned)tc[k]);
+                            if (THICK) {
+                                const Thick th = lift_thick_from(T, ey, tc[k], __ldg(A.thick_s + q0 + k), __ldg(A.thick_e + q0 + k), st[k],
+                                                                 cd[k].lo, (cm_smem ? S.cmeta[tc[k]] : load_cmeta(T, tc[k])).y);
+                                ent[2] = make_uint4((unsigned)th.ts, (unsigned)th.te, (unsigned)th.has, 0u);
+                            }
+                            pending &= ~(1u << k);
+                        }
+                        slot++;
+                    }
+                    rb += (uint64_t)nh[k];
+                }
+            }
+        }
+        // the rest (other tables, a full list): rounds of (fill the work list, expand it cooperatively)
+        // until none is pending
         if (__syncthreads_or(pending != 0)) {
             for (;;) {
                 {

@@ -58,18 +58,33 @@ constexpr int MG_SCAN_ITEMS = 16, MG_SCAN_TILE = 256 * MG_SCAN_ITEMS;  // scan_t
 // Multi-hit queries left for expand_wide_kernel: {query, first candidate block, candidates, row position}
 struct WideList {
     unsigned *count;  // appended so far (may run past cap: those were expanded on the spot)
-    uint4 *ent;
+    uint4 *ent;       // two per entry: {query, first block, candidates, row position} {start, end, strand byte, -}
     unsigned cap;
+    unsigned gscr_ctas;  // CTAs of expand_wide_kernel that own a region of the global sort scratch
 };
 // per warp tile, between the passes
 struct MergeTiles {
     uint32_t *total;          // [ntw] rows of the tile; after the scan: exclusive prefix inside its scan tile
-    int32_t *window;          // [ntw] first block of the tile's window, -1: per-query search
     unsigned long long *sum;  // [ntw / MG_SCAN_TILE + 1] rows per scan tile; after the scan: exclusive prefix
 #ifdef MG_DEBUG_COUNTS
     int32_t *dbg;             // [4 * n]: per query {lo, hi, path, -} as the count pass saw them
 #endif
 };
+
+// The deal of warp tiles in the count and write passes: chunks of MG_CHUNK consecutive tiles go round-robin
+// to the CTAs, a chunk's tiles round-robin to the CTA's warps.  A warp's next tile is then 8 tiles (1,024
+// queries) further on — in a sorted batch still inside its 64-block window most of the time — while all
+// CTAs together stay inside a few dozen megabytes of each array.  (One contiguous range per CTA was
+// measured 1.5-1.8x slower in both passes: ~1,800 streams, each on its own 2 MiB page.)
+#ifndef MG_CHUNK_STEPS_V
+#define MG_CHUNK_STEPS_V 2
+#endif
+constexpr int MG_CHUNK_STEPS = MG_CHUNK_STEPS_V, MG_CHUNK = MG_NW * MG_CHUNK_STEPS;
+__device__ __forceinline__ int deal_first() { return (int)blockIdx.x * MG_CHUNK + warp_id(); }
+__device__ __forceinline__ long long deal_next(long long tile) {
+    const long long t = tile + MG_NW;
+    return (t / MG_CHUNK != tile / MG_CHUNK) ? t + (long long)(gridDim.x - 1) * MG_CHUNK : t;
+}
 
 struct MergeSmem {
     int4 q[MG_NW][2][3][32];               // per warp, two stages: the queries {tcid}, {start}, {end} of a tile (TMA-filled)
@@ -137,24 +152,6 @@ __device__ __forceinline__ bool merge_step(int pmj, int tsj, const int (&st)[LI_
     return any != 0u;
 }
 
-// A query across exactly one gap (two candidate blocks, the usual multi-hit case): both rows, in
-// (qStart, block) order, with the running strand flip (bed.d:156-173).  Straight-line code on purpose:
-// see the note on divergent loops at merge_window.
-__device__ __forceinline__ void expand_pair(const LiftArgs &A, uint32_t q, int lo, int start, int end, unsigned char strand_byte,
-                                            uint64_t pos) {
-    const TableView &T = A.T;
-    const RowCore a = make_row(load_block(T, lo), start, end), b = make_row(load_block(T, lo + 1), start, end);
-    const bool swap = b.key < a.key;
-    const RowCore &r0 = swap ? b : a, &r1 = swap ? a : b;
-    unsigned char s0 = 0, s1 = 0;
-    if (A.strand) {
-        s0 = strand_flip(strand_byte, r0.inv);
-        s1 = strand_flip(s0, r1.inv);  // bed.d:173: the flips accumulate
-    }
-    if (pos < A.rows_cap) st_stream_v4(A.rows + pos, make_int4(r0.qcid | ((int)s0 << 16), r0.s, r0.e, (int)q));
-    if (pos + 1 < A.rows_cap) st_stream_v4(A.rows + pos + 1, make_int4(r1.qcid | ((int)s1 << 16), r1.s, r1.e, (int)q));
-}
-
 // one multi-hit query by a whole warp: sort keys in shared memory, in the warp's global scratch, or
 // (beyond that) every candidate ranks itself against all others
 __device__ __forceinline__ void expand_wide(const LiftArgs &A, const RowSink &sink, uint32_t q, int lo, int cnt, uint64_t pos,
@@ -164,8 +161,25 @@ __device__ __forceinline__ void expand_wide(const LiftArgs &A, const RowSink &si
     else expand_query<false>(A, sink, A.T.ey, q, lo, cnt, pos, lane_id(), 32);
 }
 
-// The window merge of one warp: blocks [wb, wb+64) of a contig ending at block `cend` against those of
-// the lane's four queries that are on that contig (bit k of `act`), none of which starts before smin.
+// A warp's 64-block window of the key arrays, kept in registers from tile to tile: lane l holds blocks
+// wb + l (A) and wb + 32 + l (B); positions at or behind the contig's end read as INT_MAX.  In a sorted
+// batch the tiles of a warp move slowly through the table (a block of hg19ToHg38 holds ~1,850 queries of
+// BASELINE configs[1]), so most tiles find their window already there: no search and no key loads.
+struct Window {
+    int tc;      // contig the window is on, -1: none yet
+    int wb;      // first block
+    int cend;    // end block of the contig
+    int before;  // every block of the contig in front of wb ends at or before this position
+    int pmA, tsA, pmB, tsB;
+};
+__device__ __forceinline__ void window_load_half(const TableView &T, int j0, int cend, int &pm, int &ts) {
+    const int j = j0 + lane_id();
+    pm = j < cend ? __ldg(T.pmaxKey + j) : 0x7fffffff;
+    ts = j < cend ? __ldg(T.tStartKey + j) : 0x7fffffff;
+}
+
+// The window merge of one warp: the 64 blocks of window W against those of the lane's four queries that
+// are on its contig (bit k of `act`), none of which starts before smin.
 //
 // EVERY LOOP IN THE MERGE KERNELS HAS A WARP-UNIFORM TRIP COUNT.  An earlier version finished queries
 // that ran past the window, and warps with several contigs, with per-thread searches (data-dependent
@@ -175,12 +189,11 @@ __device__ __forceinline__ void expand_wide(const LiftArgs &A, const RowSink &si
 // not there (tools/fuzz_parity.py seed 771: one lane's rows missing from a tile total, in one build
 // and not in another with a printf added).  profiles/r02_converge_experiments.md has the SASS.
 // With uniform loops there is nothing to reconverge.
-__device__ __forceinline__ void merge_window(const TableView &T, int wb, int cend, int smin, unsigned act, const int (&st)[LI_IPT],
+__device__ __forceinline__ void merge_window(const TableView &T, const Window &W, int smin, unsigned act, const int (&st)[LI_IPT],
                                              const int (&en)[LI_IPT], int (&lo)[LI_IPT], int (&hi)[LI_IPT]) {
     const int lane = lane_id();
-    const int ja = wb + lane, jb = wb + 32 + lane;
-    const int pmA = ja < cend ? __ldg(T.pmaxKey + ja) : 0x7fffffff, tsA = ja < cend ? __ldg(T.tStartKey + ja) : 0x7fffffff;
-    const int pmB = jb < cend ? __ldg(T.pmaxKey + jb) : 0x7fffffff, tsB = jb < cend ? __ldg(T.tStartKey + jb) : 0x7fffffff;
+    const int wb = W.wb, cend = W.cend;
+    const int pmA = W.pmA, tsA = W.tsA, pmB = W.pmB, tsB = W.tsB;
     // queries of other contigs take no part: no block ends at or before INT_MIN, none starts before it
     int s2[LI_IPT], e2[LI_IPT], l2[LI_IPT], h2[LI_IPT];
 #pragma unroll
@@ -237,22 +250,34 @@ __device__ __forceinline__ int find_window(const TableView &T, const MergeSmem &
     return coop_lower_gt(T.pmaxKey, g_lo, gi < cm.w ? g_lo + (1 << T.ey_shift) - 1 : cm.y, smin);
 }
 
-// Candidate block ranges [lo, hi) of the lane's four queries.  hint >= 0: the tile is on one contig and
-// its window starts at block `hint` (write pass, from the count pass); hint == -1: several contigs (or
-// invalid ones); hint == -2: not known yet (count pass).  Returns the window's first block / -1.
-__device__ __forceinline__ int warp_search(const TableView &T, const MergeSmem &S, bool cm_smem, int hint, const int (&tc)[LI_IPT],
-                                           const int (&st)[LI_IPT], const int (&en)[LI_IPT], int (&lo)[LI_IPT], int (&hi)[LI_IPT]) {
+// Candidate block ranges [lo, hi) of the lane's four queries.  C: the warp's window from its previous tile.
+__device__ __forceinline__ void warp_search(const TableView &T, const MergeSmem &S, bool cm_smem, Window &C, const int (&tc)[LI_IPT],
+                                            const int (&st)[LI_IPT], const int (&en)[LI_IPT], int (&lo)[LI_IPT], int (&hi)[LI_IPT]) {
     const int tc0 = __shfl_sync(FULL, tc[0], 0);
-    bool same = hint >= 0;
-    if (hint == -2)
-        same = __all_sync(FULL, tc[0] == tc0 && tc[1] == tc0 && tc[2] == tc0 && tc[3] == tc0) && tc0 >= 0 && tc0 < T.ntc;
+    const bool same = __all_sync(FULL, tc[0] == tc0 && tc[1] == tc0 && tc[2] == tc0 && tc[3] == tc0) && tc0 >= 0 && tc0 < T.ntc;
     if (same) {
-        const int4 cm = cm_smem ? S.cmeta[tc0] : load_cmeta(T, tc0);
         const int m01 = st[0] < st[1] ? st[0] : st[1], m23 = st[2] < st[3] ? st[2] : st[3];
         const int smin = warp_min(m01 < m23 ? m01 : m23);
-        const int wb = hint >= 0 ? hint : find_window(T, S, cm, smin);
-        merge_window(T, wb, cm.y, smin, 0xFu, st, en, lo, hi);
-        return wb;
+        bool hit = C.tc == tc0 && smin >= C.before;  // (warp-uniform)
+        if (hit && __all_sync(FULL, C.pmA <= smin)) {
+            // the first half of the window lies in front of every query: slide by one group
+            C.before = __shfl_sync(FULL, C.pmA, 31);
+            C.pmA = C.pmB, C.tsA = C.tsB;
+            C.wb += 32;
+            window_load_half(T, C.wb + 32, C.cend, C.pmB, C.tsB);
+            hit = !__all_sync(FULL, C.pmA <= smin);  // still in front: the tile is further away, search
+        }
+        if (!hit) {
+            const int4 cm = cm_smem ? S.cmeta[tc0] : load_cmeta(T, tc0);
+            C.tc = tc0;
+            C.cend = cm.y;
+            C.wb = find_window(T, S, cm, smin);
+            C.before = smin;
+            window_load_half(T, C.wb, C.cend, C.pmA, C.tsA);
+            window_load_half(T, C.wb + 32, C.cend, C.pmB, C.tsB);
+        }
+        merge_window(T, C, smin, 0xFu, st, en, lo, hi);
+        return;
     }
     // Several contigs in the tile (contig boundaries, the batch tail, unsorted stretches): one round of
     // the same merge per distinct contig, smallest id first; queries of other contigs sit the round out.
@@ -279,9 +304,15 @@ __device__ __forceinline__ int warp_search(const TableView &T, const MergeSmem &
         if (c < 0 || c >= T.ntc) continue;  // unknown contig: no candidates (lo = hi = 0)
         const int4 cm = cm_smem ? S.cmeta[c] : load_cmeta(T, c);
         const int smin = warp_min(smine);
-        merge_window(T, find_window(T, S, cm, smin), cm.y, smin, act, st, en, lo, hi);
+        Window W;
+        W.tc = c;
+        W.cend = cm.y;
+        W.wb = find_window(T, S, cm, smin);
+        W.before = smin;
+        window_load_half(T, W.wb, W.cend, W.pmA, W.tsA);
+        window_load_half(T, W.wb + 32, W.cend, W.pmB, W.tsB);
+        merge_window(T, W, smin, act, st, en, lo, hi);
     }
-    return -1;
 }
 
 // A warp's queries come through shared memory: lane 0 arms the stage's mbarrier and issues three
@@ -356,11 +387,14 @@ __global__ void __launch_bounds__(MG_TPB, 4) merge_count_kernel(const __grid_con
     merge_tables(T, S, true);
     const int lane = lane_id();
     const bool cm_smem = T.ntc <= LI_CM_CAP;
-    const int nwarps = (int)gridDim.x * MG_NW;
     uint32_t unm_acc = 0;
-    // (this pass is short per tile: plain streaming loads with the tile after the next prefetched into L2 keep
-    // more bytes in flight than the write pass's one-tile-ahead shared-memory stages; measured 267 vs 328 us)
-    for (int tile = (int)blockIdx.x * MG_NW + warp_id(); tile < A.ntiles; tile += nwarps) {
+    // (This pass is short per tile: plain streaming loads with the tile after the next prefetched into L2 keep
+    // more bytes in flight than the write pass's one-tile-ahead shared-memory stages.)
+    Window C;
+    C.tc = -1;
+    C.wb = C.cend = C.before = C.pmA = C.tsA = C.pmB = C.tsB = 0;
+    for (long long tile_ = deal_first(); tile_ < A.ntiles; tile_ = deal_next(tile_)) {
+        const int tile = (int)tile_;
         const uint32_t q0 = (uint32_t)tile * MG_QPW + (uint32_t)lane * LI_IPT;
         const bool full = (uint32_t)(tile + 1) * MG_QPW <= A.n;
         int tc[LI_IPT], st[LI_IPT], en[LI_IPT], lo[LI_IPT], hi[LI_IPT];
@@ -379,11 +413,11 @@ __global__ void __launch_bounds__(MG_TPB, 4) merge_count_kernel(const __grid_con
             }
         }
         {
-            const long long pt = (long long)tile + 2ll * nwarps;
+            const long long pt = deal_next(deal_next(tile_));
             if (lane < 12 && (pt + 1) * MG_QPW <= (long long)A.n)
                 prefetch_l2((lane < 4 ? A.tcid : lane < 8 ? A.start : A.end) + pt * MG_QPW + (lane & 3) * 32);
         }
-        const int wb = warp_search(T, S, cm_smem, -2, tc, st, en, lo, hi);
+        warp_search(T, S, cm_smem, C, tc, st, en, lo, hi);
         uint32_t tsum = 0;
 #pragma unroll
         for (int k = 0; k < LI_IPT; k++) {
@@ -394,7 +428,7 @@ __global__ void __launch_bounds__(MG_TPB, 4) merge_count_kernel(const __grid_con
             if (M.dbg && q0 + k < A.n) {
                 M.dbg[4 * (size_t)(q0 + k)] = lo[k];
                 M.dbg[4 * (size_t)(q0 + k) + 1] = hi[k];
-                M.dbg[4 * (size_t)(q0 + k) + 2] = wb;
+                M.dbg[4 * (size_t)(q0 + k) + 2] = C.wb;
                 M.dbg[4 * (size_t)(q0 + k) + 3] = (int)tsum;
             }
 #endif
@@ -411,10 +445,7 @@ __global__ void __launch_bounds__(MG_TPB, 4) merge_count_kernel(const __grid_con
         // lanes that happen to be there (found by tools/fuzz_parity.py seed 771: one lane's rows missing
         // from the tile total; profiles/r02_converge_experiments.md).
         const uint32_t total = warp_sum(tsum);
-        if (lane == 0) {
-            M.total[tile] = total;
-            M.window[tile] = wb;
-        }
+        if (lane == 0) M.total[tile] = total;
     }
     const uint32_t unm = warp_sum(unm_acc);
     if (lane == 0 && unm) atomicAdd((unsigned long long *)(A.totals + 1), (unsigned long long)unm);
@@ -481,22 +512,24 @@ __global__ void __launch_bounds__(MG_TPB, MG_WRITE_CTAS) merge_write_kernel(cons
     merge_tables(T, S, true);
     const int lane = lane_id(), w = warp_id();
     const bool cm_smem = T.ntc <= LI_CM_CAP;
-    const int nwarps = (int)gridDim.x * MG_NW;
     const int last_block = __ldg(&T.cmeta[T.ntc - 1].y) - 1;
     const RowSink sink{A.rows, A.thick, A.rows_cap};
     const uint32_t cap32 = A.rows_cap > 0xffffffffull ? 0xffffffffu : (uint32_t)A.rows_cap;
     unsigned long long *const gxs = A.gscr + ((size_t)blockIdx.x * MG_NW + w) * MG_GXS;
+    Window C;
+    C.tc = -1;
+    C.wb = C.cend = C.before = C.pmA = C.tsA = C.pmB = C.tsB = 0;
     QueryStager Q(S, A);
-    Q.issue((long long)blockIdx.x * MG_NW + w, 0);
+    if (deal_first() < A.ntiles) Q.issue(deal_first(), 0);
     int stage = 0;
-    for (int tile = (int)blockIdx.x * MG_NW + w; tile < A.ntiles; tile += nwarps, stage ^= 1) {
+    for (long long tile_ = deal_first(); tile_ < A.ntiles; tile_ = deal_next(tile_), stage ^= 1) {
+        const int tile = (int)tile_;
         const uint32_t q0 = (uint32_t)tile * MG_QPW + (uint32_t)lane * LI_IPT;
         const bool full = (uint32_t)(tile + 1) * MG_QPW <= A.n;
         int tc[LI_IPT], st[LI_IPT], en[LI_IPT], lo[LI_IPT], hi[LI_IPT];
         __syncwarp();
-        if ((long long)tile + nwarps < A.ntiles) Q.issue((long long)tile + nwarps, stage ^ 1);
+        if (deal_next(tile_) < A.ntiles) Q.issue(deal_next(tile_), stage ^ 1);
         Q.fetch(tile, stage, tc, st, en);
-        const int wb = __ldg(M.window + tile);
         const uint64_t tbase = M.sum[tile / MG_SCAN_TILE] + (uint64_t)M.total[tile];
         uchar4 sb4 = make_uchar4(0, 0, 0, 0);
         if (STRAND) {
@@ -508,7 +541,7 @@ __global__ void __launch_bounds__(MG_TPB, MG_WRITE_CTAS) merge_write_kernel(cons
                 sb4.w = q0 + 3 < A.n ? A.strand[q0 + 3] : 0;
             }
         }
-        warp_search(T, S, cm_smem, wb < 0 ? -1 : wb, tc, st, en, lo, hi);
+        warp_search(T, S, cm_smem, C, tc, st, en, lo, hi);
         // Hits, and the row of the first candidate — computed without branches for every query (four
         // independent block loads in flight); it is only stored for single-hit queries.
         Block bk[LI_IPT];
@@ -560,10 +593,13 @@ __global__ void __launch_bounds__(MG_TPB, MG_WRITE_CTAS) merge_write_kernel(cons
             for (int k = 0; k < LI_IPT; k++) {
                 if ((multi >> k) & 1u) {
                     if (cnt[k] == 2) {
-                        expand_pair(A, q0 + k, lo[k], st[k], en[k], sbk[k], p);
+                        expand_pair<false>(A, sink, Thick{0, 0, 0}, q0 + k, lo[k], st[k], en[k], sbk[k], p);
                     } else {
                         const unsigned e = atomicAdd(W.count, 1u);
-                        if (e < W.cap) W.ent[e] = make_uint4(q0 + k, (unsigned)lo[k], (unsigned)cnt[k], (uint32_t)p);
+                        if (e < W.cap) {
+                            W.ent[2 * e] = make_uint4(q0 + k, (unsigned)lo[k], (unsigned)cnt[k], (uint32_t)p);
+                            W.ent[2 * e + 1] = make_uint4((unsigned)st[k], (unsigned)en[k], sbk[k], (unsigned)tc[k]);
+                        }
                         else wide |= 1u << k;
                     }
                 }
@@ -589,19 +625,50 @@ __global__ void __launch_bounds__(MG_TPB, MG_WRITE_CTAS) merge_write_kernel(cons
     }
 }
 
-// The queries merge_write_kernel left on the list: a warp per query.  Row positions are 32-bit
-// (the host rejects batches with 2^32 rows or more).
-__global__ void __launch_bounds__(256) expand_wide_kernel(const __grid_constant__ LiftArgs A, const __grid_constant__ WideList W) {
+// The multi-hit queries merge_write_kernel (sorted batches) or lift_intervals_kernel (other batches) left
+// on the list: a warp per query, rows from registers (expand_warp_runs; the entry carries the query, so
+// nothing but the blocks is loaded); what that form declines is sorted in shared memory / the warp's
+// global scratch.  Row positions are 32-bit (the host rejects batches with 2^32 rows or more).
+template <bool THICK>
+__global__ void __launch_bounds__(256, 4) expand_wide_kernel(const __grid_constant__ LiftArgs A, const __grid_constant__ WideList W) {
     __shared__ unsigned long long xs[8][MG_XS];
-    if (__ldg(A.sorted_flag) == 0u) return;
     const unsigned n = min(*W.count, W.cap);
     const int w = warp_id();
     const RowSink sink{A.rows, A.thick, A.rows_cap};
-    unsigned long long *const gxs = A.gscr + ((size_t)blockIdx.x * 8 + w) * MG_GXS;
-    for (unsigned e = blockIdx.x * 8 + w; e < n; e += gridDim.x * 8) {
-        const uint4 v = W.ent[e];
-        expand_wide(A, sink, v.x, (int)v.y, (int)v.z, (uint64_t)v.w, xs[w], gxs);
-        converge(A);
+    unsigned long long *const gxs = A.gscr + ((size_t)blockIdx.x * 8 + w) * MG_GXS;  // (the host sizes the scratch for this grid)
+    constexpr int STRIDE = THICK ? 3 : 2;  // entries of batches with thick columns carry the lifted thickStart/End
+    // Software pipeline, two entries deep: while entry e is expanded, entry e + 2 steps is on its way from the
+    // list and the first-round blocks of entry e + 1 step from the table — the warp never waits for either.
+    const unsigned step = gridDim.x * 8;
+    const int lane = lane_id();
+    unsigned e = blockIdx.x * 8 + w;
+    const uint4 z4 = make_uint4(0, 0, 1, 0);
+    uint4 v0 = z4, x0 = z4, y0 = z4, v1 = z4, x1 = z4, y1 = z4;
+    auto load_entry = [&](unsigned i, uint4 &v, uint4 &x, uint4 &y) {
+        if (i < n) {
+            v = __ldg(W.ent + STRIDE * (size_t)i), x = __ldg(W.ent + STRIDE * (size_t)i + 1);
+            if (THICK) y = __ldg(W.ent + STRIDE * (size_t)i + 2);
+        }
+    };
+    load_entry(e, v0, x0, y0);
+    load_entry(e + step, v1, x1, y1);
+    Block b0 = load_block(A.T, (int)v0.y + min(lane, (int)v0.z - 1));
+    while (e < n) {
+        uint4 v2 = z4, x2 = z4, y2 = z4;
+        load_entry(e + 2 * step, v2, x2, y2);
+        const Block b1 = load_block(A.T, (int)v1.y + min(lane, (int)v1.z - 1));
+        Thick th{0, 0, 0};
+        if (THICK) th.ts = (int)y0.x, th.te = (int)y0.y, th.has = (int)y0.z;
+        if (!expand_warp_runs<THICK>(A, sink, th, v0.x, (int)v0.y, (int)v0.z, (uint64_t)v0.w, (int)x0.x, (int)x0.y, (unsigned char)x0.z,
+                                     reinterpret_cast<int *>(xs[w]), b0)) {
+            if ((int)v0.z <= MG_GXS)
+                expand_warp_allpairs<THICK>(A, sink, th, v0.x, (int)v0.y, (int)v0.z, (uint64_t)v0.w, (int)x0.x, (int)x0.y, (unsigned char)x0.z, gxs);
+            else
+                expand_query<THICK>(A, sink, A.T.ey, v0.x, (int)v0.y, (int)v0.z, (uint64_t)v0.w, lane, 32);
+        }
+        e += step;
+        v0 = v1, x0 = x1, y0 = y1, b0 = b1;
+        v1 = v2, x1 = x2, y1 = y2;
     }
 }
 

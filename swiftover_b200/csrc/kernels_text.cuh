@@ -875,6 +875,7 @@ struct TextSmem {
     unsigned long long scan64[TX_NB * TX_NW];
     uint32_t scan32[TX_NW + 1];
     uint64_t base_l, base_u;
+    uint64_t in_bar;  // mbarrier of the window's bulk copy
     TileCtx X;
     PendTile P;
     unsigned long long lb_part[TX_NW][2];
@@ -1358,7 +1359,12 @@ __global__ void __launch_bounds__(TX_TPB, TX_MIN_CTAS) lift_bed_text_kernel(cons
     // counted (none of which touches the stages); only then is its chained offset resolved
     // and the stage copied out.  Predecessor tiles therefore have a whole extra count phase
     // to publish their aggregates and the look-back practically never waits.
-    if (tid == 0) S.P.pend = 0;
+    if (tid == 0) {
+        S.P.pend = 0;
+        mbar_init(&S.in_bar, 1);
+        mbar_init_fence();
+    }
+    unsigned in_uses = 0;  // completed phases of S.in_bar (block-uniform)
     auto flush = [&]() {  // block-uniform
         PendTile &P = S.P;
         if (!P.pend) return;
@@ -1399,13 +1405,20 @@ __global__ void __launch_bounds__(TX_TPB, TX_MIN_CTAS) lift_bed_text_kernel(cons
         const uint32_t nst = (uint32_t)(gend - g0);
         const uint32_t wv = s0 + nst;  // window offsets < wv hold input bytes
         {
-            const uint32_t nvec = nst >> 4;
-            const int4 *src = reinterpret_cast<const int4 *>(A.in + g0);
-            int4 *dstv = reinterpret_cast<int4 *>(win + s0);
-            for (uint32_t v = tid; v < nvec; v += TX_TPB) dstv[v] = ld_stream_v4(src + v);
-            for (uint32_t i = (nvec << 4) + tid; i < nst; i += TX_TPB) win[s0 + i] = (unsigned char)A.in[g0 + i];
+            // one 1-D bulk copy (TMA) by thread 0 brings the window in; the other threads write the padding and
+            // ask for the window of the tile a grid's width ahead — about the tile some CTA draws when this one
+            // is done — to be brought into L2, so that its bulk copy finds the text there
+            const uint32_t nbulk = nst & ~15u;
+            if (tid == 0) {
+                fence_proxy_async();  // the previous tile's (generic-proxy) accesses to the window come first
+                mbar_expect_tx(&S.in_bar, nbulk);
+                if (nbulk) bulk_g2s(win + s0, A.in + g0, nbulk, &S.in_bar);
+            }
+            for (uint32_t i = nbulk + tid; i < nst; i += TX_TPB) win[s0 + i] = (unsigned char)A.in[g0 + i];
             for (uint32_t i = tid; i < s0; i += TX_TPB) win[i] = '\n';
             for (uint32_t i = wv + tid; i < TX_WIN + TX_PAD; i += TX_TPB) win[i] = '\n';
+            const uint64_t pf = t0 + (uint64_t)gridDim.x * tile_b + (uint64_t)tid * 128u;
+            if ((uint32_t)tid * 128u < tile_b + TX_LOOK && pf < A.in_len) prefetch_l2(A.in + pf);
         }
         if (tid == 0) {
             X.g0 = g0;
@@ -1418,6 +1431,8 @@ __global__ void __launch_bounds__(TX_TPB, TX_MIN_CTAS) lift_bed_text_kernel(cons
             // a terminator found at or beyond this window offset is not the line's real end
             X.limit = gend == A.in_len ? wv + 1 : wv;
         }
+        mbar_wait(&S.in_bar, in_uses & 1u);
+        in_uses++;
         __syncthreads();
 
         // ---- newline masks of the window, 64 bytes per word -----------------------------

@@ -116,6 +116,84 @@ SWO_HD int lower_gt_ey(const TableView &T, const int2 *__restrict__ ey, const in
     }
     return lo;
 }
+#if defined(__CUDACC__)
+// N lower bounds in lockstep (unsorted batches): the probes of every step are issued for all N queries
+// before any of them is used, so one round trip to shared memory / L2 serves N searches.  Same result
+// as lower_gt_ey per query; ok[i] false (unknown contig): out[i] = 0.
+template <int N>
+__device__ __forceinline__ void lower_gt_ey_n(const TableView &T, const int2 *__restrict__ ey, const int4 (&cm)[N], const bool (&ok)[N],
+                                              const int (&x)[N], int (&out)[N]) {
+    int k[N], m[N], lo[N], hi[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        k[i] = 1;
+        m[i] = ok[i] ? cm[i].w : 0;
+    }
+    for (;;) {
+        bool more = false;
+        int key[N];
+#pragma unroll
+        for (int i = 0; i < N; i++) key[i] = k[i] <= m[i] ? ey[cm[i].z - 1 + k[i]].x : 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            if (k[i] <= m[i]) {
+                k[i] = 2 * k[i] + (key[i] <= x[i] ? 1 : 0);
+                more = more || k[i] <= m[i];
+            }
+        }
+        if (!more) break;
+    }
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        const int kk = k[i] >> __ffs(~k[i]);
+        if (!ok[i]) {
+            lo[i] = hi[i] = 0;
+        } else if (kk) {
+            hi[i] = ey[cm[i].z - 1 + kk].y;  // pmaxKey[hi] > x
+            lo[i] = hi[i] - ((1 << T.ey_shift) - 1);
+        } else {
+            lo[i] = cm[i].x + (m[i] << T.ey_shift);
+            hi[i] = cm[i].y;
+        }
+    }
+    for (;;) {
+        bool more = false;
+        int i1[N], i2[N], i3[N], k1[N], k2[N], k3[N];
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            const bool act = lo[i] < hi[i];
+            const int q = (hi[i] - lo[i] + 3) >> 2;
+            i1[i] = lo[i] + q - 1;
+            i2[i] = i1[i] + q < hi[i] ? i1[i] + q : hi[i] - 1;
+            i3[i] = i2[i] + q < hi[i] ? i2[i] + q : hi[i] - 1;
+            k1[i] = act ? __ldg(T.pmaxKey + i1[i]) : 0;
+            k2[i] = act ? __ldg(T.pmaxKey + i2[i]) : 0;
+            k3[i] = act ? __ldg(T.pmaxKey + i3[i]) : 0;
+        }
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            if (lo[i] < hi[i]) {
+                if (k1[i] > x[i]) {
+                    hi[i] = i1[i];
+                } else if (k2[i] > x[i]) {
+                    lo[i] = i1[i] + 1;
+                    hi[i] = i2[i];
+                } else if (k3[i] > x[i]) {
+                    lo[i] = i2[i] + 1;
+                    hi[i] = i3[i];
+                } else {
+                    lo[i] = i3[i] + 1;
+                }
+                more = more || lo[i] < hi[i];
+            }
+        }
+        if (!more) break;
+    }
+#pragma unroll
+    for (int i = 0; i < N; i++) out[i] = lo[i];
+}
+#endif
+
 // (plain load: the text kernel keeps the per-contig table in shared memory)
 SWO_HD int4 load_cmeta(const TableView &T, int tcid) { return T.cmeta[tcid]; }
 

@@ -274,10 +274,10 @@ int launch_lift_intervals(swo_ctx *c, Device &d, size_t n, const int32_t *tcid, 
                           cudaStream_t st) {
     const int ntiles = (int)((n + LI_TILE - 1) / LI_TILE);
     // scratch: [ticket, wide-list count, sorted flag, -] [ntiles tile descriptors (per-query-search variants)]
-    // sorted variant (count / scan / write over warp tiles of MG_QPW queries): [ntw totals] [ntw windows] [nsum sums]
+    // sorted variant (count / scan / write over warp tiles of MG_QPW queries): [ntw totals] [nsum sums]
     const int ntw = (int)((n + MG_QPW - 1) / MG_QPW), nsum = (ntw + MG_SCAN_TILE - 1) / MG_SCAN_TILE;
     const size_t w_total = (16 + (size_t)ntiles * 8 + 15) & ~(size_t)15;
-    const size_t w_window = (w_total + (size_t)ntw * 4 + 15) & ~(size_t)15, w_sum = (w_window + (size_t)ntw * 4 + 15) & ~(size_t)15;
+    const size_t w_sum = (w_total + (size_t)ntw * 4 + 15) & ~(size_t)15;
     const size_t scratch_bytes = w_sum + (size_t)(nsum + 1) * 8;
     const size_t zero_bytes = w_total;  // header + tile descriptors; the sorted variant's arrays are written before they are read
     if (d.scratch_used) CK(c, cudaStreamWaitEvent(st, d.ev_scratch, 0));
@@ -305,7 +305,6 @@ int launch_lift_intervals(swo_ctx *c, Device &d, size_t n, const int32_t *tcid, 
     A.desc = reinterpret_cast<uint64_t *>(d.scratch.as<char>() + 16);
     MergeTiles M;
     M.total = reinterpret_cast<uint32_t *>(d.scratch.as<char>() + w_total);
-    M.window = reinterpret_cast<int32_t *>(d.scratch.as<char>() + w_window);
     M.sum = reinterpret_cast<unsigned long long *>(d.scratch.as<char>() + w_sum);
     A.gscr = nullptr;
     A.totals = totals;
@@ -318,7 +317,26 @@ int launch_lift_intervals(swo_ctx *c, Device &d, size_t n, const int32_t *tcid, 
     A.sorted_flag = flag;
     A.full_mask = 0xffffffffu;
     const bool th = ths != nullptr;
-    const bool merge_ok = d.T.disjoint != 0;  // the merge kernel assumes candidates == hits
+    const bool merge_ok = d.T.disjoint != 0;  // the merge kernel and expand_warp_runs assume candidates == hits
+    // Multi-hit queries of a target-disjoint table go to a list and are expanded by expand_wide_kernel behind
+    // the main kernel (whichever variant ran).  A full list is not an error: the rest is expanded on the spot.
+    WideList W;
+    W.ent = nullptr;
+    W.count = reinterpret_cast<unsigned *>(d.scratch.as<char>() + 4);
+    W.cap = 0;
+    W.gscr_ctas = (unsigned)std::max(1, d.sms * 8);  // every CTA of expand_wide_kernel (and of merge_write_kernel) owns a region
+    A.wide_ent = nullptr;
+    A.wide_count = W.count;
+    A.wide_cap = 0;
+    if (merge_ok) {
+        W.cap = (unsigned)std::min<size_t>(n, (size_t)32 << 20);
+        CK(c, d.wide.reserve((size_t)W.cap * (th ? 3 : 2) * sizeof(uint4)));
+        W.ent = d.wide.as<uint4>();
+        CK(c, d.gscr.reserve((size_t)W.gscr_ctas * MG_NW * MG_GXS * sizeof(unsigned long long)));
+        A.gscr = d.gscr.as<unsigned long long>();
+        A.wide_ent = W.ent;
+        A.wide_cap = W.cap;
+    }
     if (!th) {
         sample_sorted_kernel<<<1, 512, 0, st>>>(tcid, start, (uint32_t)n, flag, merge_ok ? 1u : 0u);
         c->launches++;
@@ -326,7 +344,7 @@ int launch_lift_intervals(swo_ctx *c, Device &d, size_t n, const int32_t *tcid, 
     for (int v = th ? 2 : 0; v < (th ? 3 : 2); v++) {
         if (v == 1) {
             // Sorted batches (flag set on the device; otherwise each of these returns at once): count pass, scan of the
-            // warp tiles' totals, write pass, and the wide multi-hit queries the write pass left on its list.
+            // warp tiles' totals, write pass.
             if (!merge_ok) continue;
             const void *fw = strand ? (const void *)merge_write_kernel<true> : (const void *)merge_write_kernel<false>;
             const size_t smem = sizeof(MergeSmem);
@@ -341,19 +359,12 @@ int launch_lift_intervals(swo_ctx *c, Device &d, size_t n, const int32_t *tcid, 
                 int per = 0;
                 CK(c, cudaFuncSetAttribute(fw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, fw, MG_TPB, smem));
-                d.bin_grid[gw] = std::max(1, per) * d.sms;
+                d.bin_grid[gw] = std::min(std::max(1, per), 3) * d.sms;  // (the global sort scratch has regions for 3 CTAs per SM)
             }
             LiftArgs Aw = A;
             Aw.ntiles = ntw;
             const int need = (ntw + MG_NW - 1) / MG_NW;
             const int grid_c = std::min(need, d.bin_grid[1]), grid_w = std::min(need, d.bin_grid[gw]);
-            CK(c, d.gscr.reserve((size_t)std::max(grid_w * MG_NW, 8) * MG_GXS * sizeof(unsigned long long)));
-            Aw.gscr = d.gscr.as<unsigned long long>();
-            WideList W;
-            W.cap = (unsigned)std::min<size_t>(n / 128 + 65536, 0x7fffffffu);
-            CK(c, d.wide.reserve((size_t)W.cap * sizeof(uint4)));
-            W.ent = d.wide.as<uint4>();
-            W.count = reinterpret_cast<unsigned *>(d.scratch.as<char>() + 4);
 #ifdef MG_DEBUG_COUNTS
             M.dbg = nullptr;
             if (getenv("SWO_DUMP_COUNTS")) cudaMalloc(&M.dbg, n * 16);
@@ -376,8 +387,7 @@ int launch_lift_intervals(swo_ctx *c, Device &d, size_t n, const int32_t *tcid, 
             scan_tiles_kernel2<<<1, 1024, 0, st>>>(flag, M, nsum, totals, row_offset + n);
             void *wargs[] = {(void *)&Aw, (void *)&M, (void *)&W};
             CK(c, cudaLaunchKernel(fw, dim3(grid_w), dim3(MG_TPB), wargs, smem, st));
-            expand_wide_kernel<<<std::max(1, grid_w * MG_NW / 8), 256, 0, st>>>(Aw, W);
-            c->launches += 5;
+            c->launches += 4;
             continue;
         }
         const void *fn = v == 0 ? (const void *)lift_intervals_kernel<false, false> : (const void *)lift_intervals_kernel<true, false>;
@@ -391,6 +401,11 @@ int launch_lift_intervals(swo_ctx *c, Device &d, size_t n, const int32_t *tcid, 
         const int grid = std::min(ntiles, d.bin_grid[v]);
         void *args[] = {(void *)&A};
         CK(c, cudaLaunchKernel(fn, dim3(grid), dim3(LI_TPB), args, smem, st));
+        c->launches++;
+    }
+    if (merge_ok) {  // latency-bound (a block load per round of 32 rows): all the warps the SMs hold
+        if (th) expand_wide_kernel<true><<<d.sms * 8, 256, 0, st>>>(A, W);
+        else expand_wide_kernel<false><<<d.sms * 8, 256, 0, st>>>(A, W);
         c->launches++;
     }
     CK(c, cudaGetLastError());
