@@ -286,30 +286,62 @@ __device__ __forceinline__ bool expand_warp_runs_t(const LiftArgs &A, const RowS
         const int c = 32 * i + lane;
         return make_row(i == 0 ? pre : load_block(T, lo + (c < cnt ? c : 0)), start, end);
     };
-    int nruns = 0, cm = 0, cv = 0;
-#pragma unroll
-    for (int i = 0; i < (R > 0 ? R : rounds); i++) {
-        if (R > 0 && i >= rounds) break;
-        const int c = 32 * i + lane;
-        const bool valid = c < cnt;
-        const RowCore row = fetch(i);
-        const int meta = (row.qcid << 1) | (row.inv < 0 ? 1 : 0), send = row.inv > 0 ? row.e : row.s;
-        int pm = __shfl_up_sync(FULL, meta, 1), pv = __shfl_up_sync(FULL, send, 1);
-        if (lane == 0) pm = cm, pv = cv;
-        const bool brk = valid && !run_continues(c, pm, pv, meta, row);
-        const unsigned bm = __ballot_sync(FULL, brk);
-        const int r = nruns + __popc(bm & le_mask) - 1;  // run of this candidate
-        if (brk && r < 32) {
-            runs[4 * r] = c;
-            runs[4 * r + 1] = row.inv > 0 ? row.s : row.e;
-            runs[4 * r + 3] = row.inv;
+    auto store = [&](const RowCore &row, int rank, int negs_le, int inv_first) {
+        const uint64_t pos = rowbase + (uint64_t)rank;
+        if (pos < K.cap) {
+            const unsigned char sb = A.strand ? strand_at_rank(orig, inv_first, rank, negs_le) : 0;
+            *reinterpret_cast<int4 *>(K.rows + pos) = make_int4(row.qcid | ((int)sb << 16), row.s, row.e, (int)q);
+            if (THICK) {
+                swo_thick tk;
+                thick_clamp(th, row.s, row.e, tk.thick_start, tk.thick_end);
+                K.thick[pos] = tk;
+            }
         }
-        if (brk && c > 0 && r <= 32) runs[4 * (r - 1) + 2] = pv;  // the previous run ended just before
-        if (valid && c == cnt - 1 && r < 32) runs[4 * r + 2] = send;
-        nruns += __popc(bm);
-        cm = __shfl_sync(FULL, meta, 31);
-        cv = __shfl_sync(FULL, send, 31);
+    };
+    // Pass 1: cut into runs; RECORD: leave the runs in the scratch.  Returns the number of runs.
+    auto cut = [&](const bool record) -> int {
+        int nruns = 0, cm = 0, cv = 0;
+#pragma unroll
+        for (int i = 0; i < (R > 0 ? R : rounds); i++) {
+            if (R > 0 && i >= rounds) break;
+            const int c = 32 * i + lane;
+            const bool valid = c < cnt;
+            const RowCore row = fetch(i);
+            const int meta = (row.qcid << 1) | (row.inv < 0 ? 1 : 0), send = row.inv > 0 ? row.e : row.s;
+            int pm = __shfl_up_sync(FULL, meta, 1), pv = __shfl_up_sync(FULL, send, 1);
+            if (lane == 0) pm = cm, pv = cv;
+            const bool brk = valid && !run_continues(c, pm, pv, meta, row);
+            const unsigned bm = __ballot_sync(FULL, brk);
+            if (record) {
+                const int r = nruns + __popc(bm & le_mask) - 1;  // run of this candidate
+                if (brk && r < 32) {
+                    runs[4 * r] = c;
+                    runs[4 * r + 1] = row.inv > 0 ? row.s : row.e;
+                    runs[4 * r + 3] = row.inv;
+                }
+                if (brk && c > 0 && r <= 32) runs[4 * (r - 1) + 2] = pv;  // the previous run ended just before
+                if (valid && c == cnt - 1 && r < 32) runs[4 * r + 2] = send;
+            }
+            nruns += __popc(bm);
+            cm = __shfl_sync(FULL, meta, 31);
+            cv = __shfl_sync(FULL, send, 31);
+        }
+        return nruns;
+    };
+    int nruns = cut(false);
+    if (nruns == 1) {  // one chain piece (the usual case): candidate order, or exactly reversed; nothing goes through the scratch
+        const int inv_first = __shfl_sync(FULL, fetch(0).inv, 0);
+#pragma unroll
+        for (int i = 0; i < (R > 0 ? R : rounds); i++) {
+            if (R > 0 && i >= rounds) break;
+            const int c = 32 * i + lane;
+            const RowCore row = fetch(i);
+            const int t = inv_first > 0 ? c : cnt - 1 - c;
+            if (c < cnt) store(row, t, inv_first < 0 ? t + 1 : 0, inv_first);
+        }
+        return true;
     }
+    cut(true);
     __syncwarp();
     // lane j = run j
     const bool have = lane < nruns && nruns <= 32;
@@ -318,7 +350,7 @@ __device__ __forceinline__ bool expand_warp_runs_t(const LiftArgs &A, const RowS
     const int r_size = have ? (lane + 1 < nruns ? runs[4 * (lane + 1)] : cnt) - r_first : 0;
     int off = 0, negoff = 0;
     bool sort = nruns > 32;
-    if (nruns > 1 && !sort) {  // warp-uniform
+    if (!sort) {  // warp-uniform
         const int mn = r_inv > 0 ? r_k0 : r_k1, mx = r_inv > 0 ? r_k1 : r_k0;
         bool bad = false;
         for (int i = 0; i < nruns; i++) {
@@ -337,79 +369,28 @@ __device__ __forceinline__ bool expand_warp_runs_t(const LiftArgs &A, const RowS
     }
     __syncwarp();  // the scratch may be rewritten by the next call
     if (sort) {
-        // Interleaved runs (a nested chain inside the gap of another: A A B A A): with the rows in registers every
-        // candidate counts the rows in front of it — smaller qStart, or equal and an earlier candidate.
+        // Runs that overlap or touch in the destination (a nested chain that lands next to its host), or more than
+        // 32 of them: every candidate counts the rows in front of it — smaller qStart, or equal and an earlier candidate.
         if (R != 1) return false;  // (through the scratch the count costs the same and needs no registers)
-        int rank[R > 0 ? R : 1], negs[R > 0 ? R : 1];
-        unsigned invm[R > 0 ? R : 1];
-#pragma unroll
-        for (int ri = 0; ri < R; ri++) {
-            const bool neg = 32 * ri + lane < cnt && rows[ri].inv < 0;
-            rank[ri] = 0;
-            negs[ri] = neg ? 1 : 0;
-            invm[ri] = __ballot_sync(FULL, neg);
+        const RowCore &mine = rows[0];
+        const bool valid = lane < cnt;
+        const unsigned invm = __ballot_sync(FULL, valid && mine.inv < 0);
+        int rank = 0, negs = valid && mine.inv < 0 ? 1 : 0;
+        for (int l = 0; l < cnt; l++) {  // warp-uniform
+            const int k = __shfl_sync(FULL, mine.key, l);
+            const int before = (k < mine.key || (k == mine.key && l < lane)) ? 1 : 0;
+            rank += before;
+            negs += before & (int)((invm >> l) & 1u);
         }
-#pragma unroll
-        for (int rj = 0; rj < R; rj++) {
-            const int lim = min(32, cnt - 32 * rj);
-            for (int l = 0; l < lim; l++) {  // warp-uniform
-                const int k = __shfl_sync(FULL, rows[rj].key, l), idx = 32 * rj + l, ng = (int)((invm[rj] >> l) & 1u);
-#pragma unroll
-                for (int ri = 0; ri < R; ri++) {
-                    const int before = (k < rows[ri].key || (k == rows[ri].key && idx < 32 * ri + lane)) ? 1 : 0;
-                    rank[ri] += before;
-                    negs[ri] += before & ng;
-                }
-            }
-        }
-        int inv_first = 1;
-#pragma unroll
-        for (int ri = 0; ri < R; ri++) {
-            const unsigned m = __ballot_sync(FULL, 32 * ri + lane < cnt && rank[ri] == 0);
-            const int iv = __shfl_sync(FULL, rows[ri].inv, m ? __ffs(m) - 1 : 0);
-            if (m) inv_first = iv;
-        }
-#pragma unroll
-        for (int ri = 0; ri < R; ri++) {
-            const uint64_t pos = rowbase + (uint64_t)rank[ri];
-            if (32 * ri + lane < cnt && pos < K.cap) {
-                const RowCore &row = rows[ri];
-                const unsigned char sb = A.strand ? strand_at_rank(orig, inv_first, rank[ri], negs[ri]) : 0;
-                *reinterpret_cast<int4 *>(K.rows + pos) = make_int4(row.qcid | ((int)sb << 16), row.s, row.e, (int)q);
-                if (THICK) {
-                    swo_thick tk;
-                    thick_clamp(th, row.s, row.e, tk.thick_start, tk.thick_end);
-                    K.thick[pos] = tk;
-                }
-            }
-        }
+        const unsigned m0 = __ballot_sync(FULL, valid && rank == 0);
+        const int inv_first = __shfl_sync(FULL, mine.inv, __ffs(m0) - 1);
+        if (valid) store(mine, rank, negs, inv_first);
         return true;
     }
     const unsigned fm = __ballot_sync(FULL, have && off == 0);
     const int inv_first = __shfl_sync(FULL, r_inv, __ffs(fm) - 1);
-    auto store = [&](const RowCore &row, int rank, int negs_le) {
-        const uint64_t pos = rowbase + (uint64_t)rank;
-        if (pos < K.cap) {
-            const unsigned char sb = A.strand ? strand_at_rank(orig, inv_first, rank, negs_le) : 0;
-            *reinterpret_cast<int4 *>(K.rows + pos) = make_int4(row.qcid | ((int)sb << 16), row.s, row.e, (int)q);
-            if (THICK) {
-                swo_thick tk;
-                thick_clamp(th, row.s, row.e, tk.thick_start, tk.thick_end);
-                K.thick[pos] = tk;
-            }
-        }
-    };
-    if (nruns == 1) {  // one chain piece (the usual case): candidate order, or exactly reversed
-#pragma unroll
-        for (int i = 0; i < (R > 0 ? R : rounds); i++) {
-            if (R > 0 && i >= rounds) break;
-            const int c = 32 * i + lane;
-            const RowCore row = fetch(i);
-            const int t = inv_first > 0 ? c : cnt - 1 - c;
-            if (c < cnt) store(row, t, inv_first < 0 ? t + 1 : 0);
-        }
-        return true;
-    }
+    // Pass 2: every candidate to its place
+    int cm = 0, cv = 0;
     nruns = 0;
 #pragma unroll
     for (int i = 0; i < (R > 0 ? R : rounds); i++) {
@@ -426,13 +407,14 @@ __device__ __forceinline__ bool expand_warp_runs_t(const LiftArgs &A, const RowS
         const int first = __shfl_sync(FULL, r_first, r), sz = __shfl_sync(FULL, r_size, r);
         const int o = __shfl_sync(FULL, off, r), no = __shfl_sync(FULL, negoff, r);
         const int t = row.inv > 0 ? c - first : first + sz - 1 - c;
-        if (valid) store(row, o + t, no + (row.inv < 0 ? t + 1 : 0));
+        if (valid) store(row, o + t, no + (row.inv < 0 ? t + 1 : 0), inv_first);
         nruns += __popc(bm);
         cm = __shfl_sync(FULL, meta, 31);
         cv = __shfl_sync(FULL, send, 31);
     }
     return true;
 }
+
 // `pre`: the lane's block of the first round, lo + min(lane, cnt - 1), loaded by the caller (expand_wide_kernel
 // loads it while the previous query is expanded, which takes the table's latency out of the chain).
 template <bool THICK>
