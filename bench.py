@@ -389,7 +389,34 @@ def other_configs(cf, S, shard, torch, dev, rank, world, peak, args):
                      "n_per_gpu": n4, "matched_rank0": matched, "refchg_rank0": refchg, "refchg_frac_of_matched": refchg / max(1, matched),
                      "ms": ms, "algorithmic_bytes_per_gpu": alg, "bytes_note": "20 B in + 13 B out + REF bytes in and out + one "
                      "32-byte genome sector per record (SURVEY.md 8d)", "kernel": "lift_vcf_points_kernel", "scaling": "strong"})
+    # the same records through the host-array call (swo_lift_vcf_points): pinned host arrays in, pinned host arrays out,
+    # chunks pipelined over three streams inside the call
+    pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t)
+    h_tc, h_pos, h_rl, h_ro, h_ref = pin(tc), pin(pos), pin(rl), pin(ro), pin(ref2)
+    h_oq, h_op, h_orl = (torch.empty(n4, dtype=torch.int32, pin_memory=True) for _ in range(3))
+    h_fl = torch.empty(n4, dtype=torch.uint8, pin_memory=True)
+    h_oref = torch.empty(nref, dtype=torch.uint8, pin_memory=True)
+    fl_dev = fl.clone()
     del tc, pos, rl, ro, ref, ref2, oq, op, orl, fl, oref
+    torch.cuda.empty_cache()
+
+    def vcf_host():
+        rc = L.lib().swo_lift_vcf_points(cf.handle, n4, h_tc.data_ptr(), h_pos.data_ptr(), h_rl.data_ptr(), h_ro.data_ptr(),
+                                         h_ref.data_ptr(), nref, h_oq.data_ptr(), h_op.data_ptr(), h_fl.data_ptr(),
+                                         h_orl.data_ptr(), h_oref.data_ptr())
+        assert rc == 0, L.lib().swo_last_error(cf.handle)
+    vcf_host()
+    assert torch.equal(h_fl, fl_dev.cpu()), "host-array VCF call disagrees with the device-resident one"
+    shard.barrier()
+    t0 = time.perf_counter()
+    for _ in range(2):
+        vcf_host()
+    shard.barrier()
+    ms = (time.perf_counter() - t0) * 1e3 / 2
+    put("cfg4_e2e", {"workload": f"configs[3] end to end: {n4} records per GPU, pinned host arrays in -> pinned host arrays out "
+                                 "(swo_lift_vcf_points)", "n_per_gpu": n4, "h2d_bytes": n4 * 20 + nref, "d2h_bytes": n4 * 13 + nref,
+                     "ms": ms})
+    del h_tc, h_pos, h_rl, h_ro, h_ref, h_oq, h_op, h_orl, h_fl, h_oref, fl_dev
     torch.cuda.empty_cache()
 
     # ---- configs[4]: fragmented (CanFam4-like) chain, 1e8 long intervals / N GPUs, in batches (rows < 2^32 per call) ----

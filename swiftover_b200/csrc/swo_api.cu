@@ -1180,36 +1180,63 @@ int swo_lift_vcf_points(swo_ctx *c, size_t n, const int32_t *tcid, const int32_t
     uint64_t *d_ro = (uint64_t *)(base + 6 * na);
     char *d_ref = base + 6 * na + n8, *d_oref = d_ref + nr;
     uint8_t *d_fl = (uint8_t *)(d_oref + nr);
-    CK(c, cudaMemcpyAsync(d_tcid, tcid, n * 4, cudaMemcpyHostToDevice, st));
-    CK(c, cudaMemcpyAsync(d_pos, pos, n * 4, cudaMemcpyHostToDevice, st));
-    CK(c, cudaMemcpyAsync(d_rl, reflen, n * 4, cudaMemcpyHostToDevice, st));
-    CK(c, cudaMemcpyAsync(d_ro, ref_off, n * 8, cudaMemcpyHostToDevice, st));
-    if (ref_bytes_len) CK(c, cudaMemcpyAsync(d_ref, ref_bytes, ref_bytes_len, cudaMemcpyHostToDevice, st));
-    VcfArgs A;
-    A.T = d.T;
-    A.G = genome_view(d);
-    A.n = (uint32_t)n;
-    A.tcid = d_tcid;
-    A.pos = d_pos;
-    A.reflen = d_rl;
-    A.ref_off = d_ro;
-    A.ref = d_ref;
-    A.out_qcid = d_oq;
-    A.out_pos = d_op;
-    A.flags = d_fl;
-    A.out_reflen = d_orl;
-    A.out_ref = d_oref;
-    const int grid = (int)std::min<size_t>((n + 255) / 256, (size_t)d.sms * 8);
-    lift_vcf_points_kernel<<<grid, 256, 0, st>>>(A);
-    c->launches++;
-    CK(c, cudaGetLastError());
-    CK(c, cudaMemcpyAsync(out_qcid, d_oq, n * 4, cudaMemcpyDeviceToHost, st));
-    CK(c, cudaMemcpyAsync(out_pos, d_op, n * 4, cudaMemcpyDeviceToHost, st));
-    CK(c, cudaMemcpyAsync(out_reflen, d_orl, n * 4, cudaMemcpyDeviceToHost, st));
-    CK(c, cudaMemcpyAsync(flags, d_fl, n, cudaMemcpyDeviceToHost, st));
-    if (out_ref && ref_bytes_len) CK(c, cudaMemcpyAsync(out_ref, d_oref, ref_bytes_len, cudaMemcpyDeviceToHost, st));
-    CK(c, cudaStreamSynchronize(st));
-    return SWO_OK;
+    // Chunks of records flow through three streams (H2D / kernel / D2H), so that both directions of the link
+    // and the kernel overlap; with caller arrays in pinned memory (swo_host_alloc) the copies run at link
+    // speed, with pageable arrays the driver stages them and the pipeline still hides the kernel.  The REF
+    // bytes travel whole: in before the first chunk, out behind the last.
+    (void)st;
+    const size_t chunk = (size_t)8 << 20;
+    const int nch = (int)((n + chunk - 1) / chunk);
+    std::vector<cudaEvent_t> ev((size_t)nch * 2, nullptr);
+    int rc = SWO_OK;
+    auto ck = [&](cudaError_t e) {
+        if (e != cudaSuccess && rc == SWO_OK) rc = fail(c, SWO_E_CUDA, cudaGetErrorString(e));
+        return e == cudaSuccess;
+    };
+    for (auto &e : ev) ck(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    // (the staging buffer's previous user is done: every host-array entry point ends with a synchronise)
+    if (rc == SWO_OK && ref_bytes_len) ck(cudaMemcpyAsync(d_ref, ref_bytes, ref_bytes_len, cudaMemcpyHostToDevice, d.s_h2d));
+    for (int k = 0; k < nch && rc == SWO_OK; k++) {
+        const size_t i0 = (size_t)k * chunk, m = std::min(chunk, n - i0);
+        ck(cudaMemcpyAsync(d_tcid + i0, tcid + i0, m * 4, cudaMemcpyHostToDevice, d.s_h2d));
+        ck(cudaMemcpyAsync(d_pos + i0, pos + i0, m * 4, cudaMemcpyHostToDevice, d.s_h2d));
+        ck(cudaMemcpyAsync(d_rl + i0, reflen + i0, m * 4, cudaMemcpyHostToDevice, d.s_h2d));
+        ck(cudaMemcpyAsync(d_ro + i0, ref_off + i0, m * 8, cudaMemcpyHostToDevice, d.s_h2d));
+        ck(cudaEventRecord(ev[2 * k], d.s_h2d));
+        ck(cudaStreamWaitEvent(d.s_comp, ev[2 * k], 0));
+        VcfArgs A;
+        A.T = d.T;
+        A.G = genome_view(d);
+        A.n = (uint32_t)m;
+        A.tcid = d_tcid + i0;
+        A.pos = d_pos + i0;
+        A.reflen = d_rl + i0;
+        A.ref_off = d_ro + i0;  // (offsets into the whole REF buffer)
+        A.ref = d_ref;
+        A.out_qcid = d_oq + i0;
+        A.out_pos = d_op + i0;
+        A.flags = d_fl + i0;
+        A.out_reflen = d_orl + i0;
+        A.out_ref = d_oref;
+        const int grid = (int)std::min<size_t>((m + 255) / 256, (size_t)d.sms * 8);
+        lift_vcf_points_kernel<<<grid, 256, 0, d.s_comp>>>(A);
+        c->launches++;
+        ck(cudaGetLastError());
+        ck(cudaEventRecord(ev[2 * k + 1], d.s_comp));
+        ck(cudaStreamWaitEvent(d.s_d2h, ev[2 * k + 1], 0));
+        ck(cudaMemcpyAsync(out_qcid + i0, d_oq + i0, m * 4, cudaMemcpyDeviceToHost, d.s_d2h));
+        ck(cudaMemcpyAsync(out_pos + i0, d_op + i0, m * 4, cudaMemcpyDeviceToHost, d.s_d2h));
+        ck(cudaMemcpyAsync(out_reflen + i0, d_orl + i0, m * 4, cudaMemcpyDeviceToHost, d.s_d2h));
+        ck(cudaMemcpyAsync(flags + i0, d_fl + i0, m, cudaMemcpyDeviceToHost, d.s_d2h));
+    }
+    if (rc == SWO_OK && out_ref && ref_bytes_len)  // behind the last kernel: s_d2h already waits for it
+        ck(cudaMemcpyAsync(out_ref, d_oref, ref_bytes_len, cudaMemcpyDeviceToHost, d.s_d2h));
+    ck(cudaStreamSynchronize(d.s_h2d));
+    ck(cudaStreamSynchronize(d.s_comp));
+    ck(cudaStreamSynchronize(d.s_d2h));
+    for (auto &e : ev)
+        if (e) cudaEventDestroy(e);
+    return rc;
 }
 
 int swo_lift_vcf_points_dev(swo_ctx *c, size_t n, const int32_t *d_tcid, const int32_t *d_pos, const int32_t *d_rl,
