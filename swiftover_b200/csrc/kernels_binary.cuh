@@ -643,12 +643,16 @@ __global__ void __launch_bounds__(LI_TPB, LI_MIN_CTAS) lift_intervals_kernel(con
         // row of a single-hit query
         int r_meta[LI_IPT], r_s[LI_IPT], r_e[LI_IPT];
         uint32_t tsum = 0, unm = 0;
+        constexpr bool LOCKSTEP = LI_LOCKSTEP && !THICK;  // (with thick columns the lockstep form was not faster)
         bool tc_ok[LI_IPT];
         int4 cm[LI_IPT];
-#pragma unroll
-        for (int k = 0; k < LI_IPT; k++) {
+        auto contig = [&](int k) {
             tc_ok[k] = tc[k] >= 0 && tc[k] < T.ntc;
             cm[k] = !tc_ok[k] ? make_int4(0, 0, 0, 0) : cm_smem ? S.cmeta[tc[k]] : load_cmeta(T, tc[k]);
+        };
+        if (LOCKSTEP) {
+#pragma unroll
+            for (int k = 0; k < LI_IPT; k++) contig(k);
         }
         // A thread whose four queries are in order (same contig, starts not moving back: sorted stretches) searches
         // the first and gallops forward for the others; otherwise the four searches run in lockstep, so that every
@@ -656,12 +660,13 @@ __global__ void __launch_bounds__(LI_TPB, LI_MIN_CTAS) lift_intervals_kernel(con
         bool chained = true;
 #pragma unroll
         for (int k = 1; k < LI_IPT; k++) chained = chained && tc[k] == tc[k - 1] && st[k] >= st[k - 1];
-        const bool lockstep = LI_LOCKSTEP && !THICK && !chained;  // (with thick columns the lockstep form was not faster)
+        const bool lockstep = LOCKSTEP && !chained;
         int lo4[LI_IPT];
         if (lockstep) lower_gt_ey_n<LI_IPT>(T, ey, cm, tc_ok, st, lo4);
 #pragma unroll
         for (int k = 0; k < LI_IPT; k++) {
             Block b0;
+            if (!LOCKSTEP) contig(k);
             if (!tc_ok[k]) {
                 cd[k] = Cand{0, 0};
             } else if (lockstep) {
@@ -766,14 +771,11 @@ __global__ void __launch_bounds__(LI_TPB, LI_MIN_CTAS) lift_intervals_kernel(con
                         sink.thick[run64] = t;
                     }
                 }
-            } else if (nh[k] == 2 && T.disjoint) {  // an interval across one gap: by its thread, straight-line
-                Thick th{0, 0, 0};
-                if (THICK)
-                    th = lift_thick_from(T, ey, tc[k], __ldg(A.thick_s + q), __ldg(A.thick_e + q), st[k], cd[k].lo,
-                                         (cm_smem ? S.cmeta[tc[k]] : load_cmeta(T, tc[k])).y);
-                expand_pair<THICK>(A, sink, th, q, cd[k].lo, st[k], en[k], A.strand ? __ldg(A.strand + q) : 0, run64);
             } else if (nh[k] >= 2) {
-                pending |= 1u << k;  // expand_wide_kernel's list, or queued below over several rounds of the work list
+                // expand_wide_kernel's list, or queued below over several rounds of the work list.  (Expanding two-hit
+                // queries here, by their thread, was measured slower on unsorted batches — configs[2] 9.8 -> 11.3 ms:
+                // they are scattered, so nearly every warp runs the extra code for one or two of its lanes.)
+                pending |= 1u << k;
             }
             run64 += (uint64_t)nh[k];
         }
@@ -782,7 +784,7 @@ __global__ void __launch_bounds__(LI_TPB, LI_MIN_CTAS) lift_intervals_kernel(con
         // warp) and expanded by expand_wide_kernel, a warp per query with the rows coming straight from
         // registers: no work-list rounds and no block barriers in here, and the block's other warps do
         // not wait for the one with the heaviest query.
-        if (!defer && T.disjoint && A.wide_ent) {
+        if (!THICK && !defer && T.disjoint && A.wide_ent) {  // (batches with thick columns: see launch_lift_intervals)
             const uint32_t mine = (uint32_t)__popc(pending);
             const uint32_t inc = warp_inclusive_scan(mine);
             const uint32_t wtot = __shfl_sync(FULL, inc, 31);

@@ -47,6 +47,7 @@ namespace swo {
 
 constexpr int MG_XS = 128;     // per-warp sort scratch in shared memory (entries)
 constexpr int MG_GXS = 2048;   // per-warp sort scratch in global memory (entries)
+constexpr int MG_PAIRS = 256;  // expand_wide_kernel: candidates up to which all-pairs counting beats the bitonic sort
 constexpr int MG_QPW = 32 * LI_IPT;  // queries per warp pass ("tile")
 constexpr int MG_NW = 8;             // warps per CTA
 constexpr int MG_TPB = MG_NW * 32;
@@ -661,10 +662,17 @@ __global__ void __launch_bounds__(256, 4) expand_wide_kernel(const __grid_consta
         if (THICK) th.ts = (int)y0.x, th.te = (int)y0.y, th.has = (int)y0.z;
         if (!expand_warp_runs<THICK>(A, sink, th, v0.x, (int)v0.y, (int)v0.z, (uint64_t)v0.w, (int)x0.x, (int)x0.y, (unsigned char)x0.z,
                                      reinterpret_cast<int *>(xs[w]), b0)) {
-            if ((int)v0.z <= MG_GXS)
+            // what the run form declined: up to MG_PAIRS candidates every one counts the keys in front of it (n^2 / 32
+            // steps per lane, six instructions each); larger ones are sorted (bitonic, n log^2 n) in the warp's
+            // global scratch; beyond that scratch all pairs again, straight from the block table
+            if ((int)v0.z <= MG_PAIRS)
                 expand_warp_allpairs<THICK>(A, sink, th, v0.x, (int)v0.y, (int)v0.z, (uint64_t)v0.w, (int)x0.x, (int)x0.y, (unsigned char)x0.z, gxs);
-            else
+            else if ((int)v0.z <= MG_GXS) {
+                expand_query_coop<false, THICK>(A, sink, A.T.ey, v0.x, (int)v0.y, (int)v0.z, (uint64_t)v0.w, gxs, nullptr, lane, 32);
+                converge(A);
+            } else {
                 expand_query<THICK>(A, sink, A.T.ey, v0.x, (int)v0.y, (int)v0.z, (uint64_t)v0.w, lane, 32);
+            }
         }
         e += step;
         v0 = v1, x0 = x1, y0 = y1, b0 = b1;

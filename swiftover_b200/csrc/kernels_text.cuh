@@ -66,6 +66,12 @@ constexpr int TX_NSEG = TX_WIN / TX_MSEG;    // 273
 constexpr int TX_OUT_STAGE = TX_TILE / 4 * 5;       // lifted bytes staged per tile
 constexpr int TX_ROUND_SLACK = 4096;         // multi-round emit: a line's rows may run this far past its round's window
 constexpr int TX_UNM_STAGE = TX_TILE + TX_LOOK;  // unmatched bytes staged per tile: a tile's unmatched text never exceeds its input
+// One stage for both streams: the unmatched text (known size: the scan has run) sits at the end, the lifted
+// text may use everything in front of it — with few unmatched records a tile's lifted text may be up to
+// 2.2x its input before the tile has to go out in rounds (with two fixed stages, 20 + 17 KiB, BED8 input
+// whose output is 1.15x the input sent a good part of its tiles through the rounds: configs[2] text
+// 127 -> see DESIGN.md).  The rounds themselves use the first TX_OUT_STAGE bytes only.
+constexpr int TX_STAGE_ALL = TX_OUT_STAGE + TX_UNM_STAGE;
 constexpr int TX_LCAP = TX_TILE / 8;           // line-start table entries
 constexpr int TX_QN_MAX = 256;               // destination contig names kept in shared memory ...
 constexpr int TX_QCHARS = 3072;              // ... if their characters fit here
@@ -859,13 +865,14 @@ struct TileCtx {
 struct PendTile {
     int pend, have_base, direct_l, direct_u, tile;
     uint32_t tot_l, tot_u;
+    uint32_t u_off;  // byte offset of the unmatched text in the stage
     uint64_t gb_l, gb_u;
 };
 
 struct TextSmem {
     uint32_t in_words[(TX_WIN + TX_PAD) / 4];
-    uint32_t out_words[TX_OUT_STAGE / 4 + 8];
-    uint32_t unm_words[TX_UNM_STAGE / 4 + 8];
+    // the tile's output: lifted text from the front, unmatched text at the very end (see TX_STAGE_ALL)
+    uint32_t stage_words[TX_STAGE_ALL / 4 + 8];
     unsigned long long nlm[TX_NSEG + 1];
     int2 ey[TX_EY_CAP];
     union {  // the line table is dead once the emit phase is over, when the expansions run
@@ -1349,8 +1356,7 @@ __global__ void __launch_bounds__(TX_TPB, TX_MIN_CTAS) lift_bed_text_kernel(cons
     }
     const TableView &T = A.T;
     unsigned char *const win = reinterpret_cast<unsigned char *>(S.in_words);
-    char *const stage_l = reinterpret_cast<char *>(S.out_words);
-    char *const stage_u = reinterpret_cast<char *>(S.unm_words);
+    char *const stage_l = reinterpret_cast<char *>(S.stage_words);
 
     // upper search levels -> shared memory (once per persistent CTA)
     for (int i = tid; i < T.ey_n; i += TX_TPB) S.ey[i] = __ldg(T.ey + i);
@@ -1378,8 +1384,8 @@ __global__ void __launch_bounds__(TX_TPB, TX_MIN_CTAS) lift_bed_text_kernel(cons
             A.sizes[0] = gb_l + P.tot_l;
             A.sizes[1] = gb_u + P.tot_u;
         }
-        if (!P.direct_l && P.tot_l && gb_l + P.tot_l <= A.lifted_cap) copy_out(A.lifted + gb_l, S.out_words, P.tot_l);
-        if (!P.direct_u && P.tot_u && gb_u + P.tot_u <= A.unm_cap) copy_out(A.unm + gb_u, S.unm_words, P.tot_u);
+        if (!P.direct_l && P.tot_l && gb_l + P.tot_l <= A.lifted_cap) copy_out(A.lifted + gb_l, S.stage_words, P.tot_l);
+        if (!P.direct_u && P.tot_u && gb_u + P.tot_u <= A.unm_cap) copy_out(A.unm + gb_u, S.stage_words, P.tot_u, P.u_off);
         __syncthreads();  // the stages may be overwritten now
         if (tid == 0) P.pend = 0;
     };
@@ -1585,7 +1591,10 @@ __global__ void __launch_bounds__(TX_TPB, TX_MIN_CTAS) lift_bed_text_kernel(cons
         }
         // a stream that does not fit its stage is written straight to global memory,
         // which needs the chained offset before formatting
-        const bool direct_l = tot_l > TX_OUT_STAGE, direct_u = tot_u > TX_UNM_STAGE;
+        const bool direct_u = tot_u > TX_UNM_STAGE;
+        const uint32_t u_off = direct_u ? (uint32_t)TX_STAGE_ALL : (uint32_t)TX_STAGE_ALL - ((tot_u + 15u) & ~15u);  // >= TX_OUT_STAGE
+        const bool direct_l = tot_l > u_off;
+        char *const stage_u = stage_l + u_off;
         uint64_t gb_l = 0, gb_u = 0;
         bool have_base = false;
         flush();  // previous tile: resolve + copy out, frees the stages
@@ -1711,7 +1720,7 @@ __global__ void __launch_bounds__(TX_TPB, TX_MIN_CTAS) lift_bed_text_kernel(cons
                     // predecessors time to publish their aggregates
                     if (!have_base) resolve_now();
                     if (gb_l + tot_l <= A.lifted_cap)
-                        copy_out(A.lifted + gb_l + S.rlo, S.out_words, S.rhi - S.rlo, S.rlo - r0);
+                        copy_out(A.lifted + gb_l + S.rlo, S.stage_words, S.rhi - S.rlo, S.rlo - r0);
                     __syncthreads();
                 }
                 if (!have_base) resolve_now();
@@ -1742,6 +1751,7 @@ __global__ void __launch_bounds__(TX_TPB, TX_MIN_CTAS) lift_bed_text_kernel(cons
             P.tile = tile;
             P.tot_l = tot_l;
             P.tot_u = tot_u;
+            P.u_off = u_off;
             P.gb_l = gb_l;
             P.gb_u = gb_u;
         }

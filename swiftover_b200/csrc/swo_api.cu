@@ -330,12 +330,16 @@ int launch_lift_intervals(swo_ctx *c, Device &d, size_t n, const int32_t *tcid, 
     A.wide_cap = 0;
     if (merge_ok) {
         W.cap = (unsigned)std::min<size_t>(n, (size_t)32 << 20);
-        CK(c, d.wide.reserve((size_t)W.cap * (th ? 3 : 2) * sizeof(uint4)));
+        CK(c, d.wide.reserve((size_t)W.cap * 2 * sizeof(uint4)));
         W.ent = d.wide.as<uint4>();
         CK(c, d.gscr.reserve((size_t)W.gscr_ctas * MG_NW * MG_GXS * sizeof(unsigned long long)));
         A.gscr = d.gscr.as<unsigned long long>();
-        A.wide_ent = W.ent;
-        A.wide_cap = W.cap;
+        // (batches with thick columns keep their multi-hit queries inside lift_intervals_kernel: measured, BASELINE
+        // configs[2], 9.8 ms against 11.4 ms through the list — there the list's entries are rare and heavy)
+        if (!th) {
+            A.wide_ent = W.ent;
+            A.wide_cap = W.cap;
+        }
     }
     if (!th) {
         sample_sorted_kernel<<<1, 512, 0, st>>>(tcid, start, (uint32_t)n, flag, merge_ok ? 1u : 0u);
@@ -403,9 +407,8 @@ int launch_lift_intervals(swo_ctx *c, Device &d, size_t n, const int32_t *tcid, 
         CK(c, cudaLaunchKernel(fn, dim3(grid), dim3(LI_TPB), args, smem, st));
         c->launches++;
     }
-    if (merge_ok) {  // latency-bound (a block load per round of 32 rows): all the warps the SMs hold
-        if (th) expand_wide_kernel<true><<<d.sms * 8, 256, 0, st>>>(A, W);
-        else expand_wide_kernel<false><<<d.sms * 8, 256, 0, st>>>(A, W);
+    if (merge_ok && !th) {  // all the warps the SMs hold: a warp per listed query
+        expand_wide_kernel<false><<<d.sms * 8, 256, 0, st>>>(A, W);
         c->launches++;
     }
     CK(c, cudaGetLastError());
