@@ -258,7 +258,7 @@ __device__ __forceinline__ void warp_search(const TableView &T, const MergeSmem 
     const bool same = __all_sync(FULL, tc[0] == tc0 && tc[1] == tc0 && tc[2] == tc0 && tc[3] == tc0) && tc0 >= 0 && tc0 < T.ntc;
     if (same) {
         const int m01 = st[0] < st[1] ? st[0] : st[1], m23 = st[2] < st[3] ? st[2] : st[3];
-        const int smin = warp_min(m01 < m23 ? m01 : m23);
+        const int smin = __reduce_min_sync(FULL, m01 < m23 ? m01 : m23);  // (redux.sync: the warp is converged here, all loops are uniform)
         bool hit = C.tc == tc0 && smin >= C.before;  // (warp-uniform)
         if (hit && __all_sync(FULL, C.pmA <= smin)) {
             // the first half of the window lies in front of every query: slide by one group
@@ -440,12 +440,9 @@ __global__ void __launch_bounds__(MG_TPB, 4) merge_count_kernel(const __grid_con
             if (M.dbg && am != FULL) printf("tile %d lane %d: active mask %08x in front of the tile total\n", tile, lane, am);
         }
 #endif
-        // Shuffles, not redux.sync: behind the divergent per-thread search the warp can still be split here
-        // (ptxas 12.9 takes it for converged and even turns converge_warp into a NOP in this kernel), a
-        // SHFL then takes its out-of-line WARPSYNC.COLLECTIVE path, whereas REDUX.SUM silently sums the
-        // lanes that happen to be there (found by tools/fuzz_parity.py seed 771: one lane's rows missing
-        // from the tile total; profiles/r02_converge_experiments.md).
-        const uint32_t total = warp_sum(tsum);
+        // (redux.sync is safe again: no per-lane loop is left in front of it — an earlier version with a divergent
+        // per-thread search lost a lane's rows here, profiles/r02_converge_experiments.md)
+        const uint32_t total = __reduce_add_sync(FULL, tsum);
         if (lane == 0) M.total[tile] = total;
     }
     const uint32_t unm = warp_sum(unm_acc);
