@@ -363,32 +363,47 @@ def other_configs(cf, S, shard, torch, dev, rank, world, peak, args):
     kind = S.uniform01(20240004, 2, first, n4, dev)  # 80 % SNV, 10 % insertion (REF 1 base), 10 % deletion (REF 2-20)
     rl = torch.where(kind < 0.9, 1, 2 + torch.floor(S.uniform01(20240004, 3, first, n4, dev) * 19).to(torch.int64)).to(torch.int32)
     tc = tc.to(torch.int32)
-    ro = torch.cumsum(rl.to(torch.int64), 0) - rl
-    nref = int((ro[-1] + rl[-1]).item())
-    ref = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)[torch.randint(0, 4, (nref,), device=dev, generator=g)]
-    oq = torch.empty(n4, dtype=torch.int32, device=dev)
-    op, orl = torch.empty_like(oq), torch.empty_like(oq)
-    fl = torch.empty(n4, dtype=torch.uint8, device=dev)
-    oref = torch.empty_like(ref)
 
-    def vcf(refb):
-        rc = L.lib().swo_lift_vcf_points_dev(cf.handle, n4, tc.data_ptr(), pos.data_ptr(), rl.data_ptr(), ro.data_ptr(),
-                                             refb.data_ptr(), oq.data_ptr(), op.data_ptr(), fl.data_ptr(), orl.data_ptr(),
-                                             oref.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
-        assert rc == 0, L.lib().swo_last_error(cf.handle)
-    vcf(ref)  # REF := what the destination genome holds there (the "source genome" agrees with it) ...
-    torch.cuda.synchronize(dev)
-    ref2 = oref.clone()
-    differ = torch.arange(0, n4, 100, device=dev)  # ... except for a fixed 1 % of the records
-    ref2[ro[differ]] = torch.where(ref2[ro[differ]] == 65, 67, 65).to(torch.uint8)
-    ms = time_dev(torch, dev, lambda: vcf(ref2), reps=5)
-    matched, refchg = int((fl & 1).sum().item()), int(((fl >> 1) & 1).sum().item())
-    alg = n4 * (20 + 13 + 32) + 2 * nref
-    put("cfg4_vcf", {"workload": f"configs[3]: {args.n_cfg4} VCF records / {world} GPU(s) (80 % SNV, 10 % insertion, 10 % deletion "
-                                 "with REF 2-20 bases), point lift + REF check against a 0.78 GB 2-bit destination genome",
-                     "n_per_gpu": n4, "matched_rank0": matched, "refchg_rank0": refchg, "refchg_frac_of_matched": refchg / max(1, matched),
-                     "ms": ms, "algorithmic_bytes_per_gpu": alg, "bytes_note": "20 B in + 13 B out + REF bytes in and out + one "
-                     "32-byte genome sector per record (SURVEY.md 8d)", "kernel": "lift_vcf_points_kernel", "scaling": "strong"})
+    def vcf_case(tc, pos, rl, key, what):
+        """Kernel-only figure for one order of the records; returns what the host-array leg needs."""
+        ro = torch.cumsum(rl.to(torch.int64), 0) - rl
+        nref = int((ro[-1] + rl[-1]).item())
+        ref = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)[torch.randint(0, 4, (nref,), device=dev, generator=g)]
+        oq = torch.empty(n4, dtype=torch.int32, device=dev)
+        op, orl = torch.empty_like(oq), torch.empty_like(oq)
+        fl = torch.empty(n4, dtype=torch.uint8, device=dev)
+        oref = torch.empty_like(ref)
+
+        def vcf(refb):
+            rc = L.lib().swo_lift_vcf_points_dev(cf.handle, n4, tc.data_ptr(), pos.data_ptr(), rl.data_ptr(), ro.data_ptr(),
+                                                 refb.data_ptr(), oq.data_ptr(), op.data_ptr(), fl.data_ptr(), orl.data_ptr(),
+                                                 oref.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+            assert rc == 0, L.lib().swo_last_error(cf.handle)
+        vcf(ref)  # REF := what the destination genome holds there (the "source genome" agrees with it) ...
+        torch.cuda.synchronize(dev)
+        ref2 = oref.clone()
+        differ = torch.arange(0, n4, 100, device=dev)  # ... except for a fixed 1 % of the records
+        ref2[ro[differ]] = torch.where(ref2[ro[differ]] == 65, 67, 65).to(torch.uint8)
+        ms = time_dev(torch, dev, lambda: vcf(ref2), reps=5)
+        matched, refchg = int((fl & 1).sum().item()), int(((fl >> 1) & 1).sum().item())
+        gather = 32 if key == "cfg4_vcf" else 0
+        alg = n4 * (20 + 13 + gather) + 2 * nref + (0 if gather else n4 // 4)
+        put(key, {"workload": f"configs[3]: {args.n_cfg4} VCF records / {world} GPU(s) (80 % SNV, 10 % insertion, 10 % deletion "
+                              f"with REF 2-20 bases), {what}; point lift + REF check against a 0.78 GB 2-bit destination genome",
+                  "n_per_gpu": n4, "matched_rank0": matched, "refchg_rank0": refchg, "refchg_frac_of_matched": refchg / max(1, matched),
+                  "ms": ms, "algorithmic_bytes_per_gpu": alg,
+                  "bytes_note": ("20 B in + 13 B out + REF bytes in and out + one 32-byte genome sector per record (SURVEY.md 8d); the "
+                                 "DRAM moves 64 bytes per gathered sector: ncu 149 B/record, 3.8 TB/s" if gather else
+                                 "20 B in + 13 B out + REF bytes in and out + 2 bits of genome per record (the gather is sequential)"),
+                  "kernel": "lift_vcf_points_kernel", "scaling": "strong"})
+        return ro, nref, ref2, fl
+
+    # records in file order of a real VCF — sorted by (contig, position) — and, the worst case, in i.i.d. order
+    order = torch.sort(pos.to(torch.int64) + (tc.to(torch.int64) << 32)).indices
+    vcf_case(tc[order].contiguous(), pos[order].contiguous(), rl[order].contiguous(), "cfg4_vcf_sorted",
+             "sorted by (contig, position) as a VCF file is")
+    del order
+    ro, nref, ref2, fl = vcf_case(tc, pos, rl, "cfg4_vcf", "i.i.d. order (every record a random gather)")
     # the same records through the host-array call (swo_lift_vcf_points): pinned host arrays in, pinned host arrays out,
     # chunks pipelined over three streams inside the call
     pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t)
@@ -397,7 +412,7 @@ def other_configs(cf, S, shard, torch, dev, rank, world, peak, args):
     h_fl = torch.empty(n4, dtype=torch.uint8, pin_memory=True)
     h_oref = torch.empty(nref, dtype=torch.uint8, pin_memory=True)
     fl_dev = fl.clone()
-    del tc, pos, rl, ro, ref, ref2, oq, op, orl, fl, oref
+    del tc, pos, rl, ro, ref2, fl
     torch.cuda.empty_cache()
 
     def vcf_host():

@@ -363,7 +363,7 @@ int launch_lift_intervals(swo_ctx *c, Device &d, size_t n, const int32_t *tcid, 
                 int per = 0;
                 CK(c, cudaFuncSetAttribute(fw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, fw, MG_TPB, smem));
-                d.bin_grid[gw] = std::min(std::max(1, per), 3) * d.sms;  // (the global sort scratch has regions for 3 CTAs per SM)
+                d.bin_grid[gw] = std::min(std::max(1, per), 8) * d.sms;  // (the global sort scratch has regions for 8 CTAs per SM)
             }
             LiftArgs Aw = A;
             Aw.ntiles = ntw;
