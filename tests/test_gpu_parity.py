@@ -161,6 +161,34 @@ def test_binary_heavy_fanout(hg):
     assert_rows_equal(got, ref, ("row_offset", "qcid", "start", "end", "src", "strand"))
 
 
+@pytest.mark.parametrize("seed", range(3))
+def test_binary_many_interleaved_runs(oracle, seed):
+    """Multi-hit queries over hundreds of tiny chains ('+' and '-', destinations anywhere): their candidates form
+    far more than 32 monotone runs, many of them overlapping in the destination — expand_wide_kernel's run form
+    must decline them and the counting / sorting forms must give the reference's row order (bed.d:156-173), in
+    sorted batches (merge passes), unsorted ones (lift_intervals_kernel's list) and with thick columns."""
+    rng = np.random.default_rng(9100 + seed)
+    chain, tn = synth.random_chain(rng, n_chains=int(rng.choice([150, 400])), n_tcontigs=2, n_qcontigs=3, max_blocks=int(rng.choice([3, 8])))
+    cf, oc = pair(oracle, chain)
+    n = 5000
+    tc = rng.integers(0, len(cf.sourceContigs), n).astype(np.int32)
+    s = rng.integers(0, 120_000, n).astype(np.int32)
+    ln = rng.choice([40, 900, 6_000, 30_000, 90_000, 400_000], n, p=[0.2, 0.2, 0.2, 0.2, 0.15, 0.05])
+    e = (s + ln).astype(np.int32)
+    strand = rng.choice(np.frombuffer(b"+-.", np.uint8), n)
+    ts = (s + rng.integers(0, 3000, n)).astype(np.int32)
+    te = (ts + rng.integers(0, 3000, n)).astype(np.int32)
+    for order in (np.arange(n), np.lexsort((s, tc))):
+        a = [x[order] for x in (tc, s, e, strand, ts, te)]
+        ref3 = oc.lift_intervals(*a[:3])
+        assert np.diff(ref3["row_offset"].astype(np.int64)).max() > 256  # the counting and the sorting form are both exercised
+        assert_rows_equal(cf.lift_intervals(*a[:3]), ref3)
+        assert_rows_equal(cf.lift_intervals(*a[:4]), oc.lift_intervals(*a[:4]), ("row_offset", "qcid", "start", "end", "src", "strand"))
+        assert_rows_equal(cf.lift_intervals(*a), oc.lift_intervals(*a),
+                          ("row_offset", "qcid", "start", "end", "src", "strand", "thick_start", "thick_end"))
+    cf.close()
+
+
 def test_points(hg):
     cf, oc = hg
     rng = np.random.default_rng(5)
