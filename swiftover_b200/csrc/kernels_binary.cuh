@@ -14,16 +14,18 @@
 // aggregate is chained to its predecessors with a decoupled look-back resolved
 // block-wide (so the variable-length output needs no separate count and scan
 // passes: every input byte is read once and every output byte is written
-// once); then rows are stored in place.  Queries with >= 2 hits go to a
-// shared-memory work list, filled and expanded in rounds: a warp (or the whole
-// block for heavy fan-out) writes one sort key per candidate to shared memory,
-// sorts only if the keys are not already ascending, and stores every row at its
-// sorted position with the cumulative strand byte.
+// once); then rows are stored in place.  Queries with >= 2 hits: on a target-disjoint
+// table (every UCSC over.chain) and without thick columns they are appended to a global
+// list and expanded behind the kernel by expand_wide_kernel (kernels_merge.cuh), a warp
+// per query and without sorting (expand_warp_runs below: the candidates of one chain are
+// in qStart order already); otherwise they go to a shared-memory work list, filled and
+// expanded in rounds: a warp (or the whole block for heavy fan-out) writes one sort key
+// per candidate to shared memory, sorts only if the keys are not already ascending, and
+// stores every row at its sorted position with the cumulative strand byte.
 //
-// Sorted batches (DEFER variant): the tile's rows and row offsets are staged in
-// shared memory, its aggregate is published, and its look-back is resolved after
-// the CTA's NEXT tile has been searched (flush_pending) — predecessors have had a
-// whole search phase to publish, so the walk does not wait; copy-out is coalesced.
+// Sorted batches without thick columns take the merge kernels (kernels_merge.cuh) instead;
+// the DEFER variant of this kernel (rows staged in shared memory, look-back resolved one
+// tile later) is their predecessor and is no longer instantiated.
 // Every block barrier / warp collective behind the divergent per-thread work is
 // preceded by converge() (device_util.cuh: converge_warp).
 #pragma once
@@ -71,7 +73,6 @@ struct LiftArgs {
     unsigned long long *gscr;     // sorted variant: per-warp sort scratch in global memory (kernels_merge.cuh)
     // multi-hit queries left for expand_wide_kernel (kernels_merge.cuh), two uint4 per entry:
     // {query, first candidate block, candidates, row position} {start, end, strand byte, tcid}
-    // and a third one in batches with thick columns: {lifted thickStart, thickEnd, has, -}
     uint4 *wide_ent;              // null: expand inside the kernel
     unsigned *wide_count;         // appended so far (may run past wide_cap: those were expanded on the spot)
     unsigned wide_cap;
@@ -797,15 +798,9 @@ __global__ void __launch_bounds__(LI_TPB, LI_MIN_CTAS) lift_intervals_kernel(con
                 for (int k = 0; k < LI_IPT; k++) {
                     if ((pending >> k) & 1u) {
                         if (slot < A.wide_cap) {
-                            constexpr int STRIDE = THICK ? 3 : 2;
-                            uint4 *const ent = A.wide_ent + STRIDE * (size_t)slot;
+                            uint4 *const ent = A.wide_ent + 2 * (size_t)slot;
                             ent[0] = make_uint4(q0 + k, (unsigned)cd[k].lo, (unsigned)nh[k], (uint32_t)rb);
                             ent[1] = make_uint4((unsigned)st[k], (unsigned)en[k], A.strand ? __ldg(A.strand + q0 + k) : 0u, (unsigned)tc[k]);
-                            if (THICK) {
-                                const Thick th = lift_thick_from(T, ey, tc[k], __ldg(A.thick_s + q0 + k), __ldg(A.thick_e + q0 + k), st[k],
-                                                                 cd[k].lo, (cm_smem ? S.cmeta[tc[k]] : load_cmeta(T, tc[k])).y);
-                                ent[2] = make_uint4((unsigned)th.ts, (unsigned)th.te, (unsigned)th.has, 0u);
-                            }
                             pending &= ~(1u << k);
                         }
                         slot++;

@@ -17,25 +17,29 @@
 //     counts, for its four queries, the blocks with tEnd <= start (they lie before the query: lo)
 //     and the blocks with tStart < end (hi).  The loop ends as soon as no query reaches block j,
 //     i.e. after (blocks spanned by the warp's queries) + 1 rounds — 2 on BASELINE configs[1],
-//     where a block holds ~1,850 queries.  A query that runs past the window is finished by its
-//     thread (four lockstep gallops); a warp with several contigs (contig boundaries, the batch
-//     tail) takes the per-thread search of kernels_binary.cuh.  Any order inside the warp is fine.
+//     where a block holds ~1,850 queries.  A query that runs past the window is finished by the
+//     whole warp (32-ary rounds over the key arrays); a warp with several contigs (contig
+//     boundaries, the batch tail) merges contig by contig.  Any order inside the warp is fine.
+//   * The 64-block window stays in the warp's registers from tile to tile (struct Window): tiles are
+//     dealt in chunks (struct Deal), a warp's next tile is 1,024 queries further on and usually
+//     still inside the window, or one 32-block slide away — no search, no key loads.
 //   * Variable-length output, three launches (the count / scan / write scheme of the task's
-//     north star): merge_count_kernel stores every warp's row total and window position,
-//     scan_tiles_kernel{1,2} turn the totals into exclusive prefixes, merge_write_kernel repeats
-//     the merge from the stored window position (no search) and stores row offsets and rows at
-//     their final places.  The queries are read twice (24 instead of 12 bytes per query of DRAM
-//     traffic) — measured against single-pass forms of the same merge with a chained look-back
-//     (block tiles or warp tiles, tickets or a static deal, 1-3 tiles of deferral; all in this
-//     file's history) the two-pass form wins: there every tile's store waits for the slowest of
-//     the ~500-10,000 tiles in flight before it, a ticket held for anything but its own search
-//     starts a convoy, and the per-tile chain ticket -> load -> search -> publish -> resolve ->
-//     store leaves the SMs idle; here no warp ever waits for another.
+//     north star): merge_count_kernel stores every warp tile's row total, scan_tiles_kernel{1,2}
+//     turn the totals into exclusive prefixes, merge_write_kernel repeats the merge and stores row
+//     offsets and rows at their final places.  The queries are read twice (24 instead of 12 bytes
+//     per query of DRAM traffic) — measured against single-pass forms of the same merge with a
+//     chained look-back (block tiles or warp tiles, tickets or a static deal, 1-3 tiles of
+//     deferral; all in this file's history) the two-pass form wins: there every tile's store waits
+//     for the slowest of the ~500-10,000 tiles in flight before it, a ticket held for anything but
+//     its own search starts a convoy, and the per-tile chain ticket -> load -> search -> publish ->
+//     resolve -> store leaves the SMs idle; here no warp ever waits for another.
 //   * The first candidate's row is computed without branches for every query (four block loads in
 //     flight per lane) and kept for single-hit queries.  A query with two candidate blocks (an
 //     interval across one gap) is expanded by its own thread, straight-line.  Larger ones are
-//     appended to a list {query, first block, candidates, row position} and expanded by
-//     expand_wide_kernel, a warp per query (list full: by their warp, on the spot).
+//     appended to a list {query, first block, candidates, row position, start, end, strand} and
+//     expanded by expand_wide_kernel, a warp per query and without sorting (expand_warp_runs,
+//     kernels_binary.cuh; list full: by their warp, on the spot).  lift_intervals_kernel appends the
+//     multi-hit queries of unsorted batches to the same list.
 //   * Every loop of the merge kernels has a warp-uniform trip count (see merge_window for why).
 // Only for target-disjoint tables (every UCSC over.chain; the host sends other tables to the
 // per-query-search variant): candidates == hits, and pmaxKey[j] == tEnd[j].
@@ -650,7 +654,8 @@ __global__ void __launch_bounds__(256, 4) expand_wide_kernel(const __grid_consta
     const int w = warp_id();
     const RowSink sink{A.rows, A.thick, A.rows_cap};
     unsigned long long *const gxs = A.gscr + ((size_t)blockIdx.x * 8 + w) * MG_GXS;  // (the host sizes the scratch for this grid)
-    constexpr int STRIDE = THICK ? 3 : 2;  // entries of batches with thick columns carry the lifted thickStart/End
+    constexpr int STRIDE = THICK ? 3 : 2;  // (a THICK instantiation would read the lifted thickStart/End from a third uint4;
+                                           //  batches with thick columns expand inside lift_intervals_kernel for now)
     // Software pipeline, two entries deep: while entry e is expanded, entry e + 2 steps is on its way from the
     // list and the first-round blocks of entry e + 1 step from the table — the warp never waits for either.
     const unsigned step = gridDim.x * 8;

@@ -10,8 +10,9 @@
 //   rows sorted by qStart, strand table, thick clamp, joined by '\t'   bed.d:156-199
 //
 // ONE persistent kernel; every input byte is read from HBM once and every output
-// byte written once.  A tile is 16 KiB of text staged in shared memory with
-// 128-bit loads; a tile owns the lines that START inside it.
+// byte written once.  A tile is 16 KiB of text staged in shared memory by one
+// 1-D bulk copy (TMA, completion on an mbarrier); a tile owns the lines that
+// START inside it.
 //   1. line starts: word-wide (SWAR) newline masks of the staged window, block
 //      scan, table of line-start offsets in shared memory;
 //   2. count phase: lines are dealt to threads round-robin (up to TX_NB = 3 per
@@ -22,8 +23,9 @@
 //      inside one group), and computes the exact byte length of its output;
 //   3. one packed multi-scan places lifted and unmatched text of all lines of the
 //      tile; the tile totals are published to the decoupled look-back chains;
-//   4. emit phase: rows are formatted from the cached state into shared-memory
-//      stages holding the tile's whole output;
+//   4. emit phase: rows are formatted from the cached state into ONE shared-memory
+//      stage holding the tile's whole output (lifted text from the front, unmatched
+//      text at the end);
 //   5. the resolve of the chained offsets and the copy-out (aligned 128-bit
 //      stores) of a tile are deferred until the NEXT tile has been counted, so
 //      that the look-back never waits for a predecessor's formatting.
