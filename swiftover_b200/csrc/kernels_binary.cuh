@@ -49,6 +49,7 @@ constexpr int LI_NW = LI_TPB / 32;
 #define LI_WL_CAP_OVR 256
 #endif
 constexpr int LI_WL_CAP = LI_WL_CAP_OVR;      // multi-hit queries queued per tile
+constexpr int LI_SMALL = 8;        // = MG_SMALL (kernels_merge.cuh)
 constexpr int LI_HEAVY_MIN = 128;   // candidates above this: the whole block expands the query
 constexpr int LI_XSCR = 1024;       // shared-memory sort scratch (= LI_NW warp regions of LI_HEAVY_MIN)
 constexpr int LI_CM_CAP = 128;      // per-contig table entries kept in shared memory (more contigs: global loads)
@@ -76,6 +77,9 @@ struct LiftArgs {
     uint4 *wide_ent;              // null: expand inside the kernel
     unsigned *wide_count;         // appended so far (may run past wide_cap: those were expanded on the spot)
     unsigned wide_cap;
+    uint4 *small_ent;             // the same for queries with at most LI_SMALL candidates (expand_small_kernel)
+    unsigned *small_count;
+    unsigned small_cap;
 };
 
 // see converge_warp (device_util.cuh)
@@ -786,24 +790,36 @@ __global__ void __launch_bounds__(LI_TPB, LI_MIN_CTAS) lift_intervals_kernel(con
         // registers: no work-list rounds and no block barriers in here, and the block's other warps do
         // not wait for the one with the heaviest query.
         if (!THICK && !defer && T.disjoint && A.wide_ent) {  // (batches with thick columns: see launch_lift_intervals)
-            const uint32_t mine = (uint32_t)__popc(pending);
+            unsigned small = 0;  // queries with at most LI_SMALL candidates go to the list of expand_small_kernel
+#pragma unroll
+            for (int k = 0; k < LI_IPT; k++)
+                if (((pending >> k) & 1u) && nh[k] <= LI_SMALL) small |= 1u << k;
+            // (both counts in one scan: big in the low, small in the high half)
+            const uint32_t mine = (uint32_t)__popc(pending & ~small) | ((uint32_t)__popc(small) << 16);
             const uint32_t inc = warp_inclusive_scan(mine);
             const uint32_t wtot = __shfl_sync(FULL, inc, 31);
             if (wtot) {  // warp-uniform
-                unsigned slot = 0;
-                if (lane_id() == 0) slot = atomicAdd(A.wide_count, wtot);
-                slot = __shfl_sync(FULL, slot, 0) + inc - mine;
+                unsigned slot_b = 0, slot_s = 0;
+                if (lane_id() == 0) {
+                    if (wtot & 0xFFFFu) slot_b = atomicAdd(A.wide_count, wtot & 0xFFFFu);
+                    if (wtot >> 16) slot_s = atomicAdd(A.small_count, wtot >> 16);
+                }
+                slot_b = __shfl_sync(FULL, slot_b, 0) + ((inc - mine) & 0xFFFFu);
+                slot_s = __shfl_sync(FULL, slot_s, 0) + ((inc - mine) >> 16);
                 uint64_t rb = gbase + excl;
 #pragma unroll
                 for (int k = 0; k < LI_IPT; k++) {
                     if ((pending >> k) & 1u) {
-                        if (slot < A.wide_cap) {
-                            uint4 *const ent = A.wide_ent + 2 * (size_t)slot;
+                        const bool sm = (small >> k) & 1u;
+                        const unsigned slot = sm ? slot_s : slot_b;
+                        if (slot < (sm ? A.small_cap : A.wide_cap)) {
+                            uint4 *const ent = (sm ? A.small_ent : A.wide_ent) + 2 * (size_t)slot;
                             ent[0] = make_uint4(q0 + k, (unsigned)cd[k].lo, (unsigned)nh[k], (uint32_t)rb);
                             ent[1] = make_uint4((unsigned)st[k], (unsigned)en[k], A.strand ? __ldg(A.strand + q0 + k) : 0u, (unsigned)tc[k]);
                             pending &= ~(1u << k);
                         }
-                        slot++;
+                        if (sm) slot_s++;
+                        else slot_b++;
                     }
                     rb += (uint64_t)nh[k];
                 }

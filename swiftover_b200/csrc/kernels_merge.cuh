@@ -51,6 +51,7 @@ namespace swo {
 
 constexpr int MG_XS = 128;     // per-warp sort scratch in shared memory (entries)
 constexpr int MG_GXS = 2048;   // per-warp sort scratch in global memory (entries)
+constexpr int MG_SMALL = 8;    // candidates up to which a listed query is expanded by eight lanes (expand_small_kernel)
 constexpr int MG_PAIRS = 256;  // expand_wide_kernel: candidates up to which all-pairs counting beats the bitonic sort
 constexpr int MG_QPW = 32 * LI_IPT;  // queries per warp pass ("tile")
 constexpr int MG_NW = 8;             // warps per CTA
@@ -65,6 +66,10 @@ struct WideList {
     unsigned *count;  // appended so far (may run past cap: those were expanded on the spot)
     uint4 *ent;       // two per entry: {query, first block, candidates, row position} {start, end, strand byte, -}
     unsigned cap;
+    // the same for queries with at most MG_SMALL candidates (expand_small_kernel: eight lanes per query)
+    unsigned *count_small;
+    uint4 *ent_small;
+    unsigned cap_small;
     unsigned gscr_ctas;  // CTAs of expand_wide_kernel that own a region of the global sort scratch
 };
 // per warp tile, between the passes
@@ -613,10 +618,12 @@ __global__ void __launch_bounds__(MG_TPB, MG_WRITE_CTAS) merge_write_kernel(cons
                     if (cnt[k] == 2) {
                         expand_pair<false>(A, sink, Thick{0, 0, 0}, q0 + k, lo[k], st[k], en[k], sbk[k], p);
                     } else {
-                        const unsigned e = atomicAdd(W.count, 1u);
-                        if (e < W.cap) {
-                            W.ent[2 * e] = make_uint4(q0 + k, (unsigned)lo[k], (unsigned)cnt[k], (uint32_t)p);
-                            W.ent[2 * e + 1] = make_uint4((unsigned)st[k], (unsigned)en[k], sbk[k], (unsigned)tc[k]);
+                        const bool small = cnt[k] <= MG_SMALL;
+                        const unsigned e = atomicAdd(small ? W.count_small : W.count, 1u);
+                        if (e < (small ? W.cap_small : W.cap)) {
+                            uint4 *const ent = (small ? W.ent_small : W.ent) + 2 * (size_t)e;
+                            ent[0] = make_uint4(q0 + k, (unsigned)lo[k], (unsigned)cnt[k], (uint32_t)p);
+                            ent[1] = make_uint4((unsigned)st[k], (unsigned)en[k], sbk[k], (unsigned)tc[k]);
                         }
                         else wide |= 1u << k;
                     }
@@ -639,6 +646,41 @@ __global__ void __launch_bounds__(MG_TPB, MG_WRITE_CTAS) merge_write_kernel(cons
                     p += (uint64_t)cnt[k];
                 }
             }
+        }
+    }
+}
+
+// Listed queries with 3..MG_SMALL candidates — three quarters of all multi-hit queries on hg19ToHg38 — by EIGHT lanes
+// each, four queries per warp: a lane per candidate, every candidate counts the keys in front of its own (eight
+// width-8 shuffles: no runs, no scratch, any order), the cumulative strand byte from the inverted rows among them.
+// The loop is warp-uniform: a group whose entry index is past the list's end carries an empty query.
+__global__ void __launch_bounds__(256) expand_small_kernel(const __grid_constant__ LiftArgs A, const __grid_constant__ WideList W) {
+    const TableView &T = A.T;
+    const unsigned n = min(*W.count_small, W.cap_small);
+    const int lane = lane_id(), g = lane & 7, gshift = lane & ~7;
+    const unsigned step = gridDim.x * 32u;
+    for (unsigned e0 = (blockIdx.x * 8u + (unsigned)warp_id()) * 4u; e0 < n; e0 += step) {
+        const unsigned e = e0 + (unsigned)(lane >> 3);
+        uint4 v = make_uint4(0, 0, 0, 0), x = v;
+        if (e < n) v = __ldg(W.ent_small + 2 * (size_t)e), x = __ldg(W.ent_small + 2 * (size_t)e + 1);
+        const int cnt = (int)v.z, start = (int)x.x, end = (int)x.y;
+        const bool valid = g < cnt;
+        const RowCore row = make_row(load_block(T, (int)v.y + (valid ? g : 0)), start, end);
+        const unsigned invb = (__ballot_sync(FULL, valid && row.inv < 0) >> gshift) & 0xFFu;
+        int rank = 0, negs = valid && row.inv < 0 ? 1 : 0;
+#pragma unroll
+        for (int l = 0; l < MG_SMALL; l++) {
+            const int k = __shfl_sync(FULL, row.key, l, 8);
+            const int before = (l < cnt && (k < row.key || (k == row.key && l < g))) ? 1 : 0;
+            rank += before;
+            negs += before & (int)((invb >> l) & 1u);
+        }
+        const unsigned m0 = (__ballot_sync(FULL, valid && rank == 0) >> gshift) & 0xFFu;
+        const int inv_first = __shfl_sync(FULL, row.inv, m0 ? __ffs(m0) - 1 : 0, 8);
+        const uint64_t pos = (uint64_t)v.w + (uint64_t)rank;
+        if (valid && pos < A.rows_cap) {
+            const unsigned char sb = A.strand ? strand_at_rank((unsigned char)x.z, inv_first, rank, negs) : 0;
+            *reinterpret_cast<int4 *>(A.rows + pos) = make_int4(row.qcid | ((int)sb << 16), row.s, row.e, (int)v.x);
         }
     }
 }

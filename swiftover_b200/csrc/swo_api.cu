@@ -273,7 +273,7 @@ int launch_lift_intervals(swo_ctx *c, Device &d, size_t n, const int32_t *tcid, 
                           uint32_t *row_offset, swo_row *rows, swo_thick *thick, size_t rows_cap, uint64_t *totals,
                           cudaStream_t st) {
     const int ntiles = (int)((n + LI_TILE - 1) / LI_TILE);
-    // scratch: [ticket, wide-list count, sorted flag, -] [ntiles tile descriptors (per-query-search variants)]
+    // scratch: [ticket, wide-list count, sorted flag, small-list count] [ntiles tile descriptors (per-query-search variants)]
     // sorted variant (count / scan / write over warp tiles of MG_QPW queries): [ntw totals] [nsum sums]
     const int ntw = (int)((n + MG_QPW - 1) / MG_QPW), nsum = (ntw + MG_SCAN_TILE - 1) / MG_SCAN_TILE;
     const size_t w_total = (16 + (size_t)ntiles * 8 + 15) & ~(size_t)15;
@@ -324,14 +324,22 @@ int launch_lift_intervals(swo_ctx *c, Device &d, size_t n, const int32_t *tcid, 
     W.ent = nullptr;
     W.count = reinterpret_cast<unsigned *>(d.scratch.as<char>() + 4);
     W.cap = 0;
+    W.count_small = reinterpret_cast<unsigned *>(d.scratch.as<char>() + 12);
+    W.ent_small = nullptr;
+    W.cap_small = 0;
     W.gscr_ctas = (unsigned)std::max(1, d.sms * 8);  // every CTA of expand_wide_kernel (and of merge_write_kernel) owns a region
     A.wide_ent = nullptr;
     A.wide_count = W.count;
     A.wide_cap = 0;
+    A.small_ent = nullptr;
+    A.small_count = W.count_small;
+    A.small_cap = 0;
     if (merge_ok) {
         W.cap = (unsigned)std::min<size_t>(n, (size_t)32 << 20);
-        CK(c, d.wide.reserve((size_t)W.cap * 2 * sizeof(uint4)));
+        W.cap_small = (unsigned)std::min<size_t>(n, (size_t)16 << 20);
+        CK(c, d.wide.reserve(((size_t)W.cap + W.cap_small) * 2 * sizeof(uint4)));
         W.ent = d.wide.as<uint4>();
+        W.ent_small = W.ent + 2 * (size_t)W.cap;
         CK(c, d.gscr.reserve((size_t)W.gscr_ctas * MG_NW * MG_GXS * sizeof(unsigned long long)));
         A.gscr = d.gscr.as<unsigned long long>();
         // (batches with thick columns keep their multi-hit queries inside lift_intervals_kernel: measured, BASELINE
@@ -339,6 +347,8 @@ int launch_lift_intervals(swo_ctx *c, Device &d, size_t n, const int32_t *tcid, 
         if (!th) {
             A.wide_ent = W.ent;
             A.wide_cap = W.cap;
+            A.small_ent = W.ent_small;
+            A.small_cap = W.cap_small;
         }
     }
     if (!th) {
@@ -408,8 +418,9 @@ int launch_lift_intervals(swo_ctx *c, Device &d, size_t n, const int32_t *tcid, 
         c->launches++;
     }
     if (merge_ok && !th) {  // all the warps the SMs hold: a warp per listed query
+        expand_small_kernel<<<d.sms * 8, 256, 0, st>>>(A, W);
         expand_wide_kernel<false><<<d.sms * 8, 256, 0, st>>>(A, W);
-        c->launches++;
+        c->launches += 2;
     }
     CK(c, cudaGetLastError());
     CK(c, cudaEventRecord(d.ev_scratch, st));
