@@ -75,6 +75,11 @@ struct WideList {
 // per warp tile, between the passes
 struct MergeTiles {
     uint32_t *total;          // [ntw] rows of the tile; after the scan: exclusive prefix inside its scan tile
+    // What the count pass found, for the write pass: per query one byte {first candidate block - lo0 of its tile,
+    // candidates << 4}, a nibble of 15 = "does not fit, merge this tile again"; the write pass then needs neither
+    // the contig column nor the merge (it reads 9 instead of 12 bytes per query and goes straight to the blocks).
+    uint32_t *packed;         // [ntw * 32] the four bytes of a lane's queries
+    int32_t *lo0;             // [ntw]
     unsigned long long *sum;  // [ntw / MG_SCAN_TILE + 1] rows per scan tile; after the scan: exclusive prefix
 #ifdef MG_DEBUG_COUNTS
     int32_t *dbg;             // [4 * n]: per query {lo, hi, path, -} as the count pass saw them
@@ -270,7 +275,7 @@ __device__ __forceinline__ int find_window(const TableView &T, const MergeSmem &
 }
 
 // Candidate block ranges [lo, hi) of the lane's four queries.  C: the warp's window from its previous tile.
-__device__ __forceinline__ void warp_search(const TableView &T, const MergeSmem &S, bool cm_smem, Window &C, const int (&tc)[LI_IPT],
+__device__ __forceinline__ bool warp_search(const TableView &T, const MergeSmem &S, bool cm_smem, Window &C, const int (&tc)[LI_IPT],
                                             const int (&st)[LI_IPT], const int (&en)[LI_IPT], int (&lo)[LI_IPT], int (&hi)[LI_IPT]) {
     const int tc0 = __shfl_sync(FULL, tc[0], 0);
     const bool same = __all_sync(FULL, tc[0] == tc0 && tc[1] == tc0 && tc[2] == tc0 && tc[3] == tc0) && tc0 >= 0 && tc0 < T.ntc;
@@ -296,7 +301,7 @@ __device__ __forceinline__ void warp_search(const TableView &T, const MergeSmem 
             window_load_half(T, C.wb + 32, C.cend, C.pmB, C.tsB);
         }
         merge_window(T, C, smin, 0xFu, st, en, lo, hi);
-        return;
+        return true;
     }
     // Several contigs in the tile (contig boundaries, the batch tail, unsorted stretches): one round of
     // the same merge per distinct contig, smallest id first; queries of other contigs sit the round out.
@@ -332,6 +337,7 @@ __device__ __forceinline__ void warp_search(const TableView &T, const MergeSmem 
         window_load_half(T, W.wb + 32, W.cend, W.pmB, W.tsB);
         merge_window(T, W, smin, act, st, en, lo, hi);
     }
+    return false;
 }
 
 // A warp's queries come through shared memory: lane 0 arms the stage's mbarrier and issues three
@@ -357,18 +363,16 @@ struct QueryStager {
     __device__ void issue(int tile, int st) {
         if (lane == 0 && whole(tile)) {
             fence_proxy_async();
-            mbar_expect_tx(&S.qbar[w][st], 3u * MG_QPW * 4u);
-            bulk_g2s(S.q[w][st][0], A.tcid + (size_t)tile * MG_QPW, MG_QPW * 4u, &S.qbar[w][st]);
+            mbar_expect_tx(&S.qbar[w][st], 2u * MG_QPW * 4u);
             bulk_g2s(S.q[w][st][1], A.start + (size_t)tile * MG_QPW, MG_QPW * 4u, &S.qbar[w][st]);
             bulk_g2s(S.q[w][st][2], A.end + (size_t)tile * MG_QPW, MG_QPW * 4u, &S.qbar[w][st]);
         }
     }
-    __device__ void fetch(int tile, int st, int (&tc)[LI_IPT], int (&sta)[LI_IPT], int (&en)[LI_IPT]) {
+    __device__ void fetch(int tile, int st, int (&sta)[LI_IPT], int (&en)[LI_IPT]) {
         if (whole(tile)) {
             mbar_wait(&S.qbar[w][st], uses[st] & 1u);
             uses[st]++;
-            const int4 a = S.q[w][st][0][lane], b = S.q[w][st][1][lane], c = S.q[w][st][2][lane];
-            tc[0] = a.x, tc[1] = a.y, tc[2] = a.z, tc[3] = a.w;
+            const int4 b = S.q[w][st][1][lane], c = S.q[w][st][2][lane];
             sta[0] = b.x, sta[1] = b.y, sta[2] = b.z, sta[3] = b.w;
             en[0] = c.x, en[1] = c.y, en[2] = c.z, en[3] = c.w;
         } else {
@@ -376,7 +380,6 @@ struct QueryStager {
 #pragma unroll
             for (int k = 0; k < LI_IPT; k++) {
                 const bool ok = q0 + k < A.n;
-                tc[k] = ok ? A.tcid[q0 + k] : -1;
                 sta[k] = ok ? A.start[q0 + k] : 0;
                 en[k] = ok ? A.end[q0 + k] : 0;
             }
@@ -437,13 +440,17 @@ __global__ void __launch_bounds__(MG_TPB, 4) merge_count_kernel(const __grid_con
             const uint32_t pt = (uint32_t)dl.next().next().tile;
             if (lane < 12 && (pt + 1u) * MG_QPW <= A.n) prefetch_l2(pf_base + (size_t)pt * MG_QPW);
         }
-        warp_search(T, S, cm_smem, C, tc, st, en, lo, hi);
-        uint32_t tsum = 0;
+        const bool one = warp_search(T, S, cm_smem, C, tc, st, en, lo, hi);
+        const int m01 = lo[0] < lo[1] ? lo[0] : lo[1], m23 = lo[2] < lo[3] ? lo[2] : lo[3];
+        const int lo0 = __reduce_min_sync(FULL, m01 < m23 ? m01 : m23);
+        uint32_t tsum = 0, pk = 0;
 #pragma unroll
         for (int k = 0; k < LI_IPT; k++) {
             const int cnt = hi[k] > lo[k] ? hi[k] - lo[k] : 0;
             tsum += (uint32_t)cnt;
             unm_acc += cnt == 0 ? 1u : 0u;  // (the empty slots behind the batch's end are taken off below)
+            const uint32_t d = (uint32_t)(lo[k] - lo0);
+            pk |= ((d < 15u ? d : 15u) | ((uint32_t)(cnt < 15 ? cnt : 15) << 4)) << (8 * k);
 #ifdef MG_DEBUG_COUNTS
             if (M.dbg && q0 + k < A.n) {
                 M.dbg[4 * (size_t)(q0 + k)] = lo[k];
@@ -462,7 +469,11 @@ __global__ void __launch_bounds__(MG_TPB, 4) merge_count_kernel(const __grid_con
         // (redux.sync is safe again: no per-lane loop is left in front of it — an earlier version with a divergent
         // per-thread search lost a lane's rows here, profiles/r02_converge_experiments.md)
         const uint32_t total = __reduce_add_sync(FULL, tsum);
-        if (lane == 0) M.total[tile] = total;
+        M.packed[(size_t)tile * 32 + lane] = one ? pk : 0xFFFFFFFFu;  // several contigs: the write pass merges again
+        if (lane == 0) {
+            M.total[tile] = total;
+            M.lo0[tile] = lo0;
+        }
     }
     uint32_t unm = warp_sum(unm_acc);
     if (lane == 0 && unm) {
@@ -549,11 +560,14 @@ __global__ void __launch_bounds__(MG_TPB, MG_WRITE_CTAS) merge_write_kernel(cons
         const int tile = dl.tile;
         const uint32_t q0 = (uint32_t)tile * MG_QPW + (uint32_t)lane * LI_IPT;
         const bool full = (uint32_t)(tile + 1) * MG_QPW <= A.n;
-        int tc[LI_IPT], st[LI_IPT], en[LI_IPT], lo[LI_IPT], hi[LI_IPT];
+        int st[LI_IPT], en[LI_IPT], lo[LI_IPT], cnt[LI_IPT];
         __syncwarp();
         if (dl.next().tile < A.ntiles) Q.issue(dl.next().tile, stage ^ 1);
-        Q.fetch(tile, stage, tc, st, en);
+        // what the count pass found for this tile (and, further down, the blocks) before the queries are needed
+        const uint32_t pk = __ldg(M.packed + (size_t)tile * 32 + lane);
+        const int lo0 = __ldg(M.lo0 + tile);
         const uint64_t tbase = M.sum[tile / MG_SCAN_TILE] + (uint64_t)M.total[tile];
+        Q.fetch(tile, stage, st, en);
         uchar4 sb4 = make_uchar4(0, 0, 0, 0);
         if (STRAND) {
             if (full) sb4 = __ldg(reinterpret_cast<const uchar4 *>(A.strand + q0));
@@ -564,20 +578,32 @@ __global__ void __launch_bounds__(MG_TPB, MG_WRITE_CTAS) merge_write_kernel(cons
                 sb4.w = q0 + 3 < A.n ? A.strand[q0 + 3] : 0;
             }
         }
-        warp_search(T, S, cm_smem, C, tc, st, en, lo, hi);
+        // a nibble of 15 anywhere in the tile: a delta or a count did not fit (or the tile has several contigs) —
+        // the whole warp merges this tile again (warp-uniform)
+        const uint32_t esc = (((pk & 0x0F0F0F0Fu) + 0x01010101u) | (((pk >> 4) & 0x0F0F0F0Fu) + 0x01010101u)) & 0x10101010u;
+        if (__any_sync(FULL, esc != 0u)) {
+            int tc[LI_IPT], hi[LI_IPT];
+#pragma unroll
+            for (int k = 0; k < LI_IPT; k++) tc[k] = q0 + k < A.n ? __ldg(A.tcid + q0 + k) : -1;
+            warp_search(T, S, cm_smem, C, tc, st, en, lo, hi);
+#pragma unroll
+            for (int k = 0; k < LI_IPT; k++) cnt[k] = hi[k] > lo[k] ? hi[k] - lo[k] : 0;
+        } else {
+#pragma unroll
+            for (int k = 0; k < LI_IPT; k++) {
+                lo[k] = lo0 + (int)((pk >> (8 * k)) & 15u);
+                cnt[k] = (int)((pk >> (8 * k + 4)) & 15u);
+            }
+        }
         // Hits, and the row of the first candidate — computed without branches for every query (four
         // independent block loads in flight); it is only stored for single-hit queries.
         Block bk[LI_IPT];
 #pragma unroll
         for (int k = 0; k < LI_IPT; k++) bk[k] = load_block(T, lo[k] < last_block ? lo[k] : last_block);
         const unsigned char sbk[LI_IPT] = {sb4.x, sb4.y, sb4.z, sb4.w};
-        int cnt[LI_IPT];
         uint32_t tsum = 0;
 #pragma unroll
-        for (int k = 0; k < LI_IPT; k++) {
-            cnt[k] = hi[k] > lo[k] ? hi[k] - lo[k] : 0;
-            tsum += (uint32_t)cnt[k];
-        }
+        for (int k = 0; k < LI_IPT; k++) tsum += (uint32_t)cnt[k];
         const uint32_t inc = warp_inclusive_scan(tsum);
         const uint64_t pos64 = tbase + (inc - tsum);
         uint32_t pos = (uint32_t)pos64;  // row indices are 32-bit (the host rejects batches with 2^32 rows or more)
@@ -623,7 +649,7 @@ __global__ void __launch_bounds__(MG_TPB, MG_WRITE_CTAS) merge_write_kernel(cons
                         if (e < (small ? W.cap_small : W.cap)) {
                             uint4 *const ent = (small ? W.ent_small : W.ent) + 2 * (size_t)e;
                             ent[0] = make_uint4(q0 + k, (unsigned)lo[k], (unsigned)cnt[k], (uint32_t)p);
-                            ent[1] = make_uint4((unsigned)st[k], (unsigned)en[k], sbk[k], (unsigned)tc[k]);
+                            ent[1] = make_uint4((unsigned)st[k], (unsigned)en[k], sbk[k], 0u);
                         }
                         else wide |= 1u << k;
                     }

@@ -274,11 +274,12 @@ int launch_lift_intervals(swo_ctx *c, Device &d, size_t n, const int32_t *tcid, 
                           cudaStream_t st) {
     const int ntiles = (int)((n + LI_TILE - 1) / LI_TILE);
     // scratch: [ticket, wide-list count, sorted flag, small-list count] [ntiles tile descriptors (per-query-search variants)]
-    // sorted variant (count / scan / write over warp tiles of MG_QPW queries): [ntw totals] [nsum sums]
+    // sorted variant (count / scan / write over warp tiles of MG_QPW queries): [ntw totals] [nsum sums] [ntw lo0] [ntw x 32 packed words]
     const int ntw = (int)((n + MG_QPW - 1) / MG_QPW), nsum = (ntw + MG_SCAN_TILE - 1) / MG_SCAN_TILE;
     const size_t w_total = (16 + (size_t)ntiles * 8 + 15) & ~(size_t)15;
     const size_t w_sum = (w_total + (size_t)ntw * 4 + 15) & ~(size_t)15;
-    const size_t scratch_bytes = w_sum + (size_t)(nsum + 1) * 8;
+    const size_t w_lo0 = (w_sum + (size_t)(nsum + 1) * 8 + 15) & ~(size_t)15, w_packed = (w_lo0 + (size_t)ntw * 4 + 15) & ~(size_t)15;
+    const size_t scratch_bytes = w_packed + (size_t)ntw * 32 * 4;  // (one byte per query between the two passes)
     const size_t zero_bytes = w_total;  // header + tile descriptors; the sorted variant's arrays are written before they are read
     if (d.scratch_used) CK(c, cudaStreamWaitEvent(st, d.ev_scratch, 0));
     CK(c, d.scratch.reserve((scratch_bytes + 3) & ~(size_t)3));
@@ -306,6 +307,8 @@ int launch_lift_intervals(swo_ctx *c, Device &d, size_t n, const int32_t *tcid, 
     MergeTiles M;
     M.total = reinterpret_cast<uint32_t *>(d.scratch.as<char>() + w_total);
     M.sum = reinterpret_cast<unsigned long long *>(d.scratch.as<char>() + w_sum);
+    M.lo0 = reinterpret_cast<int32_t *>(d.scratch.as<char>() + w_lo0);
+    M.packed = reinterpret_cast<uint32_t *>(d.scratch.as<char>() + w_packed);
     A.gscr = nullptr;
     A.totals = totals;
     // sortedness sample -> flag word in the scratch header; both variants of the kernel
