@@ -862,7 +862,7 @@ int swo_lift_intervals_dev(swo_ctx *c, size_t n, const int32_t *d_tcid, const in
     if (!c) return SWO_E_ARG;
     if (c->dev.empty()) return fail(c, SWO_E_CUDA, "inspection-only context: no CUDA device, and there is no CPU fallback");
     if (!c->have_chain) return fail(c, SWO_E_STATE, "no chain loaded");
-    if (n >= 0xFFFFFFFFull) return fail(c, SWO_E_ARG, "n must be < 2^32-1 per call");
+    if (n > 0xFFFFF000ull) return fail(c, SWO_E_ARG, "n must be at most 2^32 - 4096 per call");  // (tile index arithmetic is 32-bit)
     if ((d_ths == nullptr) != (d_the == nullptr) || (d_ths && !d_thick)) return fail(c, SWO_E_ARG, "thick arrays");
     if (!aligned16(d_tcid) || !aligned16(d_start) || !aligned16(d_end) || !aligned16(d_row_offset) ||
         !aligned16(d_rows))
@@ -879,7 +879,7 @@ int swo_lift_intervals(swo_ctx *c, size_t n, const int32_t *tcid, const int32_t 
     memset(out, 0, sizeof *out);
     if (c->dev.empty()) return fail(c, SWO_E_CUDA, "inspection-only context: no CUDA device, and there is no CPU fallback");
     if (!c->have_chain) return fail(c, SWO_E_STATE, "no chain loaded");
-    if (n >= 0xFFFFFFFFull) return fail(c, SWO_E_ARG, "n must be < 2^32-1 per call");
+    if (n > 0xFFFFF000ull) return fail(c, SWO_E_ARG, "n must be at most 2^32 - 4096 per call");  // (tile index arithmetic is 32-bit)
     if ((ths == nullptr) != (the == nullptr)) return fail(c, SWO_E_ARG, "thick_start and thick_end go together");
     Device &d = c->dev[0];
     CK(c, cudaSetDevice(d.ordinal));
